@@ -1,0 +1,158 @@
+/* ma_b200.h — C-ABI of libma_b200.so, the CUDA (sm_100a) engine behind the MongeAmpere++ API.
+ *
+ * The reference has no FFI: its API is the header templates in include/MA.
+ * The drop-in headers in this repo's include/MA/ keep those templates' names and argument order
+ * and forward to the entry points below.  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference checkout).
+ *
+ * Conventions: plain pointers and sizes only; host buffers are caller-owned, device buffers are
+ * library-owned; every call blocks until its results are in the caller's buffers; one context
+ * per host thread and per GPU.  All reals are IEEE fp64, all indices int32.
+ * Every function returns an MA_* status; ma_last_error() gives the message for the last failure.
+ * There is no CPU fallback: without a CUDA device ma_create() fails with MA_CUDA_ERROR.
+ */
+#ifndef MA_B200_H
+#define MA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ma_ctx ma_ctx;
+
+enum {
+  MA_OK = 0,
+  MA_EMPTY_CELL = 1,        /* optimal_transport.hpp:139-148: a Laguerre cell is empty at the initial point */
+  MA_SINGULAR_HESSIAN = 2,  /* optimal_transport.hpp:49-58: zero on the Hessian diagonal */
+  MA_LINSOLVE_RESIDUAL = 3, /* optimal_transport.hpp:68-71: linear solve residual above 1e-7 */
+  MA_CUDA_ERROR = 4,
+  MA_INVALID = 5,           /* bad argument / call order (the reference's shape asserts, kantorovich.hpp:60-62) */
+  MA_NOT_CONVERGED = 6      /* Newton loop hit maxiter (optimal_transport.hpp:150-151) */
+};
+
+/* ---- context ---------------------------------------------------------------------------- */
+int ma_create(ma_ctx **out, int device);
+void ma_destroy(ma_ctx *ctx);
+const char *ma_last_error(const ma_ctx *ctx);
+/* ABI version, bumped on any signature change. */
+int ma_abi_version(void);
+
+/* ---- source density: a triangulation with one linear function per face --------------------
+ * Replaces the (T densityT, Functions densityF) pair of kantorovich.hpp:37-39 / lloyd.hpp:31-33:
+ * T is given as vertices + CCW index triples (the input format of
+ * include/CGAL/Triangulation_incremental_builder_2.h:25-81, tests/test_triangulation.cpp:12-34),
+ * densityF as abc[3 f + (0,1,2)] with rho_f(x,y) = a x + b y + c (functions.hpp:55-80). */
+int ma_set_mesh(ma_ctx *ctx, int nV, const double *vx, const double *vy, int nF, const int *tri,
+                const double *abc);
+/* Same, building the per-face functions from per-vertex values as MA::Linear_function's
+ * constructor does (functions.hpp:64-71).  total_mass (may be NULL) receives
+ * sum_f area_f * rho_f(centroid_f) (functions.hpp:117). */
+int ma_set_mesh_pl(ma_ctx *ctx, int nV, const double *vx, const double *vy, const double *rho_v, int nF,
+                   const int *tri, double *total_mass);
+/* Structured n x m vertex grid on [x0,x1] x [y0,y1]: vertex (i,j) has index i*m+j and density
+ * rho_v[i*m+j]; square (i,j) is split along (i,j)-(i+1,j+1) into faces 2*(i*(m-1)+j) and +1.
+ * Replaces the triangulation built by image_to_pl_function (functions.hpp:82-120) with a fixed
+ * diagonal rule (CGAL's choice is not reproducible). */
+int ma_set_grid(ma_ctx *ctx, int n, int m, double x0, double y0, double x1, double y1, const double *rho_v,
+                double *total_mass);
+/* image_to_pl_function (functions.hpp:82-120): pixels[j*n + i] = image(i,j) (CImg layout), mapped to
+ * [-1,1]^2 with rho = image(i, m-j-1)/255 + 1e-3. */
+int ma_set_image(ma_ctx *ctx, int n, int m, const double *pixels, double *total_mass);
+
+/* ---- Diracs ------------------------------------------------------------------------------
+ * X of kantorovich.hpp:40 / optimal_transport.hpp:93: an Eigen column-major N x 2 matrix maps to
+ * (x = X.data(), y = X.data() + N) without a copy.  Sorts the points into Morton-ordered bins. */
+int ma_set_points(ma_ctx *ctx, int N, const double *x, const double *y);
+
+/* ---- one evaluation of Kantorovich's functional -------------------------------------------
+ * double kantorovich(densityT, densityF, X, weights, g, h)   kantorovich.hpp:35-42.
+ * g[N] receives the cell masses (= gradient); the Hessian is kept in the context: *nnz receives its
+ * number of stored entries and ma_get_hessian_csr copies it out as CSR in the caller's ordering
+ * (rowptr[N+1], col[nnz] ascending within a row, val[nnz]).  Row i is what the reference's triplets
+ * (i, *) sum to (kantorovich.hpp:120-121), i.e. the CSR is the row-major form of the reference's h.
+ * g, nnz may be NULL. */
+int ma_kantorovich(ma_ctx *ctx, const double *weights, double *fval, double *g, int *nnz);
+int ma_get_hessian_csr(ma_ctx *ctx, int *rowptr, int *col, double *val);
+
+/* first_moment / second_moment / lloyd   lloyd.hpp:30-144.
+ * order 1: masses[N], m1[2N] = (∫ρx [N], ∫ρy [N]) (column-major N x 2 like Eigen).
+ * order 2: additionally m2[3N] = (∫ρx², ∫ρy², ∫ρxy) (column-major N x 3).  m2 may be NULL for order 1. */
+int ma_moments(ma_ctx *ctx, const double *weights, int order, double *masses, double *m1, double *m2);
+/* lloyd(): centroids = m1 / masses (lloyd.hpp:139-143); centroids is column-major N x 2. */
+int ma_lloyd(ma_ctx *ctx, const double *weights, double *masses, double *centroids);
+
+/* ---- Newton solver -------------------------------------------------------------------------
+ * Vector solve_laplacian_matrix(h, g)   optimal_transport.hpp:41-87: grounds the LAST index, solves
+ * the leading (N-1)x(N-1) block of the CSR matrix by Jacobi-preconditioned CG on the device,
+ * d[N-1] = 0.  iters (may be NULL) receives the CG iteration count. */
+int ma_solve_laplacian(ma_ctx *ctx, int N, const int *rowptr, const int *col, const double *val, const double *g,
+                       double *d, int *iters);
+
+typedef struct ma_statistics { /* struct Statistics, optimal_transport.hpp:35-39 (+ extras) */
+  size_t niter;
+  size_t neval;
+  size_t cg_iters;     /* total CG iterations */
+  double final_norm;   /* ||m - nu||_2 at exit */
+  double fval;         /* f(w) - nu.w at exit */
+  double seconds;      /* wall time of the call */
+} ma_statistics;
+
+/* void ot_solve(t, functions, X, masses, x, eps_g, maxiter, verbose, stats)  optimal_transport.hpp:89-99.
+ * nu[N]: target masses; w[N]: in = initial guess (used iff have_initial != 0, else zeros, :125-128),
+ * out = result.  Returns MA_EMPTY_CELL and leaves w = initial guess when a cell is empty at the
+ * start (:139-148). */
+int ma_ot_solve(ma_ctx *ctx, const double *nu, double *w, int have_initial, double eps_g, size_t maxiter,
+                int verbose, ma_statistics *stats);
+
+/* ---- pieces (cell ∩ face polygons) ---------------------------------------------------------
+ * voronoi_triangulation_intersection(t, dt, out)  voronoi_triangulation_intersection.hpp:315-343:
+ * enumerates every non-empty piece.  Two-call protocol: ma_pieces_build computes them on the device
+ * and returns the counts, ma_pieces_get copies them out: piece p belongs to cell[p] and face[p] and
+ * has vertices xy[2*ptr[p] .. 2*ptr[p+1]) (CCW); tag[k] is the Laguerre neighbour across the edge
+ * starting at vertex k, or -1 for an edge of the source triangle (the EDGE_DT / EDGE_T tags of
+ * vti.hpp:54-96). */
+int ma_pieces_build(ma_ctx *ctx, const double *weights, int *npieces, int *nvertices);
+int ma_pieces_get(ma_ctx *ctx, int *cell, int *face, int *ptr, int *tag, double *xy);
+
+/* ---- device-resident evaluation (what bench.py times as `value`) -----------------------------
+ * ma_set_weights uploads w (caller order); ma_evaluate runs K1(per-eval part)+K2+K3+K4 on the
+ * device-resident state and leaves masses / Hessian on the device (internal Morton order). */
+int ma_set_weights(ma_ctx *ctx, const double *weights);
+int ma_evaluate(ma_ctx *ctx, int with_hessian);
+
+/* Laguerre adjacency found by the last evaluation (caller ordering, CSR): the neighbours whose
+ * bisector supports an edge of (cell ∩ mesh bounding box). */
+int ma_get_adjacency(ma_ctx *ctx, int *ptr /* N+1 */, int *idx /* >= ptr[N] */, int capacity);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+enum {
+  MA_T_TOTAL = 0,   /* whole evaluation */
+  MA_T_PREP = 1,    /* K1 per-eval: weight gather + max-weight pyramid */
+  MA_T_CELLS = 2,   /* K2: Laguerre-cell construction / neighbour search */
+  MA_T_PIECES = 3,  /* K3: clipping + integration */
+  MA_T_CSR = 4,     /* K4: scan + CSR fill */
+  MA_T_REDUCE = 5,  /* scalar reductions */
+  MA_T_COUNT = 8
+};
+/* CUDA-event times (ms) of the stages of the last ma_evaluate (profiling must be enabled). */
+int ma_set_profiling(ma_ctx *ctx, int on);
+int ma_get_timings(ma_ctx *ctx, float *ms /* MA_T_COUNT */);
+/* Counters of the last evaluation when stats are enabled: pieces, piece vertices, new vertices,
+ * Laguerre edges, sum k_i, sum k_i*n_p, robust-predicate fallbacks, candidate triangles. */
+int ma_set_stats(ma_ctx *ctx, int on);
+int ma_get_counters(ma_ctx *ctx, int64_t *c /* 8 */);
+/* Writes `bytes` of device memory (to evict L2 between timed steps). */
+int ma_flush_l2(ma_ctx *ctx, size_t bytes);
+/* DFMA throughput micro-benchmark (FLOP/s), the fp64 roofline denominator "of measured". */
+int ma_measure_fp64_peak(ma_ctx *ctx, double *flops_per_s);
+/* Option knobs: "kmax", "strategy" (0 auto, 1 fused thread-per-cell, 2 warp-per-cell), "cg_rtol", ... */
+int ma_set_option(ma_ctx *ctx, const char *name, double value);
+double ma_get_info(ma_ctx *ctx, const char *name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MA_B200_H */

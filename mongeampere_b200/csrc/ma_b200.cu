@@ -1,0 +1,1082 @@
+// ma_b200.cu — host side of libma_b200.so: context, device buffers, kernel orchestration and the
+// C-ABI declared in include/ma_b200.h.  No CPU fallback anywhere: every entry point needs a CUDA
+// device and fails with MA_CUDA_ERROR otherwise.
+#include "../../include/ma_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ma_pcg.cuh"
+
+using namespace ma;
+
+namespace {
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct ma_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+
+  // options
+  int kmax = 16;
+  int bin_target = 2;  // average Diracs per leaf bin
+  double cg_rtol = 1e-12;
+  int cg_maxit = 200000;
+  double filter_tol = 1e-11;
+  int profiling = 0, stats = 0;
+
+  // mesh
+  int mesh_kind = MESH_NONE;
+  int nV = 0, nF = 0;
+  double bb[4] = {0, 0, 0, 0};
+  Buf vx, vy, tri, abc, tbin_ptr, tbin_face;
+  int tg = 1;
+  double tinvx = 1, tinvy = 1;
+  int gn = 0, gm = 0;
+  double gx0 = 0, gy0 = 0, gdx = 1, gdy = 1;
+
+  // points
+  int N = 0;
+  Buf x, y, xs, ys, perm, pos, code, bin_count, bin_start, wmax;
+  int L = 0;
+  double px0 = 0, py0 = 0, ph = 1;
+
+  // evaluation state
+  Buf w, ws, nbr, nbr_cnt, cell_bb, mass, fcell, hslot, touched, rowcnt, rowptr, col, val, mom;
+  Buf scan_tmp, red_partial, red_out, counters, flags, scratch_d, scratch_i;
+  Buf cptr, ccol, cval, cg_out;  // caller-order copies
+  int nnz = 0;
+  bool have_eval = false, have_hessian = false;
+  double fval = 0, mass_sum = 0, mass_min = 0;
+
+  // pieces
+  Buf pc_count, pc_off, pc_cell, pc_face, pc_ptr, pc_tag, pc_xy;
+  int pc_np = 0, pc_nv = 0;
+
+  // pcg
+  Buf dinv, cgx, cgr, cgz, cgp0, cgp1, cgq, part_pq, part_rz, part_rr, scal, cgflag;
+  Buf nu_s, x0_s, d_s, g_s;
+  size_t last_cg_iters = 0;
+
+  // L2 flush
+  Buf flush;
+
+  // timing
+  cudaEvent_t ev[MA_T_COUNT + 2] = {};
+  float t_ms[MA_T_COUNT] = {};
+  int64_t host_counters[CNT_N] = {};
+};
+
+namespace {
+
+int fail(ma_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(c, MA_CUDA_ERROR, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+#define CKR(call)                     \
+  do {                                \
+    int r_ = (call);                  \
+    if (r_ != MA_OK) return r_;       \
+  } while (0)
+
+int ensure(ma_ctx *c, Buf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return MA_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = std::max<size_t>(bytes, 256);
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return MA_OK;
+}
+void release(Buf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// exclusive scan of n ints (device) into out[0..n], out[n] = total
+int scan_i32(ma_ctx *c, const int *in, int *out, int n) {
+  int nt = std::max(1, cdiv(n, SCAN_TILE));
+  CKR(ensure(c, c->scan_tmp, (size_t)(nt + 1) * sizeof(int)));
+  int *ts = c->scan_tmp.as<int>();
+  k_scan_tiles<<<nt, SCAN_NT, 0, c->stream>>>(in, out, ts, n);
+  k_scan_sums<<<1, SCAN_NT, 0, c->stream>>>(ts, nt, ts + nt);
+  k_scan_add<<<nt, SCAN_NT, 0, c->stream>>>(out, ts, n, ts + nt);
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+
+// out (device, 4 doubles) = { sum a, sum a*b (a*a if b null), min a, max a }
+int reduce4(ma_ctx *c, const double *a, const double *b, int n, double *out_dev) {
+  CKR(ensure(c, c->red_partial, (size_t)RED_BLOCKS * 4 * sizeof(double)));
+  int nb = std::min(RED_BLOCKS, std::max(1, cdiv(n, RED_NT)));
+  k_reduce_stage1<<<nb, RED_NT, 0, c->stream>>>(a, b, n, c->red_partial.as<double>());
+  k_reduce_stage2<<<1, RED_NT, 0, c->stream>>>(c->red_partial.as<double>(), nb, out_dev);
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mesh
+// ---------------------------------------------------------------------------------------------
+double host_total_mass(int nF, const int *tri, const double *vx, const double *vy, const double *abc) {
+  double tot = 0;
+  for (int f = 0; f < nF; ++f) {
+    int a = tri[3 * f], b = tri[3 * f + 1], cc = tri[3 * f + 2];
+    double area = ((vx[b] - vx[a]) * (vy[cc] - vy[a]) - (vx[cc] - vx[a]) * (vy[b] - vy[a])) / 2;
+    double gx = (vx[a] + vx[b] + vx[cc]) / 3, gy = (vy[a] + vy[b] + vy[cc]) / 3;
+    tot += area * (abc[3 * f] * gx + abc[3 * f + 1] * gy + abc[3 * f + 2]);
+  }
+  return tot;
+}
+
+// per-face plane through the three vertex values: what MA::Linear_function represents
+// (functions.hpp:55-80), obtained from the 2x2 system instead of three barycentric extrapolations
+void host_pl_coefficients(int nF, const int *tri, const double *vx, const double *vy, const double *rho,
+                          double *abc) {
+  for (int f = 0; f < nF; ++f) {
+    int ia = tri[3 * f], ib = tri[3 * f + 1], ic = tri[3 * f + 2];
+    double ax = vx[ia], ay = vy[ia], e1x = vx[ib] - ax, e1y = vy[ib] - ay, e2x = vx[ic] - ax, e2y = vy[ic] - ay;
+    double f1 = rho[ib] - rho[ia], f2 = rho[ic] - rho[ia];
+    double det = e1x * e2y - e2x * e1y;
+    double a = (f1 * e2y - f2 * e1y) / det, b = (e1x * f2 - e2x * f1) / det;
+    abc[3 * f] = a;
+    abc[3 * f + 1] = b;
+    abc[3 * f + 2] = rho[ia] - a * ax - b * ay;
+  }
+}
+
+int upload(ma_ctx *c, Buf &b, const void *src, size_t bytes) {
+  CKR(ensure(c, b, bytes));
+  if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return MA_OK;
+}
+
+void invalidate_eval(ma_ctx *c) {
+  c->have_eval = false;
+  c->have_hessian = false;
+}
+
+}  // namespace
+
+// =============================================================================================
+// context
+// =============================================================================================
+extern "C" int ma_abi_version(void) { return 1; }
+
+extern "C" int ma_create(ma_ctx **out, int device) {
+  if (!out) return MA_INVALID;
+  *out = nullptr;
+  ma_ctx *c = new ma_ctx();
+  c->device = device;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    // no silent CPU path: the context is returned so that the message can be read, but is unusable
+    fail(c, MA_CUDA_ERROR, "no usable CUDA device %d (%s); libma_b200 has no CPU fallback", device,
+         e == cudaSuccess ? "device index out of range" : cudaGetErrorString(e));
+    *out = c;
+    return MA_CUDA_ERROR;
+  }
+  *out = c;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+  return MA_OK;
+}
+
+extern "C" void ma_destroy(ma_ctx *c) {
+  if (!c) return;
+  if (c->stream) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Buf *all[] = {&c->vx, &c->vy, &c->tri, &c->abc, &c->tbin_ptr, &c->tbin_face, &c->x, &c->y, &c->xs, &c->ys,
+                  &c->perm, &c->pos, &c->code, &c->bin_count, &c->bin_start, &c->wmax, &c->w, &c->ws, &c->nbr,
+                  &c->nbr_cnt, &c->cell_bb, &c->mass, &c->fcell, &c->hslot, &c->touched, &c->rowcnt, &c->rowptr,
+                  &c->col, &c->val, &c->mom, &c->scan_tmp, &c->red_partial, &c->red_out, &c->counters, &c->flags,
+                  &c->scratch_d, &c->scratch_i, &c->cptr, &c->ccol, &c->cval, &c->cg_out, &c->pc_count, &c->pc_off,
+                  &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
+                  &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
+                  &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush};
+    for (Buf *b : all) release(*b);
+    for (auto &ev : c->ev)
+      if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+  }
+  delete c;
+}
+
+extern "C" const char *ma_last_error(const ma_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+#define NEED_CTX()                                                                  \
+  do {                                                                              \
+    if (!c) return MA_INVALID;                                                      \
+    if (!c->stream) return fail(c, MA_CUDA_ERROR, "context has no CUDA device");    \
+    cudaSetDevice(c->device);                                                       \
+  } while (0)
+
+extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
+  if (!c || !name) return MA_INVALID;
+  std::string n(name);
+  if (n == "kmax") {
+    int k = (int)value;
+    if (k != 16 && k != 32 && k != 64) return fail(c, MA_INVALID, "kmax must be 16, 32 or 64");
+    c->kmax = k;
+    invalidate_eval(c);
+  } else if (n == "bin_target") c->bin_target = std::max(1, (int)value);
+  else if (n == "cg_rtol") c->cg_rtol = value;
+  else if (n == "cg_maxit") c->cg_maxit = (int)value;
+  else if (n == "filter_tol") c->filter_tol = value;
+  else return fail(c, MA_INVALID, "unknown option %s", name);
+  return MA_OK;
+}
+
+extern "C" double ma_get_info(ma_ctx *c, const char *name) {
+  if (!c || !name) return -1;
+  std::string n(name);
+  if (n == "kmax") return c->kmax;
+  if (n == "levels") return c->L;
+  if (n == "nnz") return c->nnz;
+  if (n == "N") return c->N;
+  if (n == "nF") return c->nF;
+  if (n == "sm_count") return c->sm_count;
+  if (n == "mass_sum") return c->mass_sum;
+  if (n == "mass_min") return c->mass_min;
+  if (n == "cg_iters") return (double)c->last_cg_iters;
+  if (n == "mesh_kind") return c->mesh_kind;
+  return -1;
+}
+
+// =============================================================================================
+// mesh
+// =============================================================================================
+extern "C" int ma_set_mesh(ma_ctx *c, int nV, const double *vx, const double *vy, int nF, const int *tri,
+                           const double *abc) {
+  NEED_CTX();
+  if (nV < 3 || nF < 1 || !vx || !vy || !tri || !abc) return fail(c, MA_INVALID, "ma_set_mesh: bad arguments");
+  for (int f = 0; f < nF; ++f) {
+    int a = tri[3 * f], b = tri[3 * f + 1], cc = tri[3 * f + 2];
+    if (a < 0 || b < 0 || cc < 0 || a >= nV || b >= nV || cc >= nV)
+      return fail(c, MA_INVALID, "ma_set_mesh: face %d has an out-of-range vertex", f);
+    double area2 = (vx[b] - vx[a]) * (vy[cc] - vy[a]) - (vx[cc] - vx[a]) * (vy[b] - vy[a]);
+    if (!(area2 > 0)) return fail(c, MA_INVALID, "ma_set_mesh: face %d is not counter-clockwise", f);
+  }
+  c->mesh_kind = MESH_GENERAL;
+  c->nV = nV;
+  c->nF = nF;
+  c->bb[0] = c->bb[1] = 1e300;
+  c->bb[2] = c->bb[3] = -1e300;
+  for (int i = 0; i < nV; ++i) {
+    c->bb[0] = std::min(c->bb[0], vx[i]); c->bb[2] = std::max(c->bb[2], vx[i]);
+    c->bb[1] = std::min(c->bb[1], vy[i]); c->bb[3] = std::max(c->bb[3], vy[i]);
+  }
+  // bins of faces (a face is listed in every bin its bounding box overlaps)
+  int g = (int)std::ceil(std::sqrt(std::max(1.0, nF / 2.0)));
+  g = std::min(g, 2048);
+  c->tg = g;
+  c->tinvx = g / std::max(c->bb[2] - c->bb[0], 1e-300);
+  c->tinvy = g / std::max(c->bb[3] - c->bb[1], 1e-300);
+  auto range = [&](int f, int &i0, int &i1, int &j0, int &j1) {
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int k = 0; k < 3; ++k) {
+      int v = tri[3 * f + k];
+      x0 = std::min(x0, vx[v]); x1 = std::max(x1, vx[v]);
+      y0 = std::min(y0, vy[v]); y1 = std::max(y1, vy[v]);
+    }
+    i0 = std::min(std::max((int)std::floor((x0 - c->bb[0]) * c->tinvx), 0), g - 1);
+    i1 = std::min(std::max((int)std::floor((x1 - c->bb[0]) * c->tinvx), 0), g - 1);
+    j0 = std::min(std::max((int)std::floor((y0 - c->bb[1]) * c->tinvy), 0), g - 1);
+    j1 = std::min(std::max((int)std::floor((y1 - c->bb[1]) * c->tinvy), 0), g - 1);
+  };
+  std::vector<int> ptr((size_t)g * g + 1, 0);
+  for (int f = 0; f < nF; ++f) {
+    int i0, i1, j0, j1;
+    range(f, i0, i1, j0, j1);
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) ptr[(size_t)j * g + i + 1]++;
+  }
+  for (size_t b = 0; b < (size_t)g * g; ++b) ptr[b + 1] += ptr[b];
+  std::vector<int> faces(ptr.back()), fill(ptr.begin(), ptr.end() - 1);
+  for (int f = 0; f < nF; ++f) {
+    int i0, i1, j0, j1;
+    range(f, i0, i1, j0, j1);
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) faces[fill[(size_t)j * g + i]++] = f;
+  }
+  CKR(upload(c, c->vx, vx, (size_t)nV * 8));
+  CKR(upload(c, c->vy, vy, (size_t)nV * 8));
+  CKR(upload(c, c->tri, tri, (size_t)nF * 12));
+  CKR(upload(c, c->abc, abc, (size_t)nF * 24));
+  CKR(upload(c, c->tbin_ptr, ptr.data(), ptr.size() * 4));
+  CKR(upload(c, c->tbin_face, faces.data(), faces.size() * 4));
+  CK(cudaStreamSynchronize(c->stream));
+  invalidate_eval(c);
+  return MA_OK;
+}
+
+extern "C" int ma_set_mesh_pl(ma_ctx *c, int nV, const double *vx, const double *vy, const double *rho_v, int nF,
+                              const int *tri, double *total_mass) {
+  NEED_CTX();
+  if (nV < 3 || nF < 1 || !vx || !vy || !tri || !rho_v) return fail(c, MA_INVALID, "ma_set_mesh_pl: bad arguments");
+  for (int f = 0; f < 3 * nF; ++f)
+    if (tri[f] < 0 || tri[f] >= nV) return fail(c, MA_INVALID, "ma_set_mesh_pl: vertex index out of range");
+  std::vector<double> abc((size_t)3 * nF);
+  host_pl_coefficients(nF, tri, vx, vy, rho_v, abc.data());
+  if (total_mass) *total_mass = host_total_mass(nF, tri, vx, vy, abc.data());
+  return ma_set_mesh(c, nV, vx, vy, nF, tri, abc.data());
+}
+
+extern "C" int ma_set_grid(ma_ctx *c, int n, int m, double x0, double y0, double x1, double y1, const double *rho_v,
+                           double *total_mass) {
+  NEED_CTX();
+  if (n < 2 || m < 2 || !rho_v || !(x1 > x0) || !(y1 > y0)) return fail(c, MA_INVALID, "ma_set_grid: bad arguments");
+  const double dx = (x1 - x0) / double(n - 1), dy = (y1 - y0) / double(m - 1);
+  const size_t nF = (size_t)2 * (n - 1) * (m - 1);
+  if (nF > 0x7fffffffull / 3) return fail(c, MA_INVALID, "ma_set_grid: grid too large for int32 face ids");
+  std::vector<double> abc(3 * nF);
+  double tot = 0;
+  for (int i = 0; i + 1 < n; ++i)
+    for (int j = 0; j + 1 < m; ++j) {
+      // vertex coordinates exactly as functions.hpp:96-99 computes them
+      double X0 = x0 + i * dx, X1 = x0 + (i + 1) * dx, Y0 = y0 + j * dy, Y1 = y0 + (j + 1) * dy;
+      double r00 = rho_v[(size_t)i * m + j], r10 = rho_v[(size_t)(i + 1) * m + j];
+      double r11 = rho_v[(size_t)(i + 1) * m + j + 1], r01 = rho_v[(size_t)i * m + j + 1];
+      size_t f = 2 * ((size_t)i * (m - 1) + j);
+      double ex = X1 - X0, ey = Y1 - Y0;
+      {  // face {(i,j),(i+1,j),(i+1,j+1)}
+        double a = (r10 - r00) / ex, b = (r11 - r10) / ey;
+        abc[3 * f] = a; abc[3 * f + 1] = b; abc[3 * f + 2] = r00 - a * X0 - b * Y0;
+        double gx = (X0 + X1 + X1) / 3, gy = (Y0 + Y0 + Y1) / 3;
+        tot += 0.5 * ex * ey * (a * gx + b * gy + abc[3 * f + 2]);
+      }
+      {  // face {(i,j),(i+1,j+1),(i,j+1)}
+        double a = (r11 - r01) / ex, b = (r01 - r00) / ey;
+        abc[3 * f + 3] = a; abc[3 * f + 4] = b; abc[3 * f + 5] = r00 - a * X0 - b * Y0;
+        double gx = (X0 + X1 + X0) / 3, gy = (Y0 + Y1 + Y1) / 3;
+        tot += 0.5 * ex * ey * (a * gx + b * gy + abc[3 * f + 5]);
+      }
+    }
+  if (total_mass) *total_mass = tot;
+  c->mesh_kind = MESH_GRID;
+  c->gn = n; c->gm = m;
+  c->gx0 = x0; c->gy0 = y0; c->gdx = dx; c->gdy = dy;
+  c->nV = n * m;
+  c->nF = (int)nF;
+  c->bb[0] = x0; c->bb[1] = y0;
+  c->bb[2] = x0 + (n - 1) * dx; c->bb[3] = y0 + (m - 1) * dy;
+  CKR(upload(c, c->abc, abc.data(), abc.size() * 8));
+  CK(cudaStreamSynchronize(c->stream));
+  invalidate_eval(c);
+  return MA_OK;
+}
+
+extern "C" int ma_set_image(ma_ctx *c, int n, int m, const double *pixels, double *total_mass) {
+  NEED_CTX();
+  if (n < 2 || m < 2 || !pixels) return fail(c, MA_INVALID, "ma_set_image: bad arguments");
+  std::vector<double> rho((size_t)n * m);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < m; ++j)  // fgrid[p] = image(i, m-j-1)/255 + 1e-3   functions.hpp:102
+      rho[(size_t)i * m + j] = pixels[(size_t)(m - j - 1) * n + i] / double(255) + 1e-3;
+  return ma_set_grid(c, n, m, -1.0, -1.0, 1.0, 1.0, rho.data(), total_mass);
+}
+
+// =============================================================================================
+// Diracs (K1, once per point set)
+// =============================================================================================
+extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y) {
+  NEED_CTX();
+  if (N < 1 || !x || !y) return fail(c, MA_INVALID, "ma_set_points: bad arguments");
+  c->N = N;
+  invalidate_eval(c);
+  CKR(upload(c, c->x, x, (size_t)N * 8));
+  CKR(upload(c, c->y, y, (size_t)N * 8));
+  CKR(ensure(c, c->red_out, 16 * sizeof(double)));
+  k_bbox<<<1, 1024, 0, c->stream>>>(c->x.as<double>(), c->y.as<double>(), N, c->red_out.as<double>());
+  double pb[4];
+  CK(cudaMemcpyAsync(pb, c->red_out.p, sizeof pb, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (!(std::isfinite(pb[0]) && std::isfinite(pb[1]) && std::isfinite(pb[2]) && std::isfinite(pb[3])))
+    return fail(c, MA_INVALID, "ma_set_points: non-finite coordinates");
+  double ext = std::max(std::max(pb[2] - pb[0], pb[3] - pb[1]), 1e-300) * (1 + 1e-9);
+  int L = 0;
+  while (((long long)1 << (2 * L)) * c->bin_target < N && L < 12) ++L;
+  const int G = 1 << L;
+  c->L = L;
+  c->px0 = pb[0]; c->py0 = pb[1];
+  c->ph = ext / G;
+  const double pinv = G / ext;
+  const size_t nb = (size_t)G * G;
+  CKR(ensure(c, c->code, (size_t)N * 4));
+  CKR(ensure(c, c->bin_count, nb * 4));
+  CKR(ensure(c, c->bin_start, (nb + 1) * 4));
+  CKR(ensure(c, c->perm, (size_t)N * 4));
+  CKR(ensure(c, c->pos, (size_t)N * 4));
+  CKR(ensure(c, c->xs, (size_t)N * 8));
+  CKR(ensure(c, c->ys, (size_t)N * 8));
+  CKR(ensure(c, c->ws, (size_t)N * 8));
+  CKR(ensure(c, c->w, (size_t)N * 8));
+  CKR(ensure(c, c->wmax, ((4 * nb - 1) / 3) * 8));
+  CK(cudaMemsetAsync(c->bin_count.p, 0, nb * 4, c->stream));
+  k_bin_count<<<cdiv(N, 256), 256, 0, c->stream>>>(c->x.as<double>(), c->y.as<double>(), N, c->px0, c->py0, pinv, G,
+                                                   c->code.as<unsigned>(), c->bin_count.as<int>());
+  CKR(scan_i32(c, c->bin_count.as<int>(), c->bin_start.as<int>(), (int)nb));
+  CK(cudaMemsetAsync(c->bin_count.p, 0, nb * 4, c->stream));
+  k_bin_scatter<<<cdiv(N, 256), 256, 0, c->stream>>>(c->code.as<unsigned>(), N, c->bin_start.as<int>(),
+                                                     c->bin_count.as<int>(), c->perm.as<int>());
+  k_bin_sort<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(c->bin_start.as<int>(), (int)nb, c->perm.as<int>());
+  k_gather_points<<<cdiv(N, 256), 256, 0, c->stream>>>(c->x.as<double>(), c->y.as<double>(), c->perm.as<int>(), N,
+                                                       c->xs.as<double>(), c->ys.as<double>(), c->pos.as<int>());
+  CK(cudaMemsetAsync(c->w.p, 0, (size_t)N * 8, c->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return MA_OK;
+}
+
+// =============================================================================================
+// evaluation (K1 per-eval + K2 + K3 + K4)
+// =============================================================================================
+namespace {
+
+int fill_params(ma_ctx *c, Params &p) {
+  memset(&p, 0, sizeof p);
+  p.N = c->N;
+  p.xs = c->xs.as<double>(); p.ys = c->ys.as<double>(); p.ws = c->ws.as<double>();
+  p.L = c->L; p.px0 = c->px0; p.py0 = c->py0; p.ph = c->ph;
+  p.bin_start = c->bin_start.as<int>();
+  p.wmax = c->wmax.as<double>();
+  for (int k = 0; k < 4; ++k) p.bb[k] = c->bb[k];
+  p.mesh_kind = c->mesh_kind;
+  p.nF = c->nF;
+  p.abc = c->abc.as<double>();
+  p.gn = c->gn; p.gm = c->gm; p.gx0 = c->gx0; p.gy0 = c->gy0; p.gdx = c->gdx; p.gdy = c->gdy;
+  p.vx = c->vx.as<double>(); p.vy = c->vy.as<double>(); p.tri = c->tri.as<int>();
+  p.tg = c->tg; p.tinvx = c->tinvx; p.tinvy = c->tinvy;
+  p.tbin_ptr = c->tbin_ptr.as<int>(); p.tbin_face = c->tbin_face.as<int>();
+  p.kmax = c->kmax;
+  p.nbr = c->nbr.as<int>(); p.nbr_cnt = c->nbr_cnt.as<int>(); p.cell_bb = c->cell_bb.as<double>();
+  p.mass = c->mass.as<double>(); p.fcell = c->fcell.as<double>(); p.hslot = c->hslot.as<double>();
+  p.touched = c->touched.as<unsigned long long>(); p.rowcnt = c->rowcnt.as<int>();
+  p.mom = c->mom.as<double>();
+  p.counters = c->counters.as<unsigned long long>();
+  p.stats = c->stats;
+  p.flags = c->flags.as<int>();
+  p.filter_tol = c->filter_tol;
+  return MA_OK;
+}
+
+template <int MAXV, int NT> int launch_cells(ma_ctx *c, const Params &p) {
+  size_t sm = cells_smem_bytes<MAXV, NT>();
+  CK(cudaFuncSetAttribute(k_cells<MAXV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_cells<MAXV, NT><<<cdiv(p.N, NT), NT, sm, c->stream>>>(p);
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+template <int KMAX, int MAXV, int MODE> int launch_pieces(ma_ctx *c, const Params &p) {
+  size_t sm = pieces_warp_bytes<KMAX, MAXV>() * PIECES_WPB;
+  CK(cudaFuncSetAttribute(k_pieces<KMAX, MAXV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_pieces<KMAX, MAXV, MODE><<<cdiv(p.N, PIECES_WPB), PIECES_WPB * 32, sm, c->stream>>>(p);
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+template <int MODE> int launch_pieces_mode(ma_ctx *c, const Params &p) {
+  switch (c->kmax) {
+    case 16: return launch_pieces<16, 12, MODE>(c, p);
+    case 32: return launch_pieces<32, 20, MODE>(c, p);
+    default: return launch_pieces<64, 40, MODE>(c, p);
+  }
+}
+int launch_cells_kmax(ma_ctx *c, const Params &p) {
+  switch (c->kmax) {
+    case 16: return launch_cells<20, 128>(c, p);
+    case 32: return launch_cells<36, 64>(c, p);
+    default: return launch_cells<64, 32>(c, p);
+  }
+}
+
+int alloc_eval(ma_ctx *c) {
+  const size_t N = c->N, K = c->kmax;
+  CKR(ensure(c, c->nbr, N * K * 4));
+  CKR(ensure(c, c->nbr_cnt, N * 4));
+  CKR(ensure(c, c->cell_bb, N * 32));
+  CKR(ensure(c, c->mass, N * 8));
+  CKR(ensure(c, c->fcell, N * 8));
+  CKR(ensure(c, c->hslot, N * K * 8));
+  CKR(ensure(c, c->touched, N * 8));
+  CKR(ensure(c, c->rowcnt, N * 4));
+  CKR(ensure(c, c->rowptr, (N + 1) * 4));
+  CKR(ensure(c, c->counters, CNT_N * 8));
+  CKR(ensure(c, c->flags, 16));
+  CKR(ensure(c, c->red_out, 16 * sizeof(double)));
+  return MA_OK;
+}
+
+// K1 per-eval part + K2 on the current device weights (c->w, caller order)
+int run_cells(ma_ctx *c, Params &p) {
+  const int N = c->N;
+  k_gather<<<cdiv(N, 256), 256, 0, c->stream>>>(c->w.as<double>(), c->perm.as<int>(), N, c->ws.as<double>());
+  const size_t nb = (size_t)1 << (2 * c->L);
+  k_wmax_leaf<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(c->ws.as<double>(), c->bin_start.as<int>(), c->L,
+                                                               c->wmax.as<double>());
+  if (c->L >= 5) k_wmax_top<<<1, 1024, 0, c->stream>>>(c->L, c->wmax.as<double>());
+  CK(cudaGetLastError());
+  if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PREP + 1], c->stream));
+  CKR(launch_cells_kmax(c, p));
+  if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CELLS + 1], c->stream));
+  return MA_OK;
+}
+
+// one evaluation with automatic capacity escalation
+template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
+  if (c->mesh_kind == MESH_NONE) return fail(c, MA_INVALID, "no mesh set");
+  if (c->N < 1) return fail(c, MA_INVALID, "no points set");
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    CKR(alloc_eval(c));
+    if (MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) CKR(ensure(c, c->mom, (size_t)c->N * 48));
+    Params p;
+    fill_params(c, p);
+    CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
+    if (c->stats) CK(cudaMemsetAsync(c->counters.p, 0, CNT_N * 8, c->stream));
+    if (c->profiling) CK(cudaEventRecord(c->ev[0], c->stream));
+    CKR(run_cells(c, p));
+    CKR(launch_pieces_mode<MODE>(c, p));
+    if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
+    if (MODE == MODE_KANTOROVICH) {
+      if (with_hessian) CKR(scan_i32(c, c->rowcnt.as<int>(), c->rowptr.as<int>(), c->N));
+      CKR(reduce4(c, c->fcell.as<double>(), nullptr, c->N, c->red_out.as<double>()));
+      CKR(reduce4(c, c->mass.as<double>(), nullptr, c->N, c->red_out.as<double>() + 4));
+    }
+    int h_flags = 0;
+    double red[8] = {0};
+    int h_nnz = 0;
+    CK(cudaMemcpyAsync(&h_flags, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (MODE == MODE_KANTOROVICH) {
+      CK(cudaMemcpyAsync(red, c->red_out.p, sizeof red, cudaMemcpyDeviceToHost, c->stream));
+      if (with_hessian)
+        CK(cudaMemcpyAsync(&h_nnz, c->rowptr.as<int>() + c->N, 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (h_flags & (FLAG_CELL_OVERFLOW | FLAG_PIECE_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
+      if (c->kmax >= 64) return fail(c, MA_INVALID, "polygon capacity exceeded even at kmax=64 (flags=%d)", h_flags);
+      c->kmax *= 2;  // escalate to the next capacity class and redo the evaluation
+      continue;
+    }
+    if (h_flags & FLAG_STACK_OVERFLOW) return fail(c, MA_INVALID, "quadtree stack overflow");
+    if (MODE == MODE_KANTOROVICH) {
+      c->fval = red[0];
+      c->mass_sum = red[4];
+      c->mass_min = red[6];
+      if (with_hessian) {
+        c->nnz = h_nnz;
+        CKR(ensure(c, c->col, (size_t)std::max(h_nnz, 1) * 4));
+        CKR(ensure(c, c->val, (size_t)std::max(h_nnz, 1) * 8));
+        if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
+        const int N = c->N;
+        switch (c->kmax) {
+          case 16: k_csr_fill<16><<<cdiv(N, 128), 128, 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+          case 32: k_csr_fill<32><<<cdiv(N, 128), 128, 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+          default: k_csr_fill<64><<<cdiv(N, 128), 128, 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+        }
+        CK(cudaGetLastError());
+        if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CSR + 1], c->stream));
+      }
+    }
+    if (c->profiling) {
+      CK(cudaEventRecord(c->ev[MA_T_COUNT + 1], c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      for (auto &t : c->t_ms) t = 0;
+      cudaEventElapsedTime(&c->t_ms[MA_T_TOTAL], c->ev[0], c->ev[MA_T_COUNT + 1]);
+      cudaEventElapsedTime(&c->t_ms[MA_T_PREP], c->ev[0], c->ev[MA_T_PREP + 1]);
+      cudaEventElapsedTime(&c->t_ms[MA_T_CELLS], c->ev[MA_T_PREP + 1], c->ev[MA_T_CELLS + 1]);
+      cudaEventElapsedTime(&c->t_ms[MA_T_PIECES], c->ev[MA_T_CELLS + 1], c->ev[MA_T_PIECES + 1]);
+      if (MODE == MODE_KANTOROVICH && with_hessian) {
+        cudaEventElapsedTime(&c->t_ms[MA_T_REDUCE], c->ev[MA_T_PIECES + 1], c->ev[MA_T_REDUCE + 1]);
+        cudaEventElapsedTime(&c->t_ms[MA_T_CSR], c->ev[MA_T_REDUCE + 1], c->ev[MA_T_CSR + 1]);
+      }
+    }
+    if (c->stats) {
+      unsigned long long hc[CNT_N];
+      CK(cudaMemcpy(hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost));
+      for (int k = 0; k < CNT_N; ++k) c->host_counters[k] = (int64_t)hc[k];
+    }
+    c->have_eval = true;
+    c->have_hessian = (MODE == MODE_KANTOROVICH) && with_hessian;
+    return MA_OK;
+  }
+  return fail(c, MA_INVALID, "evaluation failed after capacity escalation");
+}
+
+}  // namespace
+
+extern "C" int ma_set_weights(ma_ctx *c, const double *w) {
+  NEED_CTX();
+  if (!w || c->N < 1) return fail(c, MA_INVALID, "ma_set_weights: bad arguments");
+  CK(cudaMemcpyAsync(c->w.p, w, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+  return MA_OK;
+}
+
+extern "C" int ma_evaluate(ma_ctx *c, int with_hessian) {
+  NEED_CTX();
+  return evaluate_mode<MODE_KANTOROVICH>(c, with_hessian != 0);
+}
+
+extern "C" int ma_kantorovich(ma_ctx *c, const double *w, double *fval, double *g, int *nnz) {
+  NEED_CTX();
+  CKR(ma_set_weights(c, w));
+  CKR(evaluate_mode<MODE_KANTOROVICH>(c, true));
+  if (fval) *fval = c->fval;
+  if (nnz) *nnz = c->nnz;
+  if (g) {
+    CKR(ensure(c, c->cg_out, (size_t)c->N * 8));
+    k_scatter_to_caller<<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->mass.as<double>(), c->perm.as<int>(), c->N,
+                                                               c->cg_out.as<double>());
+    CK(cudaMemcpyAsync(g, c->cg_out.p, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return MA_OK;
+}
+
+extern "C" int ma_get_hessian_csr(ma_ctx *c, int *rowptr, int *col, double *val) {
+  NEED_CTX();
+  if (!c->have_hessian) return fail(c, MA_INVALID, "no Hessian: call ma_kantorovich first");
+  if (!rowptr || !col || !val) return fail(c, MA_INVALID, "ma_get_hessian_csr: null output");
+  const int N = c->N;
+  CKR(ensure(c, c->scratch_i, (size_t)N * 4));
+  CKR(ensure(c, c->cptr, (size_t)(N + 1) * 4));
+  CKR(ensure(c, c->ccol, (size_t)std::max(c->nnz, 1) * 4));
+  CKR(ensure(c, c->cval, (size_t)std::max(c->nnz, 1) * 8));
+  k_rowcnt_to_caller<<<cdiv(N, 256), 256, 0, c->stream>>>(c->rowptr.as<int>(), c->pos.as<int>(), N,
+                                                          c->scratch_i.as<int>());
+  CKR(scan_i32(c, c->scratch_i.as<int>(), c->cptr.as<int>(), N));
+  k_csr_to_caller<<<cdiv(N, 128), 128, 0, c->stream>>>(N, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(),
+                                                       c->pos.as<int>(), c->perm.as<int>(), c->cptr.as<int>(),
+                                                       c->ccol.as<int>(), c->cval.as<double>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rowptr, c->cptr.p, (size_t)(N + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (c->nnz) {
+    CK(cudaMemcpyAsync(col, c->ccol.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(val, c->cval.p, (size_t)c->nnz * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return MA_OK;
+}
+
+extern "C" int ma_get_adjacency(ma_ctx *c, int *ptr, int *idx, int capacity) {
+  NEED_CTX();
+  if (!c->have_eval) return fail(c, MA_INVALID, "no evaluation yet");
+  const int N = c->N;
+  CKR(ensure(c, c->scratch_i, (size_t)N * 4));
+  CKR(ensure(c, c->cptr, (size_t)(N + 1) * 4));
+  k_adj_count<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->nbr_cnt.as<int>(), c->pos.as<int>(), c->scratch_i.as<int>());
+  CKR(scan_i32(c, c->scratch_i.as<int>(), c->cptr.as<int>(), N));
+  int total = 0;
+  CK(cudaMemcpyAsync(&total, c->cptr.as<int>() + N, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(ptr, c->cptr.p, (size_t)(N + 1) * 4, cudaMemcpyDeviceToHost));
+  if (!idx) return MA_OK;  // size query: ptr[N] is the number of entries
+  if (capacity < total) return fail(c, MA_INVALID, "adjacency needs %d entries", total);
+  CKR(ensure(c, c->ccol, (size_t)std::max(total, 1) * 4));
+  k_adj_fill<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->kmax, c->nbr.as<int>(), c->nbr_cnt.as<int>(), c->pos.as<int>(),
+                                                  c->perm.as<int>(), c->cptr.as<int>(), c->ccol.as<int>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(idx, c->ccol.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MA_OK;
+}
+
+// =============================================================================================
+// moments / lloyd
+// =============================================================================================
+extern "C" int ma_moments(ma_ctx *c, const double *w, int order, double *masses, double *m1, double *m2) {
+  NEED_CTX();
+  if (order != 1 && order != 2) return fail(c, MA_INVALID, "ma_moments: order must be 1 or 2");
+  if (order == 2 && !m2) return fail(c, MA_INVALID, "ma_moments: m2 is required for order 2");
+  CKR(ma_set_weights(c, w));
+  if (order == 1) CKR(evaluate_mode<MODE_MOMENTS1>(c, false));
+  else CKR(evaluate_mode<MODE_MOMENTS2>(c, false));
+  const int N = c->N;
+  std::vector<double> h((size_t)N * 6);
+  std::vector<int> perm(N);
+  CK(cudaMemcpy(h.data(), c->mom.p, h.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(perm.data(), c->perm.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < N; ++k) {
+    int i = perm[k];
+    const double *o = &h[6 * (size_t)k];
+    if (masses) masses[i] = o[0];
+    if (m1) { m1[i] = o[1]; m1[(size_t)N + i] = o[2]; }
+    if (order == 2) { m2[i] = o[3]; m2[(size_t)N + i] = o[4]; m2[2 * (size_t)N + i] = o[5]; }
+  }
+  return MA_OK;
+}
+
+extern "C" int ma_lloyd(ma_ctx *c, const double *w, double *masses, double *centroids) {
+  NEED_CTX();
+  if (!masses || !centroids) return fail(c, MA_INVALID, "ma_lloyd: null output");
+  CKR(ma_moments(c, w, 1, masses, centroids, nullptr));
+  const int N = c->N;
+  for (int i = 0; i < N; ++i) {  // lloyd.hpp:139-143
+    centroids[i] /= masses[i];
+    centroids[(size_t)N + i] /= masses[i];
+  }
+  return MA_OK;
+}
+
+// =============================================================================================
+// pieces
+// =============================================================================================
+extern "C" int ma_pieces_build(ma_ctx *c, const double *w, int *npieces, int *nvertices) {
+  NEED_CTX();
+  if (c->mesh_kind == MESH_NONE || c->N < 1) return fail(c, MA_INVALID, "mesh/points not set");
+  CKR(ma_set_weights(c, w));
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    CKR(alloc_eval(c));
+    const int N = c->N;
+    CKR(ensure(c, c->pc_count, (size_t)N * 8));
+    CKR(ensure(c, c->pc_off, ((size_t)2 * N + 1) * 4));
+    Params p;
+    fill_params(c, p);
+    p.stats = 0;
+    p.pc_count = c->pc_count.as<int>();
+    CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
+    CKR(run_cells(c, p));
+    CKR(launch_pieces_mode<MODE_PIECES_COUNT>(c, p));
+    int h_flags = 0;
+    CK(cudaMemcpyAsync(&h_flags, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h_flags & (FLAG_CELL_OVERFLOW | FLAG_PIECE_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
+      if (c->kmax >= 64) return fail(c, MA_INVALID, "polygon capacity exceeded");
+      c->kmax *= 2;
+      continue;
+    }
+    // interleaved (pieces, vertices) counts -> two exclusive scans done on the host (output stage)
+    std::vector<int> cnt((size_t)2 * N), off((size_t)2 * N);
+    CK(cudaMemcpy(cnt.data(), c->pc_count.p, cnt.size() * 4, cudaMemcpyDeviceToHost));
+    long long np = 0, nv = 0;
+    for (int i = 0; i < N; ++i) {
+      off[2 * (size_t)i] = (int)np; off[2 * (size_t)i + 1] = (int)nv;
+      np += cnt[2 * (size_t)i]; nv += cnt[2 * (size_t)i + 1];
+    }
+    if (nv > 0x7fffffffll) return fail(c, MA_INVALID, "too many piece vertices");
+    c->pc_np = (int)np; c->pc_nv = (int)nv;
+    CK(cudaMemcpy(c->pc_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    CKR(ensure(c, c->pc_cell, (size_t)std::max(c->pc_np, 1) * 4));
+    CKR(ensure(c, c->pc_face, (size_t)std::max(c->pc_np, 1) * 4));
+    CKR(ensure(c, c->pc_ptr, ((size_t)c->pc_np + 1) * 4));
+    CKR(ensure(c, c->pc_tag, (size_t)std::max(c->pc_nv, 1) * 4));
+    CKR(ensure(c, c->pc_xy, (size_t)std::max(c->pc_nv, 1) * 16));
+    p.pc_off = c->pc_off.as<int>();
+    p.pc_cell = c->pc_cell.as<int>(); p.pc_face = c->pc_face.as<int>(); p.pc_ptr = c->pc_ptr.as<int>();
+    p.pc_tag = c->pc_tag.as<int>(); p.pc_xy = c->pc_xy.as<double>();
+    CKR(launch_pieces_mode<MODE_PIECES_FILL>(c, p));
+    CK(cudaMemcpyAsync(c->pc_ptr.as<int>() + c->pc_np, &c->pc_nv, 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (npieces) *npieces = c->pc_np;
+    if (nvertices) *nvertices = c->pc_nv;
+    c->have_eval = true;
+    return MA_OK;
+  }
+  return fail(c, MA_INVALID, "pieces failed after capacity escalation");
+}
+
+extern "C" int ma_pieces_get(ma_ctx *c, int *cell, int *face, int *ptr, int *tag, double *xy) {
+  NEED_CTX();
+  const int np = c->pc_np, nv = c->pc_nv;
+  std::vector<int> perm(c->N), hc(std::max(np, 1)), ht(std::max(nv, 1));
+  CK(cudaMemcpy(perm.data(), c->perm.p, (size_t)c->N * 4, cudaMemcpyDeviceToHost));
+  if (np) {
+    CK(cudaMemcpy(hc.data(), c->pc_cell.p, (size_t)np * 4, cudaMemcpyDeviceToHost));
+    if (face) CK(cudaMemcpy(face, c->pc_face.p, (size_t)np * 4, cudaMemcpyDeviceToHost));
+  }
+  if (ptr) CK(cudaMemcpy(ptr, c->pc_ptr.p, ((size_t)np + 1) * 4, cudaMemcpyDeviceToHost));
+  if (nv) {
+    CK(cudaMemcpy(ht.data(), c->pc_tag.p, (size_t)nv * 4, cudaMemcpyDeviceToHost));
+    if (xy) CK(cudaMemcpy(xy, c->pc_xy.p, (size_t)nv * 16, cudaMemcpyDeviceToHost));
+  }
+  if (cell) for (int k = 0; k < np; ++k) cell[k] = perm[hc[k]];
+  if (tag) for (int k = 0; k < nv; ++k) tag[k] = ht[k] >= 0 ? perm[ht[k]] : -1;
+  return MA_OK;
+}
+
+// =============================================================================================
+// K5: PCG + Newton
+// =============================================================================================
+namespace {
+
+// Solve H d = sign * g on the device (internal order), grounded at `ground`.  d_out may alias nothing.
+int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double *val, const double *g, double sign,
+              int ground, double *d_out, int *iters_out, double *relres_out) {
+  PcgState s;
+  const int nblocks = std::min(PCG_MAX_BLOCKS, std::max(1, cdiv(n, PCG_NT)));
+  CKR(ensure(c, c->dinv, (size_t)n * 8)); CKR(ensure(c, c->cgx, (size_t)n * 8)); CKR(ensure(c, c->cgr, (size_t)n * 8));
+  CKR(ensure(c, c->cgz, (size_t)n * 8)); CKR(ensure(c, c->cgp0, (size_t)n * 8)); CKR(ensure(c, c->cgp1, (size_t)n * 8));
+  CKR(ensure(c, c->cgq, (size_t)n * 8));
+  CKR(ensure(c, c->part_pq, (size_t)nblocks * 8)); CKR(ensure(c, c->part_rz, (size_t)2 * nblocks * 8));
+  CKR(ensure(c, c->part_rr, (size_t)nblocks * 8)); CKR(ensure(c, c->scal, 64)); CKR(ensure(c, c->cgflag, 16));
+  s.n = n; s.ground = ground; s.rowptr = rowptr; s.col = col; s.val = val;
+  s.dinv = c->dinv.as<double>(); s.x = c->cgx.as<double>(); s.r = c->cgr.as<double>(); s.z = c->cgz.as<double>();
+  s.p[0] = c->cgp0.as<double>(); s.p[1] = c->cgp1.as<double>(); s.q = c->cgq.as<double>();
+  s.part_pq = c->part_pq.as<double>(); s.part_rz = c->part_rz.as<double>(); s.part_rr = c->part_rr.as<double>();
+  s.scal = c->scal.as<double>(); s.nblocks = nblocks; s.flag = c->cgflag.as<int>();
+  CK(cudaMemsetAsync(c->cgflag.p, 0, 16, c->stream));
+  CK(cudaMemsetAsync(c->part_rz.p, 0, (size_t)2 * nblocks * 8, c->stream));
+  k_pcg_init<<<nblocks, PCG_NT, 0, c->stream>>>(s, g, sign);
+  k_pcg_init2<<<1, PCG_NT, 0, c->stream>>>(s);
+  CK(cudaGetLastError());
+  double h_scal[4];
+  int h_flag = 0;
+  CK(cudaMemcpyAsync(h_scal, c->scal.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&h_flag, c->cgflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (h_flag & 1) {
+    fail(c, MA_SINGULAR_HESSIAN, "Error: hessian of Kantorovich's functional is not invertible (zero diagonal)");
+    return MA_SINGULAR_HESSIAN;
+  }
+  const double gg = h_scal[2];
+  int it = 0;
+  double rr = gg;
+  if (gg > 0) {
+    const int batch = 32;  // even, so iteration parity is the same in every graph launch
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    for (int b = 0; b < batch; ++b) {
+      // iteration 0 of the very first batch must use beta = 0: p_old is zero-initialised and
+      // part_rz parity 0 is zero, so beta = 0/rz = 0 falls out without a special case
+      k_pcg_A<<<nblocks, PCG_NT, 0, c->stream>>>(s, b + 2);
+      k_pcg_B<<<nblocks, PCG_NT, 0, c->stream>>>(s, b + 2);
+    }
+    k_pcg_rr<<<1, PCG_NT, 0, c->stream>>>(s);
+    CK(cudaStreamEndCapture(c->stream, &graph));
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    const double tol2 = c->cg_rtol * c->cg_rtol * gg;
+    while (it < c->cg_maxit) {
+      CK(cudaGraphLaunch(exec, c->stream));
+      CK(cudaMemcpyAsync(&rr, c->scal.as<double>() + 3, 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      it += batch;
+      if (!(rr > tol2)) break;  // also stops on NaN
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+  }
+  if (d_out) CK(cudaMemcpyAsync(d_out, s.x, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  if (iters_out) *iters_out = it;
+  if (relres_out) *relres_out = gg > 0 ? std::sqrt(rr / gg) : 0.0;
+  c->last_cg_iters = it;
+  if (!(rr == rr)) return fail(c, MA_LINSOLVE_RESIDUAL, "PCG produced NaN");
+  return MA_OK;
+}
+
+}  // namespace
+
+extern "C" int ma_solve_laplacian(ma_ctx *c, int N, const int *rowptr, const int *col, const double *val,
+                                  const double *g, double *d, int *iters) {
+  NEED_CTX();
+  if (N < 1 || !rowptr || !col || !val || !g || !d) return fail(c, MA_INVALID, "ma_solve_laplacian: bad arguments");
+  const int nnz = rowptr[N];
+  Buf b_ptr, b_col, b_val, b_g, b_d;
+  int rc = MA_OK;
+  do {
+    if ((rc = upload(c, b_ptr, rowptr, (size_t)(N + 1) * 4))) break;
+    if ((rc = upload(c, b_col, col, (size_t)std::max(nnz, 1) * 4))) break;
+    if ((rc = upload(c, b_val, val, (size_t)std::max(nnz, 1) * 8))) break;
+    if ((rc = upload(c, b_g, g, (size_t)N * 8))) break;
+    if ((rc = ensure(c, b_d, (size_t)N * 8))) break;
+    int it = 0;
+    double relres = 0;
+    rc = pcg_solve(c, N, b_ptr.as<int>(), b_col.as<int>(), b_val.as<double>(), b_g.as<double>(), 1.0, N - 1,
+                   b_d.as<double>(), &it, &relres);
+    if (iters) *iters = it;
+    if (rc != MA_OK && rc != MA_SINGULAR_HESSIAN) break;
+    if (rc == MA_SINGULAR_HESSIAN) { std::fill(d, d + N, 0.0); break; }
+    if (cudaMemcpyAsync(d, b_d.p, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      rc = fail(c, MA_CUDA_ERROR, "copy of the solution failed");
+      break;
+    }
+    if (relres > 1e-7 && relres * 0 == 0) {  // optimal_transport.hpp:68-71 (absolute there; relative here)
+      rc = fail(c, MA_LINSOLVE_RESIDUAL, "WARNING: in solve_laplacian_matrix: relative residual=%g after %d iterations",
+                relres, it);
+    }
+  } while (0);
+  release(b_ptr); release(b_col); release(b_val); release(b_g); release(b_d);
+  return rc;
+}
+
+extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_initial, double eps_g, size_t maxiter,
+                           int verbose, ma_statistics *stats) {
+  NEED_CTX();
+  if (!nu || !w) return fail(c, MA_INVALID, "ma_ot_solve: null argument");
+  if (c->mesh_kind == MESH_NONE || c->N < 1) return fail(c, MA_INVALID, "mesh/points not set");
+  auto t0 = std::chrono::steady_clock::now();
+  const int N = c->N;
+  size_t neval = 0, niter = 0, cg_total = 0;
+  CKR(ensure(c, c->nu_s, (size_t)N * 8)); CKR(ensure(c, c->x0_s, (size_t)N * 8));
+  CKR(ensure(c, c->d_s, (size_t)N * 8)); CKR(ensure(c, c->g_s, (size_t)N * 8));
+  CKR(ensure(c, c->scratch_d, (size_t)N * 8));
+  CKR(ensure(c, c->red_out, 16 * sizeof(double)));
+  // nu in caller order on the device (scratch_d), then sorted copy nu_s
+  CK(cudaMemcpyAsync(c->scratch_d.p, nu, (size_t)N * 8, cudaMemcpyHostToDevice, c->stream));
+  k_gather<<<cdiv(N, 256), 256, 0, c->stream>>>(c->scratch_d.as<double>(), c->perm.as<int>(), N, c->nu_s.as<double>());
+  // x: caller-order device weights live in c->w (what the evaluation reads)
+  if (have_initial) CK(cudaMemcpyAsync(c->w.p, w, (size_t)N * 8, cudaMemcpyHostToDevice, c->stream));
+  else CK(cudaMemsetAsync(c->w.p, 0, (size_t)N * 8, c->stream));  // :125-128
+  double nu_red[4], x_dot_nu = 0, gnorm = 0, mmin = 0, fx = 0;
+  CKR(reduce4(c, c->nu_s.as<double>(), nullptr, N, c->red_out.as<double>() + 8));
+  CK(cudaMemcpyAsync(nu_red, c->red_out.as<double>() + 8, sizeof nu_red, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const double nu_min = nu_red[2];
+
+  // f(x): evaluation + (m, g = m - nu, f - nu.x)   optimal_transport.hpp:110-120
+  auto feval = [&]() -> int {
+    ++neval;
+    CKR(evaluate_mode<MODE_KANTOROVICH>(c, true));
+    // ws is the sorted copy of the weights used by this evaluation
+    k_sub<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->mass.as<double>(), c->nu_s.as<double>(), c->g_s.as<double>());
+    CKR(reduce4(c, c->g_s.as<double>(), nullptr, N, c->red_out.as<double>()));
+    CKR(reduce4(c, c->ws.as<double>(), c->nu_s.as<double>(), N, c->red_out.as<double>() + 4));
+    double red[8];
+    CK(cudaMemcpyAsync(red, c->red_out.p, sizeof red, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    gnorm = std::sqrt(red[1]);
+    x_dot_nu = red[5];
+    mmin = c->mass_min;
+    fx = c->fval - x_dot_nu;
+    return MA_OK;
+  };
+  auto finish = [&](int rc) {
+    if (stats) {
+      stats->niter = niter; stats->neval = neval; stats->cg_iters = cg_total;
+      stats->final_norm = gnorm; stats->fval = fx;
+      stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return rc;
+  };
+
+  CKR(feval());  // :131
+  const double eps0 = std::min(mmin, nu_min) / 2;  // :137-138
+  if (!(eps0 > 0)) {                              // :139-148
+    if (verbose) fprintf(stderr, "Error: computed minimum mass is non-positive\n");
+    fail(c, MA_EMPTY_CELL, "computed minimum mass is non-positive: a Laguerre cell is empty at the initial point");
+    return finish(MA_EMPTY_CELL);  // w is left untouched (= initial guess)
+  }
+  const int ground = [&]() {
+    int g = 0;
+    cudaMemcpy(&g, c->pos.as<int>() + (N - 1), 4, cudaMemcpyDeviceToHost);  // last index of the caller's ordering (T7)
+    return g;
+  }();
+  int rc_final = MA_OK;
+  while (gnorm >= eps_g && niter++ <= maxiter) {  // :150-151 (including the maxiter+1 quirk, T6)
+    int it = 0;
+    double relres = 0;
+    // d = -solve_laplacian_matrix(h, g)   :153   (internal order)
+    int rc = pcg_solve(c, N, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(), c->g_s.as<double>(), -1.0,
+                       ground, c->d_s.as<double>(), &it, &relres);
+    cg_total += it;
+    if (rc != MA_OK) return finish(rc);
+    if (verbose && relres > 1e-7) fprintf(stderr, "WARNING: in solve_laplacian_matrix: relres=%g\n", relres);
+    double alpha = 1;
+    const double n0 = gnorm;
+    // x0 (sorted) = ws of the last evaluation
+    CK(cudaMemcpyAsync(c->x0_s.p, c->ws.p, (size_t)N * 8, cudaMemcpyDeviceToDevice, c->stream));
+    size_t nls = 0;
+    while (true) {  // :163-176
+      // x = x0 + alpha d, written in caller order into c->w
+      k_axpy_to<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->x0_s.as<double>(), alpha, c->d_s.as<double>(),
+                                                     c->scratch_d.as<double>());
+      k_scatter_to_caller<<<cdiv(N, 256), 256, 0, c->stream>>>(c->scratch_d.as<double>(), c->perm.as<int>(), N,
+                                                               c->w.as<double>());
+      CKR(feval());
+      if (mmin >= eps0 && gnorm <= (1 - alpha / 2) * n0) break;
+      alpha *= .5;
+      if (verbose) fprintf(stderr, "subit %zu.%zu: min(masses)=%g\n", niter, nls++, mmin);
+      if (alpha < 1e-30) {
+        rc_final = fail(c, MA_NOT_CONVERGED, "line search failed (alpha underflow)");
+        break;
+      }
+    }
+    if (verbose)
+      fprintf(stderr, "it %zu: f=%.15g |df|=%g min(m)=%g tau = %g eval = %zu cg = %d\n", niter, fx, gnorm, nu_min,
+              alpha, neval, it);
+    if (rc_final != MA_OK) break;
+  }
+  CK(cudaMemcpyAsync(w, c->w.p, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (rc_final == MA_OK && gnorm >= eps_g) rc_final = fail(c, MA_NOT_CONVERGED, "maxiter reached with |g|=%g", gnorm);
+  return finish(rc_final);
+}
+
+// =============================================================================================
+// instrumentation
+// =============================================================================================
+extern "C" int ma_set_profiling(ma_ctx *c, int on) { if (!c) return MA_INVALID; c->profiling = on; return MA_OK; }
+extern "C" int ma_set_stats(ma_ctx *c, int on) { if (!c) return MA_INVALID; c->stats = on; return MA_OK; }
+extern "C" int ma_get_timings(ma_ctx *c, float *ms) {
+  if (!c || !ms) return MA_INVALID;
+  for (int k = 0; k < MA_T_COUNT; ++k) ms[k] = c->t_ms[k];
+  return MA_OK;
+}
+extern "C" int ma_get_counters(ma_ctx *c, int64_t *out) {
+  if (!c || !out) return MA_INVALID;
+  for (int k = 0; k < CNT_N; ++k) out[k] = c->host_counters[k];
+  return MA_OK;
+}
+extern "C" int ma_flush_l2(ma_ctx *c, size_t bytes) {
+  NEED_CTX();
+  CKR(ensure(c, c->flush, bytes));
+  k_fill_bytes<<<c->sm_count * 4, 256, 0, c->stream>>>(c->flush.as<unsigned long long>(), bytes / 8, 0x0123456789abcdefull);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return MA_OK;
+}
+extern "C" int ma_measure_fp64_peak(ma_ctx *c, double *flops_per_s) {
+  NEED_CTX();
+  if (!flops_per_s) return MA_INVALID;
+  CKR(ensure(c, c->red_out, 16 * sizeof(double)));
+  const int iters = 1 << 15, blocks = c->sm_count * 8;
+  cudaEvent_t a = c->ev[0], b = c->ev[1];
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(a, c->stream));
+    k_dfma_probe<<<blocks, 256, 0, c->stream>>>(c->red_out.as<double>(), iters, 1.0000001, 1e-9);
+    CK(cudaEventRecord(b, c->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    double fl = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, fl);
+  }
+  *flops_per_s = best;
+  return MA_OK;
+}

@@ -1,0 +1,429 @@
+// ma_cell.cuh — per-thread / per-lane work of the two evaluation kernels, written as
+// __host__ __device__ functions so that tests/emu can run the very same code serially on the CPU.
+//
+//   cell_build   (K2)  replaces CGAL Regular_triangulation_2's neighbour circulator
+//                      (kantorovich.hpp:65-72, vti.hpp:265): builds the power cell of Dirac i inside
+//                      the mesh bounding box by clipping against candidate sites found by a
+//                      nearest-first walk over a quadtree of Morton-ordered bins, pruned with the
+//                      per-node maximum weight ("security radius").
+//   lane_pieces  (K3)  replaces the overlay traversal + callbacks (vti.hpp:250-305,
+//                      kantorovich.hpp:87-136, lloyd.hpp:48-68,91-122): one lane clips candidate
+//                      triangles against the cell's half-plane table and integrates the pieces.
+#pragma once
+#include "ma_geom.cuh"
+
+namespace ma {
+
+enum { MESH_NONE = 0, MESH_GENERAL = 1, MESH_GRID = 2 };
+enum { MODE_KANTOROVICH = 0, MODE_MOMENTS1 = 1, MODE_MOMENTS2 = 2, MODE_PIECES_COUNT = 3, MODE_PIECES_FILL = 4 };
+enum { FLAG_CELL_OVERFLOW = 1, FLAG_PIECE_OVERFLOW = 2, FLAG_KMAX_OVERFLOW = 4, FLAG_STACK_OVERFLOW = 8 };
+enum { CNT_PIECES = 0, CNT_VERTS = 1, CNT_NEWV = 2, CNT_LEDGES = 3, CNT_SUMK = 4, CNT_SUMKNP = 5, CNT_FALLBACK = 6,
+       CNT_CAND = 7, CNT_N = 8 };
+
+struct Params {
+  // Diracs, Morton-bin order
+  int N;
+  const double *xs, *ys, *ws;
+  // quadtree of bins over the Diracs: level l has 4^l nodes, node (l, code) covers a square of side
+  // ph * 2^(L-l); wmax holds all levels, level l at offset (4^l - 1) / 3.
+  int L;
+  double px0, py0, ph;
+  const int *bin_start;
+  const double *wmax;
+  // mesh bounding box
+  double bb[4];
+  // source mesh
+  int mesh_kind;
+  int nF;
+  const double *abc;
+  // grid mesh
+  int gn, gm;
+  double gx0, gy0, gdx, gdy;
+  // general mesh + its face bins
+  const double *vx, *vy;
+  const int *tri;
+  int tg;  // bins per side
+  double tinvx, tinvy;
+  const int *tbin_ptr, *tbin_face;
+  // K2 outputs
+  int kmax;
+  int *nbr;         // N * kmax, -1 padded, CCW
+  int *nbr_cnt;     // N, -1 = empty cell
+  double *cell_bb;  // N * 4 (absolute xmin, ymin, xmax, ymax)
+  // K3 outputs
+  double *mass;     // N
+  double *fcell;    // N: m_i w_i - cost_i
+  double *hslot;    // N * kmax: sum over pieces of (edge integral / (2 |y_i - y_j|)) per neighbour slot
+  unsigned long long *touched;  // N: bit s set iff slot s received an edge
+  int *rowcnt;      // N
+  double *mom;      // N * 6 (moments modes)
+  // pieces dump
+  int *pc_count;    // N * 2 (pieces, vertices) per cell              (MODE_PIECES_COUNT)
+  const int *pc_off;  // N * 2 exclusive offsets                      (MODE_PIECES_FILL)
+  int *pc_cell, *pc_face, *pc_ptr, *pc_tag;
+  double *pc_xy;
+  // instrumentation
+  unsigned long long *counters;  // CNT_N, only when stats != 0
+  int stats;
+  int *flags;
+  double filter_tol;  // relative threshold below which a sign goes to the double-double fallback
+};
+
+// ------------------------------------------------------------------------------------------------
+// K2: power cell of Dirac i in the mesh box.  Returns n (0 = empty, -1 = capacity overflow).
+// ------------------------------------------------------------------------------------------------
+template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT> &P, int maxv, int *flags_out) {
+  const double xi = p.xs[i], yi = p.ys[i], wi = p.ws[i];
+  const double bx0 = p.bb[0] - xi, by0 = p.bb[1] - yi, bx1 = p.bb[2] - xi, by1 = p.bb[3] - yi;
+  P.X(0) = bx0; P.Y(0) = by0; P.T(0) = -1;  // bottom
+  P.X(1) = bx1; P.Y(1) = by0; P.T(1) = -2;  // right
+  P.X(2) = bx1; P.Y(2) = by1; P.T(2) = -3;  // top
+  P.X(3) = bx0; P.Y(3) = by1; P.T(3) = -4;  // left
+  int n = 4;
+  double R2 = fmax(bx0 * bx0, bx1 * bx1) + fmax(by0 * by0, by1 * by1);
+  auto lineof = [&](int tag, double &nx, double &ny, double &cl) {
+    if (tag >= 0) {
+      double Dx = p.xs[tag] - xi, Dy = p.ys[tag] - yi;
+      nx = Dx; ny = Dy;
+      cl = 0.5 * (Dx * Dx + Dy * Dy + (wi - p.ws[tag]));
+    } else if (tag == -1) { nx = 0; ny = 1; cl = by0; }
+    else if (tag == -2) { nx = 1; ny = 0; cl = bx1; }
+    else if (tag == -3) { nx = 0; ny = 1; cl = by1; }
+    else { nx = 1; ny = 0; cl = bx0; }
+  };
+  const double NEG_INF = -1.0 / 0.0;
+  unsigned stk[52];
+  int sp = 0;
+  stk[sp++] = 0u;
+  while (sp > 0 && n > 0) {
+    unsigned e = stk[--sp];
+    int l = (int)(e >> 26);
+    unsigned code = e & 0x3ffffffu;
+    double wm = p.wmax[(((size_t)1 << (2 * l)) - 1) / 3 + code];
+    if (wm == NEG_INF) continue;
+    double S = p.ph * (double)(1u << (p.L - l));
+    double ox = p.px0 + (double)morton_compact1(code) * S - xi;
+    double oy = p.py0 + (double)morton_compact1(code >> 1) * S - yi;
+    double dx = fmax(fmax(ox, -(ox + S)), 0.0), dy = fmax(fmax(oy, -(oy + S)), 0.0);
+    double d2 = dx * dx + dy * dy;
+    if (d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) continue;
+    if (l < p.L) {
+      // children, nearest first (pushed in reverse)
+      double cx = ox + 0.5 * S, cy = oy + 0.5 * S;
+      unsigned q0 = (cx <= 0.0 ? 1u : 0u) | (cy <= 0.0 ? 2u : 0u);
+      bool xfirst = fabs(cx) < fabs(cy);
+      unsigned q1 = q0 ^ (xfirst ? 1u : 2u), q2 = q0 ^ (xfirst ? 2u : 1u), q3 = q0 ^ 3u;
+      unsigned base = ((unsigned)(l + 1) << 26) | (code << 2);
+      if (sp + 4 > 52) { *flags_out |= FLAG_STACK_OVERFLOW; return -1; }
+      stk[sp++] = base | q3; stk[sp++] = base | q2; stk[sp++] = base | q1; stk[sp++] = base | q0;
+      continue;
+    }
+    const int b0 = p.bin_start[code], b1 = p.bin_start[code + 1];
+    for (int j = b0; j < b1 && n > 0; ++j) {
+      if (j == i) continue;
+      double Dx = p.xs[j] - xi, Dy = p.ys[j] - yi, wj = p.ws[j];
+      double dd2 = Dx * Dx + Dy * Dy;
+      if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
+        if (wj > wi || (wj == wi && j < i)) n = 0;
+        continue;
+      }
+      double s = dd2 + (wi - wj);
+      if (s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12)) continue;  // bisector beyond every vertex
+      double c = 0.5 * s;
+      unsigned long long in = 0ull;
+      for (int k = 0; k < n; ++k)
+        if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
+      unsigned long long full = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+      if (in == full) continue;
+      if (in == 0ull) { n = 0; break; }
+      int n2 = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, j, lineof);
+      if (n2 < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
+      n = n2;
+      R2 = 0.0;
+      for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
+    }
+  }
+  return n;
+}
+
+// writes the neighbour list / bounding box of a built cell
+template <int NT> MA_DEV void cell_emit(const Params &p, int i, const PolyRef<NT> &P, int n) {
+  const double xi = p.xs[i], yi = p.ys[i];
+  int *nb = p.nbr + (size_t)i * p.kmax;
+  int cnt = 0;
+  double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+  for (int k = 0; k < n; ++k) {
+    int t = P.T(k);
+    if (t >= 0) {
+      if (cnt < p.kmax) nb[cnt] = t;
+      ++cnt;
+    }
+    x0 = fmin(x0, P.X(k)); x1 = fmax(x1, P.X(k));
+    y0 = fmin(y0, P.Y(k)); y1 = fmax(y1, P.Y(k));
+  }
+  if (cnt > p.kmax) {
+    *p.flags |= FLAG_KMAX_OVERFLOW;  // benign race: every writer ORs the same bit in
+    cnt = p.kmax;
+  }
+  for (int k = cnt; k < p.kmax; ++k) nb[k] = -1;
+  p.nbr_cnt[i] = (n <= 0) ? -1 : cnt;
+  double *bb = p.cell_bb + 4 * (size_t)i;
+  bb[0] = x0 + xi; bb[1] = y0 + yi; bb[2] = x1 + xi; bb[3] = y1 + yi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------
+// Per-cell half-plane table (shared memory on the GPU): slot s is neighbour J[s] with bisector
+// { u . (Dx,Dy) = C } and Hessian scale S = 1 / (2 |y_i - y_j|) (kantorovich.hpp:118-119).
+struct CellTable {
+  double *Dx, *Dy, *C, *S;
+  int *J;
+  int k;
+};
+
+MA_DEV void cell_table_fill(const Params &p, int i, int s, const CellTable &T) {
+  int j = p.nbr[(size_t)i * p.kmax + s];
+  double Dx = p.xs[j] - p.xs[i], Dy = p.ys[j] - p.ys[i];
+  double d2 = Dx * Dx + Dy * Dy;
+  T.J[s] = j;
+  T.Dx[s] = Dx;
+  T.Dy[s] = Dy;
+  T.C[s] = 0.5 * (d2 + (p.ws[i] - p.ws[j]));
+  T.S[s] = 0.5 / sqrt(d2);
+}
+
+struct LaneAcc {
+  double mass, cost;
+  double m[5];  // ∫ρ ux, ∫ρ uy, ∫ρ ux², ∫ρ uy², ∫ρ ux uy (local coordinates)
+  unsigned long long touched;
+  unsigned long long cnt[CNT_N];
+  int npieces, nverts;  // pieces modes
+};
+
+struct Tri {  // one candidate face: global vertex coordinates + id
+  double gx[3], gy[3];
+  int f;
+};
+
+// Clip triangle t (local coordinates already in P, tags -1,-2,-3 for edges a->b, b->c, c->a) by the
+// k half-planes of the cell.  Returns the vertex count of the piece (0 = empty, -1 overflow).
+template <int NT>
+MA_DEV int piece_clip(const Params &p, const PolyRef<NT> &P, int maxv, const CellTable &T, const Tri &t, double xi,
+                      double yi, double wi, LaneAcc &acc) {
+  int n = 3;
+  const double ax = t.gx[0] - xi, ay = t.gy[0] - yi, bx = t.gx[1] - xi, by = t.gy[1] - yi, cx = t.gx[2] - xi,
+               cy = t.gy[2] - yi;
+  P.X(0) = ax; P.Y(0) = ay; P.T(0) = -1;
+  P.X(1) = bx; P.Y(1) = by; P.T(1) = -2;
+  P.X(2) = cx; P.Y(2) = cy; P.T(2) = -3;
+  auto lineof = [&](int tag, double &nx, double &ny, double &cl) {
+    if (tag >= 0) { nx = T.Dx[tag]; ny = T.Dy[tag]; cl = T.C[tag]; }
+    else {
+      double px = tag == -1 ? ax : (tag == -2 ? bx : cx), py = tag == -1 ? ay : (tag == -2 ? by : cy);
+      double qx = tag == -1 ? bx : (tag == -2 ? cx : ax), qy = tag == -1 ? by : (tag == -2 ? cy : ay);
+      nx = py - qy; ny = qx - px; cl = nx * px + ny * py;
+    }
+  };
+  // exact-ish line of an edge tag from the ORIGINAL inputs (double-double)
+  auto ddlineof = [&](int tag) -> ddline {
+    if (tag >= 0) { int j = T.J[tag]; return dd_bisector(xi, yi, wi, p.xs[j], p.ys[j], p.ws[j]); }
+    int a = -1 - tag, b = (a == 2) ? 0 : a + 1;
+    return dd_mesh_edge(xi, yi, t.gx[a], t.gy[a], t.gx[b], t.gy[b]);
+  };
+  for (int s = 0; s < T.k && n > 0; ++s) {
+    const double Dx = T.Dx[s], Dy = T.Dy[s], c = T.C[s];
+    unsigned long long in = 0ull;
+    for (int k = 0; k < n; ++k) {
+      double tx = P.X(k) * Dx, ty = P.Y(k) * Dy;
+      double val = c - (tx + ty);
+      bool inside = val > 0.0;
+      if (fabs(val) <= p.filter_tol * (fabs(c) + fabs(tx) + fabs(ty))) {
+        // filtered predicate failed: decide from the original data (Side1 / Side2 / Side3,
+        // predicates.hpp:73-135); ties are outside (strict "== SMALLER", App. B T3)
+        acc.cnt[CNT_FALLBACK]++;
+        int tb = P.T(k), ta = P.T(k == 0 ? n - 1 : k - 1);
+        ddline Lt = ddlineof(s);
+        int sg;
+        if (ta < 0 && tb < 0) {
+          int v = -1 - tb;  // edge tb starts at triangle vertex (-1-tb); edge ta ends there
+          sg = dd_side_point(xi, yi, t.gx[v], t.gy[v], Lt);
+        } else {
+          sg = dd_side(ddlineof(ta), ddlineof(tb), Lt);
+        }
+        inside = sg > 0;
+      }
+      if (inside) in |= 1ull << k;
+    }
+    unsigned long long full = (1ull << n) - 1ull;
+    if (in == full) continue;
+    if (in == 0ull) { n = 0; break; }
+    n = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, s, lineof);
+    if (n < 0) return -1;
+  }
+  return n;
+}
+
+// kantorovich.hpp:105-135 on one piece; rho(u) = a ux + b uy + r0 in local coordinates.
+template <int NT>
+MA_DEV void piece_kantorovich(const PolyRef<NT> &P, int n, double a, double b, double r0, const CellTable &T,
+                              double *hacc, int hstride, LaneAcc &acc) {
+  for (int k = 0; k < n; ++k) {  // Hessian: midpoint rule on every Laguerre edge (:110-122, quadrature.hpp:79-85)
+    int tg = P.T(k);
+    if (tg < 0) continue;
+    int kk = (k + 1 == n) ? 0 : k + 1;
+    double x0 = P.X(k), y0 = P.Y(k), x1 = P.X(kk), y1 = P.Y(kk);
+    double ex = x1 - x0, ey = y1 - y0;
+    double r = sqrt(ex * ex + ey * ey) * (a * (0.5 * (x0 + x1)) + b * (0.5 * (y0 + y1)) + r0);
+    hacc[tg * hstride] += r * T.S[tg];
+    acc.touched |= 1ull << tg;
+    acc.cnt[CNT_LEDGES]++;
+  }
+  const double x0 = P.X(0), y0 = P.Y(0);
+  double mass = 0.0, cost = 0.0;
+  for (int q = 1; q + 1 < n; ++q) {  // fan from vertex 0 (quadrature.hpp:128-129, 140-141)
+    double x1 = P.X(q), y1 = P.Y(q), x2 = P.X(q + 1), y2 = P.Y(q + 1);
+    double A = 0.5 * ((x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0));
+    const double third = 1.0 / 3.0;
+    mass += A * (a * ((x0 + x1 + x2) * third) + b * ((y0 + y1 + y2) * third) + r0);  // centroid rule (:69-77)
+    double s = 0.0;
+    albrecht_collatz_points(x0, y0, x1, y1, x2, y2, [&](double x, double y, double w) {
+      s += w * ((a * x + b * y + r0) * (x * x + y * y));  // fv(p) * |p - y_v|^2 (kantorovich.hpp:126-131)
+    });
+    cost += A * s;
+  }
+  acc.mass += mass;
+  acc.cost += cost;
+}
+
+// lloyd.hpp:57-67 / :100-121 on one piece, in local coordinates (shifted to global by the caller).
+template <int NT, int ORDER>
+MA_DEV void piece_moments(const PolyRef<NT> &P, int n, double a, double b, double r0, LaneAcc &acc) {
+  const double x0 = P.X(0), y0 = P.Y(0);
+  for (int q = 1; q + 1 < n; ++q) {
+    double x1 = P.X(q), y1 = P.Y(q), x2 = P.X(q + 1), y2 = P.Y(q + 1);
+    double A = 0.5 * ((x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0));
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0;
+    albrecht_collatz_points(x0, y0, x1, y1, x2, y2, [&](double x, double y, double w) {
+      double fp = w * (a * x + b * y + r0);
+      s0 += fp; s1 += fp * x; s2 += fp * y;
+      if (ORDER == 2) { s3 += fp * x * x; s4 += fp * y * y; s5 += fp * x * y; }
+    });
+    acc.mass += A * s0; acc.m[0] += A * s1; acc.m[1] += A * s2;
+    if (ORDER == 2) { acc.m[2] += A * s3; acc.m[3] += A * s4; acc.m[4] += A * s5; }
+  }
+}
+
+template <int NT> MA_DEV void piece_stats(const PolyRef<NT> &P, int n, int k, LaneAcc &acc) {
+  acc.cnt[CNT_PIECES]++;
+  acc.cnt[CNT_VERTS] += n;
+  acc.cnt[CNT_SUMKNP] += (unsigned long long)k * n;
+  for (int q = 0; q < n; ++q) {
+    int ta = P.T(q == 0 ? n - 1 : q - 1), tb = P.T(q);
+    if (!(ta < 0 && tb < 0)) acc.cnt[CNT_NEWV]++;
+  }
+}
+
+// process one candidate face
+template <int NT, int MODE>
+MA_DEV void lane_face(const Params &p, int i, const PolyRef<NT> &P, int maxv, const CellTable &T, const Tri &t,
+                      double xi, double yi, double wi, double *hacc, int hstride, LaneAcc &acc, int lane_piece_base,
+                      int lane_vert_base) {
+  if (p.stats) acc.cnt[CNT_CAND]++;
+  int n = piece_clip<NT>(p, P, maxv, T, t, xi, yi, wi, acc);
+  if (n < 0) { *p.flags |= FLAG_PIECE_OVERFLOW; return; }
+  if (n < 3) return;
+  if (p.stats) piece_stats<NT>(P, n, T.k, acc);
+  if (MODE == MODE_PIECES_COUNT) { acc.npieces++; acc.nverts += n; return; }
+  if (MODE == MODE_PIECES_FILL) {
+    int pi = lane_piece_base + acc.npieces, vi = lane_vert_base + acc.nverts;
+    p.pc_cell[pi] = i;
+    p.pc_face[pi] = t.f;
+    p.pc_ptr[pi] = vi;
+    for (int k = 0; k < n; ++k) {
+      p.pc_xy[2 * (size_t)(vi + k)] = P.X(k) + xi;
+      p.pc_xy[2 * (size_t)(vi + k) + 1] = P.Y(k) + yi;
+      int tg = P.T(k);
+      p.pc_tag[vi + k] = tg >= 0 ? T.J[tg] : -1;
+    }
+    acc.npieces++; acc.nverts += n;
+    return;
+  }
+  const double a = p.abc[3 * (size_t)t.f], b = p.abc[3 * (size_t)t.f + 1], c0 = p.abc[3 * (size_t)t.f + 2];
+  const double r0 = c0 + a * xi + b * yi;
+  if (MODE == MODE_KANTOROVICH) piece_kantorovich<NT>(P, n, a, b, r0, T, hacc, hstride, acc);
+  if (MODE == MODE_MOMENTS1) piece_moments<NT, 1>(P, n, a, b, r0, acc);
+  if (MODE == MODE_MOMENTS2) piece_moments<NT, 2>(P, n, a, b, r0, acc);
+}
+
+// All candidate faces of cell i handled by `lane` out of `nlanes` (round-robin).  For the pieces
+// modes each lane's output range is [lane_piece_base, ...) computed by the caller.
+template <int NT, int MODE>
+MA_DEV void lane_pieces(const Params &p, int i, int lane, int nlanes, const PolyRef<NT> &P, int maxv,
+                        const CellTable &T, double *hacc, int hstride, LaneAcc &acc, int lane_piece_base = 0,
+                        int lane_vert_base = 0) {
+  const double xi = p.xs[i], yi = p.ys[i], wi = p.ws[i];
+  const double *cb = p.cell_bb + 4 * (size_t)i;
+  Tri t;
+  if (p.mesh_kind == MESH_GRID) {
+    // squares overlapped by the cell's bounding box
+    const double pad = 1e-12;
+    int i0 = (int)floor((cb[0] - p.gx0) / p.gdx - pad), i1 = (int)floor((cb[2] - p.gx0) / p.gdx + pad);
+    int j0 = (int)floor((cb[1] - p.gy0) / p.gdy - pad), j1 = (int)floor((cb[3] - p.gy0) / p.gdy + pad);
+    i0 = max(i0, 0); j0 = max(j0, 0);
+    i1 = min(i1, p.gn - 2); j1 = min(j1, p.gm - 2);
+    if (i1 < i0 || j1 < j0) return;
+    const int nrows = j1 - j0 + 1;
+    const int ncand = (i1 - i0 + 1) * nrows * 2;
+    for (int c = lane; c < ncand; c += nlanes) {
+      int sq = c >> 1, which = c & 1;
+      int ci = sq / nrows, cj = sq - ci * nrows;
+      int si = i0 + ci, sj = j0 + cj;
+      double X0 = p.gx0 + si * p.gdx, X1 = p.gx0 + (si + 1) * p.gdx;
+      double Y0 = p.gy0 + sj * p.gdy, Y1 = p.gy0 + (sj + 1) * p.gdy;
+      t.gx[0] = X0; t.gy[0] = Y0;
+      if (which == 0) { t.gx[1] = X1; t.gy[1] = Y0; t.gx[2] = X1; t.gy[2] = Y1; }
+      else            { t.gx[1] = X1; t.gy[1] = Y1; t.gx[2] = X0; t.gy[2] = Y1; }
+      t.f = 2 * (si * (p.gm - 1) + sj) + which;
+      lane_face<NT, MODE>(p, i, P, maxv, T, t, xi, yi, wi, hacc, hstride, acc, lane_piece_base, lane_vert_base);
+    }
+  } else {
+    // general mesh: faces binned on a tg x tg grid over the mesh box; a face is handled in the first
+    // bin of (its bin range ∩ the query window)
+    const int g = p.tg;
+    int i0 = min(max((int)floor((cb[0] - p.bb[0]) * p.tinvx - 1e-9), 0), g - 1);
+    int i1 = min(max((int)floor((cb[2] - p.bb[0]) * p.tinvx + 1e-9), 0), g - 1);
+    int j0 = min(max((int)floor((cb[1] - p.bb[1]) * p.tinvy - 1e-9), 0), g - 1);
+    int j1 = min(max((int)floor((cb[3] - p.bb[1]) * p.tinvy + 1e-9), 0), g - 1);
+    int seen = 0;
+    for (int bj = j0; bj <= j1; ++bj)
+      for (int bi = i0; bi <= i1; ++bi) {
+        const int q0 = p.tbin_ptr[bj * g + bi], q1 = p.tbin_ptr[bj * g + bi + 1];
+        for (int q = q0; q < q1; ++q, ++seen) {
+          if (seen % nlanes != lane) continue;
+          int f = p.tbin_face[q];
+          double fx0 = 1e300, fy0 = 1e300;
+          for (int k = 0; k < 3; ++k) {
+            int v = p.tri[3 * (size_t)f + k];
+            t.gx[k] = p.vx[v]; t.gy[k] = p.vy[v];
+            fx0 = fmin(fx0, t.gx[k]); fy0 = fmin(fy0, t.gy[k]);
+          }
+          int fi0 = max(min(max((int)floor((fx0 - p.bb[0]) * p.tinvx), 0), g - 1), i0);
+          int fj0 = max(min(max((int)floor((fy0 - p.bb[1]) * p.tinvy), 0), g - 1), j0);
+          if (fi0 != bi || fj0 != bj) continue;
+          t.f = f;
+          lane_face<NT, MODE>(p, i, P, maxv, T, t, xi, yi, wi, hacc, hstride, acc, lane_piece_base, lane_vert_base);
+        }
+      }
+  }
+}
+
+MA_DEV void lane_acc_zero(LaneAcc &a) {
+  a.mass = a.cost = 0.0;
+  for (int k = 0; k < 5; ++k) a.m[k] = 0.0;
+  a.touched = 0ull;
+  for (int k = 0; k < CNT_N; ++k) a.cnt[k] = 0ull;
+  a.npieces = a.nverts = 0;
+}
+
+}  // namespace ma

@@ -1,0 +1,480 @@
+// ma_kernels.cuh — __global__ kernels of the evaluation path (K1 binning, K2 cells, K3 pieces,
+// K4 CSR) and small utility kernels (scan, reductions, gathers).  sm_100a, fp64 CUDA-core work.
+#pragma once
+#include "ma_cell.cuh"
+
+namespace ma {
+
+// ================================================================================================
+// utility: exclusive scan of int32 (n inputs -> n+1 outputs, out[n] = total)
+// ================================================================================================
+constexpr int SCAN_NT = 1024, SCAN_ITEMS = 4, SCAN_TILE = SCAN_NT * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+  __shared__ int warp_sums[32];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    int s = lane < nw ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  *total = warp_sums[nw - 1];
+  int res = x - v + (warp > 0 ? warp_sums[warp - 1] : 0);
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(SCAN_NT) k_scan_tiles(const int *__restrict__ in, int *__restrict__ out,
+                                                         int *__restrict__ tile_sums, int n) {
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  int total;
+  int ex = block_exclusive_scan(s, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile sums in place, total to *grand
+__global__ void __launch_bounds__(SCAN_NT) k_scan_sums(int *__restrict__ tile_sums, int nt, int *__restrict__ grand) {
+  int carry = 0;
+  for (int base = 0; base < nt; base += SCAN_NT) {
+    int idx = base + threadIdx.x;
+    int v = idx < nt ? tile_sums[idx] : 0;
+    int total;
+    int ex = block_exclusive_scan(v, &total);
+    if (idx < nt) tile_sums[idx] = ex + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *grand = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_NT) k_scan_add(int *__restrict__ out, const int *__restrict__ tile_sums, int n,
+                                                       const int *__restrict__ grand) {
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int off = tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+    if (base + k < n) out[base + k] += off;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *grand;
+}
+
+// ================================================================================================
+// utility: deterministic reductions (fixed tree, no atomics)
+// ================================================================================================
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// out[0] = sum a, out[1] = sum a*a  (or a*b when b != null), out[2] = min a, out[3] = max a.
+// Two stages: RED_BLOCKS partials, then one block.
+constexpr int RED_NT = 256, RED_BLOCKS = 296;
+
+__device__ __forceinline__ void block_reduce4(double s, double q, double mn, double mx, double *dst) {
+  __shared__ double sh[4][RED_NT / 32];
+  s = warp_sum(s); q = warp_sum(q); mn = warp_min(mn); mx = warp_max(mx);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = q; sh[2][warp] = mn; sh[3][warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    constexpr int NW = RED_NT / 32;
+    s = lane < NW ? sh[0][lane] : 0.0;
+    q = lane < NW ? sh[1][lane] : 0.0;
+    mn = lane < NW ? sh[2][lane] : 1e300;
+    mx = lane < NW ? sh[3][lane] : -1e300;
+    s = warp_sum(s); q = warp_sum(q); mn = warp_min(mn); mx = warp_max(mx);
+    if (lane == 0) { dst[0] = s; dst[1] = q; dst[2] = mn; dst[3] = mx; }
+  }
+}
+
+__global__ void __launch_bounds__(RED_NT) k_reduce_stage1(const double *__restrict__ a, const double *__restrict__ b,
+                                                           int n, double *__restrict__ partial) {
+  double s = 0, q = 0, mn = 1e300, mx = -1e300;
+  for (int i = blockIdx.x * RED_NT + threadIdx.x; i < n; i += gridDim.x * RED_NT) {
+    double v = a[i];
+    s += v;
+    q += b ? v * b[i] : v * v;
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+  }
+  block_reduce4(s, q, mn, mx, partial + 4 * blockIdx.x);
+}
+__global__ void __launch_bounds__(RED_NT) k_reduce_stage2(const double *__restrict__ partial, int nb,
+                                                           double *__restrict__ out) {
+  double s = 0, q = 0, mn = 1e300, mx = -1e300;
+  for (int i = threadIdx.x; i < nb; i += RED_NT) {
+    s += partial[4 * i]; q += partial[4 * i + 1];
+    mn = fmin(mn, partial[4 * i + 2]); mx = fmax(mx, partial[4 * i + 3]);
+  }
+  block_reduce4(s, q, mn, mx, out);
+}
+
+// ================================================================================================
+// K1: Morton-ordered uniform bins of the Diracs (once per point set) + per-eval max-weight pyramid
+// ================================================================================================
+__global__ void __launch_bounds__(1024) k_bbox(const double *__restrict__ x, const double *__restrict__ y, int n,
+                                                double *__restrict__ out) {
+  double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    x0 = fmin(x0, x[i]); x1 = fmax(x1, x[i]);
+    y0 = fmin(y0, y[i]); y1 = fmax(y1, y[i]);
+  }
+  __shared__ double sh[4][32];
+  x0 = warp_min(x0); x1 = warp_max(x1); y0 = warp_min(y0); y1 = warp_max(y1);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = x0; sh[1][warp] = x1; sh[2][warp] = y0; sh[3][warp] = y1; }
+  __syncthreads();
+  if (warp == 0) {
+    x0 = warp_min(sh[0][lane]); x1 = warp_max(sh[1][lane]); y0 = warp_min(sh[2][lane]); y1 = warp_max(sh[3][lane]);
+    if (lane == 0) { out[0] = x0; out[1] = y0; out[2] = x1; out[3] = y1; }
+  }
+}
+
+__global__ void k_bin_count(const double *__restrict__ x, const double *__restrict__ y, int n, double px0, double py0,
+                            double pinv, int G, unsigned *__restrict__ code, int *__restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int bx = min(max((int)((x[i] - px0) * pinv), 0), G - 1);
+  int by = min(max((int)((y[i] - py0) * pinv), 0), G - 1);
+  unsigned c = morton2((unsigned)bx, (unsigned)by);
+  code[i] = c;
+  atomicAdd(&count[c], 1);
+}
+__global__ void k_bin_scatter(const unsigned *__restrict__ code, int n, const int *__restrict__ bin_start,
+                              int *__restrict__ fill, int *__restrict__ perm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned c = code[i];
+  int slot = atomicAdd(&fill[c], 1);
+  perm[bin_start[c] + slot] = i;
+}
+// order inside a bin = caller index order, so that the internal ordering (and every sum order that
+// follows from it) is reproducible from run to run
+__global__ void k_bin_sort(const int *__restrict__ bin_start, int nbins, int *__restrict__ perm) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbins) return;
+  int s = bin_start[b], e = bin_start[b + 1];
+  for (int i = s + 1; i < e; ++i) {
+    int v = perm[i], j = i - 1;
+    while (j >= s && perm[j] > v) { perm[j + 1] = perm[j]; --j; }
+    perm[j + 1] = v;
+  }
+}
+__global__ void k_gather_points(const double *__restrict__ x, const double *__restrict__ y,
+                                const int *__restrict__ perm, int n, double *__restrict__ xs, double *__restrict__ ys,
+                                int *__restrict__ pos) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int i = perm[k];
+  xs[k] = x[i];
+  ys[k] = y[i];
+  pos[i] = k;
+}
+// dst[k] = src[perm[k]]
+__global__ void k_gather(const double *__restrict__ src, const int *__restrict__ perm, int n, double *__restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[perm[k]];
+}
+
+// per-eval: leaf maxima of the bins + 4 levels above, one block per 256 consecutive Morton bins
+__global__ void __launch_bounds__(256) k_wmax_leaf(const double *__restrict__ ws, const int *__restrict__ bin_start,
+                                                    int L, double *__restrict__ wmax) {
+  __shared__ double sh[256];
+  const size_t nleaf = (size_t)1 << (2 * L);
+  size_t b = (size_t)blockIdx.x * 256 + threadIdx.x;
+  double m = -1.0 / 0.0;
+  if (b < nleaf) {
+    int s = bin_start[b], e = bin_start[b + 1];
+    for (int k = s; k < e; ++k) m = fmax(m, ws[k]);
+    wmax[(nleaf - 1) / 3 + b] = m;
+  }
+  sh[threadIdx.x] = m;
+  __syncthreads();
+  int width = 256;
+  for (int up = 1; up <= 4 && up <= L; ++up) {
+    width >>= 2;
+    double v = 0;
+    if ((int)threadIdx.x < width) {
+      int c = 4 * threadIdx.x;
+      v = fmax(fmax(sh[c], sh[c + 1]), fmax(sh[c + 2], sh[c + 3]));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < width) {
+      sh[threadIdx.x] = v;
+      size_t nl = (size_t)1 << (2 * (L - up));
+      size_t node = (size_t)blockIdx.x * width + threadIdx.x;
+      if (node < nl) wmax[(nl - 1) / 3 + node] = v;
+    }
+    __syncthreads();
+  }
+}
+// remaining top levels (L-5 .. 0), single block
+__global__ void __launch_bounds__(1024) k_wmax_top(int L, double *__restrict__ wmax) {
+  for (int l = L - 5; l >= 0; --l) {
+    size_t nl = (size_t)1 << (2 * l);
+    const double *child = wmax + (4 * nl - 1) / 3;
+    double *mine = wmax + (nl - 1) / 3;
+    for (size_t c = threadIdx.x; c < nl; c += 1024)
+      mine[c] = fmax(fmax(child[4 * c], child[4 * c + 1]), fmax(child[4 * c + 2], child[4 * c + 3]));
+    __syncthreads();
+  }
+}
+
+// ================================================================================================
+// K2: one thread per cell
+// ================================================================================================
+template <int MAXV, int NT> __global__ void __launch_bounds__(NT) k_cells(Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sx = reinterpret_cast<double *>(smem_raw);
+  double *sy = sx + MAXV * NT;
+  int *st = reinterpret_cast<int *>(sy + MAXV * NT);
+  int i = blockIdx.x * NT + threadIdx.x;
+  if (i >= p.N) return;
+  PolyRef<NT> P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+  int fl = 0;
+  int n = cell_build<NT>(p, i, P, MAXV, &fl);
+  if (fl) atomicOr(p.flags, fl);
+  if (n < 0) n = 0;
+  cell_emit<NT>(p, i, P, n);
+}
+template <int MAXV, int NT> constexpr size_t cells_smem_bytes() { return (size_t)MAXV * NT * (8 + 8 + 4); }
+
+// ================================================================================================
+// K3: one warp per cell; lanes take candidate faces round-robin
+// ================================================================================================
+constexpr int PIECES_WPB = 4;  // warps per block
+template <int KMAX, int MAXV> constexpr size_t pieces_warp_bytes() {
+  return (size_t)(4 * KMAX + 2 * MAXV * 32 + KMAX * 33) * 8 + (size_t)(MAXV * 32 + KMAX) * 4;
+}
+
+template <int KMAX, int MAXV, int MODE> __global__ void __launch_bounds__(PIECES_WPB * 32) k_pieces(Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * PIECES_WPB + warp;
+  if (i >= p.N) return;  // warp-uniform; no block-level barrier below
+  unsigned char *base = smem_raw + (size_t)warp * pieces_warp_bytes<KMAX, MAXV>();
+  double *d = reinterpret_cast<double *>(base);
+  CellTable T;
+  T.Dx = d; T.Dy = d + KMAX; T.C = d + 2 * KMAX; T.S = d + 3 * KMAX;
+  double *px = d + 4 * KMAX, *py = px + MAXV * 32;
+  double *hacc = py + MAXV * 32;  // [KMAX][33]
+  int *ptag = reinterpret_cast<int *>(hacc + KMAX * 33);
+  T.J = ptag + MAXV * 32;
+  PolyRef<32> P{px + lane, py + lane, ptag + lane};
+
+  const int k = p.nbr_cnt[i];
+  T.k = k < 0 ? 0 : k;
+  LaneAcc acc;
+  lane_acc_zero(acc);
+  if (k >= 0) {
+    for (int s = lane; s < k; s += 32) cell_table_fill(p, i, s, T);
+    if (MODE == MODE_KANTOROVICH)
+      for (int s = 0; s < KMAX; ++s) hacc[s * 33 + lane] = 0.0;
+    __syncwarp();
+    int pbase = 0, vbase = 0;
+    if (MODE == MODE_PIECES_FILL) {
+      // per-lane output offsets: cell offset + exclusive prefix over lanes of the counts, recomputed
+      // by a dry run (the enumeration is deterministic)
+      LaneAcc dry;
+      lane_acc_zero(dry);
+      Params q = p;
+      q.stats = 0;
+      lane_pieces<32, MODE_PIECES_COUNT>(q, i, lane, 32, P, MAXV, T, hacc, 33, dry);
+      int np = dry.npieces, nv = dry.nverts;
+      int ep = np, ev = nv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int a = __shfl_up_sync(0xffffffffu, ep, o), b = __shfl_up_sync(0xffffffffu, ev, o);
+        if (lane >= o) { ep += a; ev += b; }
+      }
+      pbase = p.pc_off[2 * i] + ep - np;
+      vbase = p.pc_off[2 * i + 1] + ev - nv;
+      __syncwarp();
+    }
+    lane_pieces<32, MODE>(p, i, lane, 32, P, MAXV, T, hacc + lane, 33, acc, pbase, vbase);
+    __syncwarp();
+  }
+  // ---- per-cell reductions (fixed order => reproducible) ----
+  if (MODE == MODE_KANTOROVICH) {
+    double mass = warp_sum(acc.mass), cost = warp_sum(acc.cost);
+    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)(acc.touched & 0xffffffffull));
+    unsigned hi = KMAX > 32 ? __reduce_or_sync(0xffffffffu, (unsigned)(acc.touched >> 32)) : 0u;
+    unsigned long long touched = ((unsigned long long)hi << 32) | lo;
+    for (int s = lane; s < KMAX; s += 32) {
+      double h = 0.0;
+      if (s < T.k && ((touched >> s) & 1ull)) {
+        const double *row = hacc + s * 33;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) h += row[l];
+      }
+      p.hslot[(size_t)i * KMAX + s] = h;
+    }
+    if (lane == 0) {
+      p.mass[i] = mass;
+      p.fcell[i] = mass * p.ws[i] - cost;
+      p.touched[i] = touched;
+      int c = __popcll(touched);
+      p.rowcnt[i] = c ? c + 1 : 0;
+    }
+  } else if (MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) {
+    double mass = warp_sum(acc.mass);
+    double m0 = warp_sum(acc.m[0]), m1 = warp_sum(acc.m[1]);
+    double m2 = 0, m3 = 0, m4 = 0;
+    if (MODE == MODE_MOMENTS2) { m2 = warp_sum(acc.m[2]); m3 = warp_sum(acc.m[3]); m4 = warp_sum(acc.m[4]); }
+    if (lane == 0) {
+      const double xi = p.xs[i], yi = p.ys[i];
+      double *o = p.mom + 6 * (size_t)i;
+      o[0] = mass;
+      o[1] = m0 + xi * mass;  // ∫ρ x = ∫ρ (xi + ux)
+      o[2] = m1 + yi * mass;
+      o[3] = m2 + 2 * xi * m0 + xi * xi * mass;
+      o[4] = m3 + 2 * yi * m1 + yi * yi * mass;
+      o[5] = m4 + xi * m1 + yi * m0 + xi * yi * mass;
+    }
+  } else if (MODE == MODE_PIECES_COUNT) {
+    int np = acc.npieces, nv = acc.nverts;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      np += __shfl_xor_sync(0xffffffffu, np, o);
+      nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    }
+    if (lane == 0) { p.pc_count[2 * i] = np; p.pc_count[2 * i + 1] = nv; }
+  }
+  if (p.stats) {
+    if (lane == 0 && k > 0) acc.cnt[CNT_SUMK] += k;
+    for (int c = 0; c < CNT_N; ++c) {
+      unsigned long long v = acc.cnt[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v) atomicAdd(&p.counters[c], v);
+    }
+  }
+}
+
+// ================================================================================================
+// K4: CSR fill (internal Morton order).  Row i = { (nbr slot s, -hslot) : touched } ∪ { (i, Σ hslot) },
+// columns ascending (what Eigen's setFromTriplets yields per row, kantorovich.hpp:120-121,137-139).
+// ================================================================================================
+template <int KMAX>
+__global__ void k_csr_fill(int N, const int *__restrict__ nbr, const double *__restrict__ hslot,
+                           const unsigned long long *__restrict__ touched, const int *__restrict__ rowptr,
+                           int *__restrict__ col, double *__restrict__ val) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  unsigned long long t = touched[i];
+  if (!t) return;
+  int c[KMAX + 1];
+  double v[KMAX + 1];
+  int n = 0;
+  double diag = 0.0;
+  for (int s = 0; s < KMAX; ++s)
+    if ((t >> s) & 1ull) {
+      double h = hslot[(size_t)i * KMAX + s];
+      int j = nbr[(size_t)i * KMAX + s];
+      diag += h;
+      // insertion into the sorted prefix
+      int q = n++;
+      while (q > 0 && c[q - 1] > j) { c[q] = c[q - 1]; v[q] = v[q - 1]; --q; }
+      c[q] = j; v[q] = -h;
+    }
+  {
+    int q = n++;
+    while (q > 0 && c[q - 1] > i) { c[q] = c[q - 1]; v[q] = v[q - 1]; --q; }
+    c[q] = i; v[q] = diag;
+  }
+  int o = rowptr[i];
+  for (int q = 0; q < n; ++q) { col[o + q] = c[q]; val[o + q] = v[q]; }
+}
+
+// caller-order views -----------------------------------------------------------------------------
+__global__ void k_scatter_to_caller(const double *__restrict__ src_sorted, const int *__restrict__ perm, int n,
+                                    double *__restrict__ dst_caller) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst_caller[perm[k]] = src_sorted[k];
+}
+__global__ void k_rowcnt_to_caller(const int *__restrict__ rowptr_sorted, const int *__restrict__ pos, int n,
+                                   int *__restrict__ cnt_caller) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { int k = pos[i]; cnt_caller[i] = rowptr_sorted[k + 1] - rowptr_sorted[k]; }
+}
+__global__ void k_csr_to_caller(int n, const int *__restrict__ rowptr_s, const int *__restrict__ col_s,
+                                const double *__restrict__ val_s, const int *__restrict__ pos,
+                                const int *__restrict__ perm, const int *__restrict__ rowptr_c, int *__restrict__ col_c,
+                                double *__restrict__ val_c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int k = pos[i];
+  int s = rowptr_s[k], e = rowptr_s[k + 1], o = rowptr_c[i];
+  for (int q = s; q < e; ++q) {  // insertion sort by caller column while copying
+    int cj = perm[col_s[q]];
+    double vj = val_s[q];
+    int w = o + (q - s);
+    while (w > o && col_c[w - 1] > cj) { col_c[w] = col_c[w - 1]; val_c[w] = val_c[w - 1]; --w; }
+    col_c[w] = cj; val_c[w] = vj;
+  }
+}
+// adjacency in caller order
+__global__ void k_adj_count(int n, const int *__restrict__ nbr_cnt, const int *__restrict__ pos, int *__restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cnt[i] = max(nbr_cnt[pos[i]], 0);
+}
+__global__ void k_adj_fill(int n, int kmax, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt,
+                           const int *__restrict__ pos, const int *__restrict__ perm, const int *__restrict__ ptr,
+                           int *__restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int k = pos[i], c = max(nbr_cnt[k], 0), o = ptr[i];
+  for (int s = 0; s < c; ++s) idx[o + s] = perm[nbr[(size_t)k * kmax + s]];
+}
+
+__global__ void k_fill_bytes(unsigned long long *p, size_t n, unsigned long long v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// DFMA throughput probe: 8 independent chains per thread
+__global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace ma

@@ -1,0 +1,84 @@
+"""ctypes front-end of tests/emu/emu_harness.cu (CPU emulation of the CUDA per-lane code; TEST ONLY)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = os.path.join(_HERE, "_build", "libma_emu.so")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "emu_harness.cu")
+    deps = [src] + [os.path.join(_ROOT, "mongeampere_b200", "csrc", f) for f in ("ma_cell.cuh", "ma_geom.cuh")]
+    if not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(d) for d in deps):
+        return _LIB
+    os.makedirs(os.path.dirname(_LIB), exist_ok=True)
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "--expt-extended-lambda", "--expt-relaxed-constexpr",
+                           "-Xcompiler", "-fPIC", "-shared", src, "-o", _LIB])
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_target=2, nlanes=32):
+    """mesh: dict(kind='grid', n, m, x0, y0, x1, y1, abc) or dict(kind='mesh', vx, vy, tri, abc).
+    Returns dict(f, g, H, mom, counters, flags, adjacency)."""
+    X = np.asarray(X, np.float64)
+    N = len(X)
+    x = np.ascontiguousarray(X[:, 0]); y = np.ascontiguousarray(X[:, 1])
+    w = np.ascontiguousarray(w, np.float64)
+    abc = np.ascontiguousarray(mesh["abc"], np.float64).reshape(-1)
+    perm = np.zeros(N, np.int32); mass = np.zeros(N); fcell = np.zeros(N)
+    nbr_cnt = np.zeros(N, np.int32); nbr = np.zeros(N * kmax, np.int32); hslot = np.zeros(N * kmax)
+    touched = np.zeros(N, np.uint64); mom = np.zeros(N * 6); counters = np.zeros(8, np.int64)
+    flags = C.c_int(0)
+    if mesh["kind"] == "grid":
+        n, m = mesh["n"], mesh["m"]
+        x0, y0, x1, y1 = mesh.get("x0", -1.0), mesh.get("y0", -1.0), mesh.get("x1", 1.0), mesh.get("y1", 1.0)
+        gargs = (2, n, m, C.c_double(x0), C.c_double(y0), C.c_double((x1 - x0) / (n - 1)), C.c_double((y1 - y0) / (m - 1)),
+                 0, None, None, 0, None)
+    else:
+        vx = np.ascontiguousarray(mesh["vx"], np.float64); vy = np.ascontiguousarray(mesh["vy"], np.float64)
+        tri = np.ascontiguousarray(mesh["tri"], np.int32).reshape(-1)
+        gargs = (1, 0, 0, C.c_double(0), C.c_double(0), C.c_double(1), C.c_double(1),
+                 len(vx), vx.ctypes.data_as(C.c_void_p), vy.ctypes.data_as(C.c_void_p), len(tri) // 3,
+                 tri.ctypes.data_as(C.c_void_p))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emu_eval(*gargs, p(abc), N, p(x), p(y), p(w), kmax, maxv_piece, mode, C.c_double(filter_tol),
+                        bin_target, nlanes, p(perm), p(mass), p(fcell), p(nbr_cnt), p(nbr), p(hslot), p(touched),
+                        p(mom), p(counters), C.byref(flags))
+    assert rc == 0
+    g = np.zeros(N); g[perm] = mass
+    momc = np.zeros((N, 6)); momc[perm] = mom.reshape(N, 6)
+    # CSR from slots (what k_csr_fill does)
+    rows, cols, vals = [], [], []
+    nbr = nbr.reshape(N, kmax); hslot = hslot.reshape(N, kmax)
+    adj = [None] * N
+    for k in range(N):
+        i = perm[k]
+        adj[i] = sorted(int(perm[j]) for j in nbr[k, :max(nbr_cnt[k], 0)])
+        t = int(touched[k])
+        if not t:
+            continue
+        d = 0.0
+        for s in range(kmax):
+            if (t >> s) & 1:
+                rows.append(i); cols.append(perm[nbr[k, s]]); vals.append(-hslot[k, s]); d += hslot[k, s]
+        rows.append(i); cols.append(i); vals.append(d)
+    H = sp.csr_matrix((vals, (rows, cols)), shape=(N, N))
+    names = ("pieces", "piece_vertices", "new_vertices", "laguerre_edges", "sum_k", "sum_k_np", "fallbacks", "candidates")
+    return dict(f=float(fcell.sum()), g=g, H=H, mom=momc, counters=dict(zip(names, map(int, counters))),
+                flags=flags.value, adjacency=adj)

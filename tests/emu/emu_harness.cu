@@ -1,0 +1,196 @@
+// emu_harness.cu — TEST INFRASTRUCTURE: runs the __host__ __device__ per-thread / per-lane code of
+// the CUDA kernels (mongeampere_b200/csrc/ma_cell.cuh) serially on the CPU, so that the clipping /
+// integration / neighbour-search logic can be checked against the oracle without a GPU
+// (`pytest -m "not gpu"`).  It is NOT a product path: nothing in mongeampere_b200/ links to it.
+// The host code below re-does K1 (binning, max-weight pyramid) in the simplest possible way.
+//
+// Build: nvcc -O2 -std=c++17 --expt-extended-lambda --expt-relaxed-constexpr -Xcompiler -fPIC -shared
+//        tests/emu/emu_harness.cu -o tests/emu/_build/libma_emu.so
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../../mongeampere_b200/csrc/ma_cell.cuh"
+
+using namespace ma;
+
+extern "C" int emu_eval(int mesh_kind,
+                        // grid mesh
+                        int gn, int gm, double gx0, double gy0, double gdx, double gdy,
+                        // general mesh
+                        int nV, const double *vx, const double *vy, int nF, const int *tri,
+                        // densities
+                        const double *abc,
+                        // Diracs
+                        int N, const double *x, const double *y, const double *w,
+                        // knobs
+                        int kmax, int maxv_piece, int mode, double filter_tol, int bin_target, int nlanes,
+                        // outputs (internal order) + permutation
+                        int *perm_out, double *mass, double *fcell, int *nbr_cnt, int *nbr, double *hslot,
+                        unsigned long long *touched, double *mom, long long *counters, int *flags_out) {
+  Params p;
+  memset(&p, 0, sizeof p);
+  // ---- mesh ----
+  p.mesh_kind = mesh_kind;
+  p.abc = abc;
+  std::vector<int> tbin_ptr, tbin_face;
+  if (mesh_kind == MESH_GRID) {
+    p.gn = gn; p.gm = gm; p.gx0 = gx0; p.gy0 = gy0; p.gdx = gdx; p.gdy = gdy;
+    p.nF = 2 * (gn - 1) * (gm - 1);
+    p.bb[0] = gx0; p.bb[1] = gy0; p.bb[2] = gx0 + (gn - 1) * gdx; p.bb[3] = gy0 + (gm - 1) * gdy;
+  } else {
+    p.nF = nF; p.vx = vx; p.vy = vy; p.tri = tri;
+    p.bb[0] = p.bb[1] = 1e300; p.bb[2] = p.bb[3] = -1e300;
+    for (int i = 0; i < nV; ++i) {
+      p.bb[0] = std::min(p.bb[0], vx[i]); p.bb[2] = std::max(p.bb[2], vx[i]);
+      p.bb[1] = std::min(p.bb[1], vy[i]); p.bb[3] = std::max(p.bb[3], vy[i]);
+    }
+    int g = (int)std::ceil(std::sqrt(std::max(1.0, nF / 2.0)));
+    p.tg = g;
+    p.tinvx = g / (p.bb[2] - p.bb[0]); p.tinvy = g / (p.bb[3] - p.bb[1]);
+    auto range = [&](int f, int &i0, int &i1, int &j0, int &j1) {
+      double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+      for (int k = 0; k < 3; ++k) {
+        int v = tri[3 * f + k];
+        x0 = std::min(x0, vx[v]); x1 = std::max(x1, vx[v]);
+        y0 = std::min(y0, vy[v]); y1 = std::max(y1, vy[v]);
+      }
+      i0 = std::min(std::max((int)std::floor((x0 - p.bb[0]) * p.tinvx), 0), g - 1);
+      i1 = std::min(std::max((int)std::floor((x1 - p.bb[0]) * p.tinvx), 0), g - 1);
+      j0 = std::min(std::max((int)std::floor((y0 - p.bb[1]) * p.tinvy), 0), g - 1);
+      j1 = std::min(std::max((int)std::floor((y1 - p.bb[1]) * p.tinvy), 0), g - 1);
+    };
+    tbin_ptr.assign((size_t)g * g + 1, 0);
+    for (int f = 0; f < nF; ++f) {
+      int i0, i1, j0, j1; range(f, i0, i1, j0, j1);
+      for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) tbin_ptr[(size_t)j * g + i + 1]++;
+    }
+    for (size_t b = 0; b < (size_t)g * g; ++b) tbin_ptr[b + 1] += tbin_ptr[b];
+    tbin_face.resize(tbin_ptr.back());
+    std::vector<int> fill(tbin_ptr.begin(), tbin_ptr.end() - 1);
+    for (int f = 0; f < nF; ++f) {
+      int i0, i1, j0, j1; range(f, i0, i1, j0, j1);
+      for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) tbin_face[fill[(size_t)j * g + i]++] = f;
+    }
+    p.tbin_ptr = tbin_ptr.data(); p.tbin_face = tbin_face.data();
+  }
+  // ---- K1 on the host ----
+  double bx0 = 1e300, bx1 = -1e300, by0 = 1e300, by1 = -1e300;
+  for (int i = 0; i < N; ++i) {
+    bx0 = std::min(bx0, x[i]); bx1 = std::max(bx1, x[i]);
+    by0 = std::min(by0, y[i]); by1 = std::max(by1, y[i]);
+  }
+  double ext = std::max(std::max(bx1 - bx0, by1 - by0), 1e-300) * (1 + 1e-9);
+  int L = 0;
+  while (((long long)1 << (2 * L)) * bin_target < N && L < 12) ++L;
+  const int G = 1 << L;
+  const double pinv = G / ext;
+  p.L = L; p.px0 = bx0; p.py0 = by0; p.ph = ext / G;
+  std::vector<unsigned> code(N);
+  std::vector<int> order(N);
+  for (int i = 0; i < N; ++i) {
+    int bx = std::min(std::max((int)((x[i] - bx0) * pinv), 0), G - 1);
+    int by = std::min(std::max((int)((y[i] - by0) * pinv), 0), G - 1);
+    code[i] = morton2(bx, by);
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
+  const size_t nb = (size_t)G * G;
+  std::vector<int> bin_start(nb + 1, 0);
+  for (int i = 0; i < N; ++i) bin_start[code[i] + 1]++;
+  for (size_t b = 0; b < nb; ++b) bin_start[b + 1] += bin_start[b];
+  std::vector<double> xs(N), ys(N), ws(N);
+  for (int k = 0; k < N; ++k) { xs[k] = x[order[k]]; ys[k] = y[order[k]]; ws[k] = w[order[k]]; perm_out[k] = order[k]; }
+  std::vector<double> wmax((4 * nb - 1) / 3);
+  const double NEG = -std::numeric_limits<double>::infinity();
+  for (size_t b = 0; b < nb; ++b) {
+    double m = NEG;
+    for (int k = bin_start[b]; k < bin_start[b + 1]; ++k) m = std::max(m, ws[k]);
+    wmax[(nb - 1) / 3 + b] = m;
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    size_t nl = (size_t)1 << (2 * l);
+    for (size_t c = 0; c < nl; ++c) {
+      const double *ch = &wmax[(4 * nl - 1) / 3 + 4 * c];
+      wmax[(nl - 1) / 3 + c] = std::max(std::max(ch[0], ch[1]), std::max(ch[2], ch[3]));
+    }
+  }
+  p.N = N; p.xs = xs.data(); p.ys = ys.data(); p.ws = ws.data();
+  p.bin_start = bin_start.data(); p.wmax = wmax.data();
+  // ---- outputs ----
+  std::vector<double> cell_bb((size_t)4 * N);
+  std::vector<unsigned long long> cnt(CNT_N, 0);
+  int flags = 0;
+  p.kmax = kmax; p.nbr = nbr; p.nbr_cnt = nbr_cnt; p.cell_bb = cell_bb.data();
+  p.mass = mass; p.fcell = fcell; p.hslot = hslot; p.touched = touched; p.mom = mom;
+  p.counters = cnt.data(); p.stats = 1; p.flags = &flags; p.filter_tol = filter_tol;
+  // ---- K2 ----
+  const int maxv_cell = kmax + 4;
+  {
+    std::vector<double> px(maxv_cell), py(maxv_cell);
+    std::vector<int> pt(maxv_cell);
+    PolyRef<1> P{px.data(), py.data(), pt.data()};
+    for (int i = 0; i < N; ++i) {
+      int fl = 0;
+      int n = cell_build<1>(p, i, P, maxv_cell, &fl);
+      flags |= fl;
+      if (n < 0) n = 0;
+      cell_emit<1>(p, i, P, n);
+    }
+  }
+  // ---- K3 ----
+  {
+    std::vector<double> tDx(kmax), tDy(kmax), tC(kmax), tS(kmax), hacc((size_t)kmax * nlanes);
+    std::vector<int> tJ(kmax);
+    std::vector<double> px(maxv_piece), py(maxv_piece);
+    std::vector<int> pt(maxv_piece);
+    PolyRef<1> P{px.data(), py.data(), pt.data()};
+    for (int i = 0; i < N; ++i) {
+      CellTable T{tDx.data(), tDy.data(), tC.data(), tS.data(), tJ.data(), 0};
+      int k = nbr_cnt[i];
+      T.k = k < 0 ? 0 : k;
+      std::fill(hacc.begin(), hacc.end(), 0.0);
+      double m = 0, cost = 0, mo[5] = {0, 0, 0, 0, 0};
+      unsigned long long tch = 0;
+      if (k >= 0) {
+        for (int s = 0; s < k; ++s) cell_table_fill(p, i, s, T);
+        for (int lane = 0; lane < nlanes; ++lane) {
+          LaneAcc acc;
+          lane_acc_zero(acc);
+          if (mode == MODE_KANTOROVICH)
+            lane_pieces<1, MODE_KANTOROVICH>(p, i, lane, nlanes, P, maxv_piece, T, hacc.data() + lane, nlanes, acc);
+          else if (mode == MODE_MOMENTS1)
+            lane_pieces<1, MODE_MOMENTS1>(p, i, lane, nlanes, P, maxv_piece, T, hacc.data() + lane, nlanes, acc);
+          else
+            lane_pieces<1, MODE_MOMENTS2>(p, i, lane, nlanes, P, maxv_piece, T, hacc.data() + lane, nlanes, acc);
+          m += acc.mass; cost += acc.cost; tch |= acc.touched;
+          for (int q = 0; q < 5; ++q) mo[q] += acc.m[q];
+          for (int q = 0; q < CNT_N; ++q) cnt[q] += acc.cnt[q];
+        }
+        cnt[CNT_SUMK] += k;
+      }
+      mass[i] = m;
+      fcell[i] = m * ws[i] - cost;
+      touched[i] = tch;
+      for (int s = 0; s < kmax; ++s) {
+        double h = 0;
+        if (s < T.k && ((tch >> s) & 1ull))
+          for (int lane = 0; lane < nlanes; ++lane) h += hacc[(size_t)s * nlanes + lane];
+        hslot[(size_t)i * kmax + s] = h;
+      }
+      if (mom) {
+        const double xi = xs[i], yi = ys[i];
+        double *o = mom + 6 * (size_t)i;
+        o[0] = m; o[1] = mo[0] + xi * m; o[2] = mo[1] + yi * m;
+        o[3] = mo[2] + 2 * xi * mo[0] + xi * xi * m;
+        o[4] = mo[3] + 2 * yi * mo[1] + yi * yi * m;
+        o[5] = mo[4] + xi * mo[1] + yi * mo[0] + xi * yi * m;
+      }
+    }
+  }
+  for (int q = 0; q < CNT_N; ++q) counters[q] = (long long)cnt[q];
+  *flags_out = flags;
+  return 0;
+}

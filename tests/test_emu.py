@@ -1,0 +1,107 @@
+"""CPU emulation of the CUDA kernels' per-thread / per-lane code (tests/emu, same __host__ __device__
+functions the GPU runs) against the oracle.  Covers the geometry logic of K2/K3 without a GPU."""
+import numpy as np
+import pytest
+
+from mongeampere_b200 import inputs
+from tests import common
+
+CASES = [("c1", 0.05, "zero"), ("c1", 0.05, "0.4"), ("c1r", 0.03, "0.2"), ("c2", 0.004, "zero"), ("c2", 0.004, "0.5"),
+         ("c3", 0.0005, "0.3"), ("c5", 0.0001, "0.2")]
+
+
+def check(r, ref, orc_counters, tol=1e-10):
+    f0, g0, H0 = ref
+    assert r["flags"] == 0
+    assert abs(r["f"] - f0) <= tol * abs(f0)
+    assert np.abs(r["g"] - g0).max() <= tol * np.abs(g0).max()
+    assert common.same_pattern(H0, r["H"])
+    assert abs(H0 - r["H"]).max() <= tol * np.abs(H0.diagonal()).max()
+    for k in ("pieces", "piece_vertices", "new_vertices", "laguerre_edges", "sum_k", "sum_k_np"):
+        assert orc_counters[k] == r["counters"][k], k
+
+
+@pytest.mark.parametrize("name,scale,weights", CASES)
+def test_emulated_kernels_match_oracle(oracle_mod, emu_mod, name, scale, weights):
+    case = common.make_case(name, scale, weights)
+    orc = common.oracle_for(oracle_mod, case)
+    ref = orc.kantorovich(case["w"])
+    r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"])
+    check(r, ref, orc.counters())
+
+
+def test_general_mesh_enumeration(oracle_mod, emu_mod):
+    case = common.make_case("c2", 0.004, "0.5")
+    cfg = case["cfg"]
+    orc = common.oracle_for(oracle_mod, case)
+    ref = orc.kantorovich(case["w"])
+    mesh = dict(kind="mesh", vx=cfg["vx"], vy=cfg["vy"], tri=cfg["tri"], abc=case["abc"])
+    check(emu_mod.evaluate(mesh, case["X"], case["w"]), ref, orc.counters())
+
+
+def test_double_double_fallback_agrees(oracle_mod, emu_mod):
+    """Force EVERY sign through the double-double predicates (filter_tol = inf)."""
+    case = common.make_case("c2", 0.004, "0.5")
+    orc = common.oracle_for(oracle_mod, case)
+    ref = orc.kantorovich(case["w"])
+    r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], filter_tol=1e300)
+    assert r["counters"]["fallbacks"] > 1000
+    check(r, ref, orc.counters())
+
+
+@pytest.mark.parametrize("nlanes,bin_target", [(1, 1), (8, 4), (32, 16)])
+def test_lane_count_and_bin_size_do_not_matter(oracle_mod, emu_mod, nlanes, bin_target):
+    case = common.make_case("c3", 0.0005, "0.3")
+    orc = common.oracle_for(oracle_mod, case)
+    ref = orc.kantorovich(case["w"])
+    check(emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], nlanes=nlanes, bin_target=bin_target), ref,
+          orc.counters())
+
+
+def test_moments(oracle_mod, emu_mod):
+    case = common.make_case("c2", 0.004, "0.3")
+    orc = common.oracle_for(oracle_mod, case)
+    for order, mode in ((1, 1), (2, 2)):
+        ref = orc.moments(case["w"], order)
+        r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], mode=mode)
+        ncol = 3 if order == 1 else 6
+        scale = np.abs(ref[:, :ncol]).max(axis=0)
+        assert (np.abs(r["mom"][:, :ncol] - ref[:, :ncol]).max(axis=0) <= 1e-11 * scale).all()
+
+
+def test_lattice_degenerate_input(oracle_mod, emu_mod):
+    """Exactly co-circular sites on the mesh diagonal: ties everywhere.  Values must still be right."""
+    n = 6
+    vx, vy, tri = inputs.unit_square_mesh()
+    abc = inputs.pl_coefficients(vx, vy, np.ones(4), tri)
+    c = (np.arange(n) + 0.5) / n
+    X = np.stack(np.meshgrid(c, c, indexing="ij"), -1).reshape(-1, 2)
+    r = emu_mod.evaluate(dict(kind="mesh", vx=vx, vy=vy, tri=tri, abc=abc), X, np.zeros(n * n))
+    assert np.allclose(r["g"], 1.0 / n ** 2, atol=1e-14)
+    Hd = r["H"].toarray()
+    assert np.allclose(np.diag(Hd)[[n + 1, 2 * n + 2]], 2.0, atol=1e-12)
+    assert np.abs(Hd.sum(1)).max() < 1e-12
+
+
+def test_hidden_and_coincident_diracs(emu_mod):
+    vx, vy, tri = inputs.unit_square_mesh()
+    abc = inputs.pl_coefficients(vx, vy, np.ones(4), tri)
+    mesh = dict(kind="mesh", vx=vx, vy=vy, tri=tri, abc=abc)
+    X = np.array([[0.3, 0.5], [0.7, 0.5], [0.5, 0.5]])
+    r = emu_mod.evaluate(mesh, X, np.array([0.0, 0.0, -1.0]))
+    assert r["g"][2] == 0 and abs(r["g"].sum() - 1) < 1e-15 and r["H"].getrow(2).nnz == 0
+    X = np.array([[0.3, 0.5], [0.7, 0.5], [0.7, 0.5]])  # duplicate site: exactly one of the twins keeps the cell
+    r = emu_mod.evaluate(mesh, X, np.zeros(3))
+    assert abs(r["g"].sum() - 1) < 1e-15 and sorted(r["g"][1:])[0] == 0
+
+
+def test_capacity_overflow_is_flagged(emu_mod):
+    """A cell with more neighbours than kmax must raise the overflow flag (the host then escalates)."""
+    vx, vy, tri = inputs.unit_square_mesh()
+    abc = inputs.pl_coefficients(vx, vy, np.ones(4), tri)
+    t = np.linspace(0, 2 * np.pi, 40, endpoint=False)
+    X = np.r_[[[0.5, 0.5]], 0.5 + 0.3 * np.c_[np.cos(t), np.sin(t)]]
+    r = emu_mod.evaluate(dict(kind="mesh", vx=vx, vy=vy, tri=tri, abc=abc), X, np.zeros(len(X)), kmax=16, maxv_piece=12)
+    assert r["flags"] != 0
+    r = emu_mod.evaluate(dict(kind="mesh", vx=vx, vy=vy, tri=tri, abc=abc), X, np.zeros(len(X)), kmax=64, maxv_piece=70)
+    assert r["flags"] == 0 and abs(r["g"].sum() - 1) < 1e-14 and len(r["adjacency"][0]) == 40

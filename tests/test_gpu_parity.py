@@ -1,0 +1,203 @@
+"""GPU parity: the CUDA engine through its C-ABI vs the CPU oracle on the same seeded inputs.
+Tolerances are the north star's: masses / gradient / Hessian 1e-10 relative (Hessian relative to the
+row diagonal), neighbour pattern bit-identical on non-degenerate inputs."""
+import numpy as np
+import pytest
+
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("c1", 0.2, "zero"), ("c1", 0.2, "0.3"), ("c1r", 0.1, "zero"), ("c2", 0.02, "zero"), ("c2", 0.02, "0.5"),
+         ("c3", 0.003, "0.3"), ("c5", 0.0005, "zero")]
+
+
+@pytest.mark.parametrize("name,scale,weights", CASES)
+def test_kantorovich_matches_oracle(gpu_ctx, oracle_mod, name, scale, weights):
+    case = common.make_case(name, scale, weights)
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(case["w"])
+    common.load_engine(gpu_ctx, case)
+    gpu_ctx.set_stats(True)
+    f1, g1, H1 = gpu_ctx.kantorovich(case["w"])
+    gscale = np.abs(g0).max()
+    assert abs(f1 - f0) <= 1e-10 * max(abs(f0), 1e-300), (f0, f1)
+    assert np.abs(g1 - g0).max() <= 1e-10 * gscale
+    assert common.same_pattern(H0, H1), (H0.nnz, H1.nnz)
+    # Hessian entries: 1e-10 relative to the diagonal scale.  (Relative to each row's OWN diagonal the
+    # oracle itself is only good to ~1e-9 on near-hidden cells, because it follows the reference's
+    # global-coordinate CGAL::radical_axis; see test_tiny_cell_arbitration_exact.)
+    assert abs(H0 - H1).max() <= 1e-10 * np.abs(H0.diagonal()).max()
+    co, cg = orc.counters(), gpu_ctx.counters()
+    for k in ("pieces", "piece_vertices", "new_vertices", "laguerre_edges", "sum_k", "sum_k_np"):
+        assert co[k] == cg[k], (k, co[k], cg[k])
+    gpu_ctx.set_stats(False)
+
+
+def test_general_mesh_path_equals_grid_path(gpu_ctx, oracle_mod):
+    case = common.make_case("c2", 0.01, "0.4")
+    common.load_engine(gpu_ctx, case)
+    f1, g1, H1 = gpu_ctx.kantorovich(case["w"])
+    common.load_engine(gpu_ctx, case, as_general_mesh=True)
+    f2, g2, H2 = gpu_ctx.kantorovich(case["w"])
+    assert abs(f1 - f2) <= 1e-12 * abs(f1)
+    assert np.abs(g1 - g2).max() <= 1e-12 * np.abs(g1).max()
+    assert common.same_pattern(H1, H2)
+
+
+def test_mass_conservation_full_size(gpu_ctx):
+    """tests/test_quantization.cpp:78-79 at BASELINE size: sum of cell masses = total mass."""
+    case = common.make_case("c2", 1.0, "zero")
+    tm = gpu_ctx.set_grid(case["cfg"]["n"], case["cfg"]["m"], case["cfg"]["rho"])
+    gpu_ctx.set_points(case["X"])
+    f, g, H = gpu_ctx.kantorovich(case["w"])
+    assert abs(g.sum() - tm) <= 1e-11 * tm
+    rs = np.abs(np.asarray(H.sum(axis=1))).max()
+    assert rs <= 1e-9 * np.abs(H.diagonal()).max()
+    assert abs(H - H.T).max() <= 1e-9 * np.abs(H.diagonal()).max()
+
+
+def test_tiny_cell_arbitration_exact(gpu_ctx, oracle_mod):
+    """Where engine and oracle differ most (a near-hidden cell), exact rational arithmetic sides with
+    the engine: its cell-local coordinates avoid the cancellation of the reference's global-coordinate
+    radical axis (predicates.hpp:46-52)."""
+    from fractions import Fraction as Fr
+    import math
+    import scipy.sparse as sp
+    case = common.make_case("c1", 0.2, "0.3")
+    X, w = case["X"], case["w"]
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(w)
+    common.load_engine(gpu_ctx, case)
+    f1, g1, H1 = gpu_ctx.kantorovich(w)
+    D = sp.coo_matrix(H0 - H1)
+    k = int(np.argmax(np.abs(D.data) / np.abs(H0.diagonal())[D.row]))
+    i = int(D.row[k])
+    F = lambda v: Fr(float(v))
+    xi, yi, wi = F(X[i, 0]), F(X[i, 1]), F(w[i])
+    poly = [(Fr(0), Fr(0)), (Fr(1), Fr(0)), (Fr(1), Fr(1)), (Fr(0), Fr(1))]
+    tags = [-1, -2, -3, -4]
+    cols = [int(c) for c in H0.getrow(i).indices if c != i]
+    cand = set(cols)
+    for c in cols:
+        cand |= {int(q) for q in H0.getrow(c).indices}
+    cand.discard(i)
+    for j in sorted(cand):
+        xj, yj, wj = F(X[j, 0]), F(X[j, 1]), F(w[j])
+        a, b, c = 2 * (xi - xj), 2 * (yi - yj), -xi * xi - yi * yi + xj * xj + yj * yj + wi - wj
+        out, ot = [], []
+        n = len(poly)
+        for q in range(n):
+            p0, p1 = poly[q], poly[(q + 1) % n]
+            s0, s1 = a * p0[0] + b * p0[1] + c, a * p1[0] + b * p1[1] + c
+            if s0 > 0:
+                out.append(p0); ot.append(tags[q])
+                if not s1 > 0:
+                    t = s0 / (s0 - s1); out.append((p0[0] + t * (p1[0] - p0[0]), p0[1] + t * (p1[1] - p0[1]))); ot.append(j)
+            elif s1 > 0:
+                t = s0 / (s0 - s1); out.append((p0[0] + t * (p1[0] - p0[0]), p0[1] + t * (p1[1] - p0[1]))); ot.append(tags[q])
+        poly, tags = out, ot
+    n = len(poly)
+    area = float(sum(poly[q][0] * poly[(q + 1) % n][1] - poly[(q + 1) % n][0] * poly[q][1] for q in range(n)) / 2)
+    diag = 0.0
+    for q in range(n):
+        if tags[q] >= 0:
+            p0, p1 = poly[q], poly[(q + 1) % n]
+            l = math.sqrt(float((p1[0] - p0[0]) ** 2 + (p1[1] - p0[1]) ** 2))
+            diag += l / (2 * math.hypot(X[i, 0] - X[tags[q], 0], X[i, 1] - X[tags[q], 1]))
+    assert abs(g1[i] - area) <= 1e-10 * area
+    assert abs(H1[i, i] - diag) <= 1e-10 * diag
+    assert abs(H1[i, i] - diag) <= abs(H0[i, i] - diag) + 1e-15
+
+
+@pytest.mark.parametrize("fname", ["c1_n50_w", "c1r_n200", "c2_n300_w", "c3_n500_w"])
+def test_golden_fixtures(gpu_ctx, fname):
+    """Committed golden vectors (tests/golden, generated by make_golden.py from the oracle)."""
+    import os
+    import scipy.sparse as sp
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", fname + ".npz"))
+    if str(z["kind"]) == "grid":
+        gpu_ctx.set_grid(int(z["n"]), int(z["m"]), z["rho"])
+    else:
+        gpu_ctx.set_mesh(z["vx"], z["vy"], z["tri"], z["abc"])
+    gpu_ctx.set_points(z["X"])
+    f, g, H = gpu_ctx.kantorovich(z["w"])
+    H0 = sp.csr_matrix((z["H_data"], z["H_indices"], z["H_indptr"]), shape=H.shape)
+    assert abs(f - float(z["f"])) <= 1e-10 * abs(float(z["f"]))
+    assert np.abs(g - z["g"]).max() <= 1e-10 * np.abs(z["g"]).max()
+    assert common.same_pattern(H0, H)
+    assert abs(H - H0).max() <= 1e-10 * np.abs(H0.diagonal()).max()
+
+
+def test_moments_and_lloyd_match_oracle(gpu_ctx, oracle_mod):
+    case = common.make_case("c2", 0.01, "0.3")
+    orc = common.oracle_for(oracle_mod, case)
+    common.load_engine(gpu_ctx, case)
+    ref = orc.moments(case["w"], 2)
+    m, m1, m2 = gpu_ctx.moments(case["w"], 2)
+    got = np.c_[m, m1, m2]
+    assert (np.abs(got - ref).max(axis=0) <= 1e-11 * np.abs(ref).max(axis=0)).all()
+    m, c = gpu_ctx.lloyd(np.zeros(case["N"]))
+    m0, c0 = orc.lloyd(np.zeros(case["N"]))
+    assert np.abs(m - m0).max() <= 1e-11 * m0.max() and np.abs(c - c0).max() <= 1e-11
+
+
+def test_pieces_match_oracle(gpu_ctx, oracle_mod):
+    """voronoi_triangulation_intersection: same set of (cell, face) pieces, same polygons."""
+    case = common.make_case("c2", 0.005, "0.4")
+    orc = common.oracle_for(oracle_mod, case)
+    orc.kantorovich(case["w"], mode=oracle_mod.MODE_RECORD | 1)
+    c0, f0, p0, t0, xy0 = orc.pieces()
+    common.load_engine(gpu_ctx, case)
+    c1, f1, p1, t1, xy1 = gpu_ctx.pieces(case["w"])
+    key0 = {(int(c), int(f)): k for k, (c, f) in enumerate(zip(c0, f0))}
+    key1 = {(int(c), int(f)): k for k, (c, f) in enumerate(zip(c1, f1))}
+    assert set(key0) == set(key1)
+    for kf, a in key0.items():
+        b = key1[kf]
+        A, B = xy0[p0[a]:p0[a + 1]], xy1[p1[b]:p1[b + 1]]
+        assert len(A) == len(B)
+        ta, tb = list(t0[p0[a]:p0[a + 1]]), list(t1[p1[b]:p1[b + 1]])
+        # same cyclic sequence of (tag, vertex) up to rotation
+        rot = [r for r in range(len(A)) if tb[r:] + tb[:r] == ta]
+        assert rot, (kf, ta, tb)
+        assert min(np.abs(np.roll(B, -r, axis=0) - A).max() for r in rot) < 1e-12
+
+
+def test_ot_solve_matches_oracle_newton(gpu_ctx, oracle_mod):
+    """Full damped Newton: same iteration / evaluation counts, weights and cost within 1e-8."""
+    case = common.make_case("c2", 0.01, "zero")
+    orc = common.oracle_for(oracle_mod, case)
+    common.load_engine(gpu_ctx, case)
+    N = case["N"]
+    nu = np.full(N, gpu_ctx.total_mass / N)
+    x0, st0, _ = oracle_mod.ot_solve(orc, nu, eps_g=1e-9)
+    x1, st1, rc = gpu_ctx.ot_solve(nu, eps_g=1e-9)
+    assert rc == 0
+    assert st1["niter"] == st0["niter"] and st1["neval"] == st0["neval"]
+    assert np.abs((x1 - x1[-1]) - (x0 - x0[-1])).max() <= 1e-8
+    f0 = orc.kantorovich(x0)[0] - nu.dot(x0)
+    assert abs(st1["fval"] - f0) <= 1e-8 * abs(f0)
+    assert st1["final_norm"] < 1e-9
+
+
+def test_solve_laplacian_matrix(gpu_ctx, oracle_mod):
+    case = common.make_case("c1", 0.1, "0.3")
+    orc = common.oracle_for(oracle_mod, case)
+    f, g, H = orc.kantorovich(case["w"])
+    rhs = g - g.mean()
+    d0 = oracle_mod.solve_laplacian_matrix(H, rhs, direct=True)
+    d1, it = gpu_ctx.solve_laplacian_matrix(H, rhs)
+    assert d1[-1] == 0 and it > 0
+    assert np.abs(d1 - d0).max() <= 1e-9 * np.abs(d0).max()
+
+
+def test_empty_initial_cell_is_reported(gpu_ctx):
+    """optimal_transport.hpp:139-148: ot_solve refuses to start when a cell is empty and leaves x alone."""
+    from mongeampere_b200 import capi, inputs
+    vx, vy, tri = inputs.unit_square_mesh()
+    gpu_ctx.set_mesh_pl(vx, vy, np.ones(4), tri)
+    gpu_ctx.set_points(np.array([[0.3, 0.5], [0.7, 0.5], [0.5, 0.5]]))
+    x_in = np.array([0.0, 0.0, -1.0])
+    x, st, rc = gpu_ctx.ot_solve(np.full(3, 1 / 3), x=x_in)
+    assert rc == capi.MA_EMPTY_CELL and np.array_equal(x, x_in) and st["neval"] == 1
