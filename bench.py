@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of BASELINE.json measured on B200: Laguerre-cell evaluations per second
+(cell masses + sparse Hessian of Kantorovich's functional, MA::kantorovich, kantorovich.hpp:37-141)
+at 1 M Diracs on the 2048 x 2048 image triangulation (BASELINE.json configs[2], "c3").
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # the CPU restatement on the host cores
+
+One step = one full evaluation (K1 per-eval part + K2 cells + K3 pieces + K4 CSR + reductions) of ALL
+N Diracs.  With N > 1 GPUs (torchrun, one rank per GPU) the Diracs are split into Morton tiles, one per
+rank, points / weights / mesh replicated (strong scaling of the same 1 M-Dirac problem, no data-path
+collective); the time is the max over ranks of the CUDA-event time on each engine's own stream.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      K3 (clipping + exact integration), the dominant kernel, against the fp64 DFMA peak
+                measured in the same run (MEASURED_PEAKS.json has no fp64 figure); roofline_hbm is the
+                CSR fill (K4) against the measured HBM copy bandwidth.
+  cpu_baseline  the oracle (CPU restatement, "port": the reference itself needs CGAL/Eigen/Boost,
+                absent here) on a bounded sample of the same workload.
+  e2e           the same metric through the reference-facing call (ma_kantorovich + ma_get_hessian_csr)
+                with pinned HOST buffers: H2D of the weights, D2H of g and of the Hessian CSR.
+  newton        metric 2: full damped-Newton OT solve (ma_ot_solve) wall seconds.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "laguerre_cell_evals_per_s"
+UNIT = "cell-evals/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", help="c1 | c2 | c3 | c4 | c5 (BASELINE.json configs)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrinks N and the grid (debug only)")
+    ap.add_argument("--weights", default="zero", help="'zero' or a float: random weights of that relative size")
+    ap.add_argument("--no-newton", action="store_true", help="skip the metric-2 Newton solve")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--newton-workload", default="c2")
+    ap.add_argument("--cpu-sample", type=float, default=0.1, help="fraction of the cells the CPU legs evaluate")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    names = {"c1": "c1: unit square, uniform density, 10k Diracs",
+             "c2": "c2: 512x512 PL Gaussian-mixture grid, 100k Diracs",
+             "c3": "c3: 2048x2048 image triangulation (8.38M faces), 1M Diracs",
+             "c4": "c4: 1024x1024 PL grid, 250k Diracs",
+             "c5": "c5: uniform density on 2 triangles, 4M Diracs"}
+    s = names[args.workload]
+    if args.scale != 1.0:
+        s += f" (scaled x{args.scale})"
+    return s
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        rows = [r for r in self.rows if t0 is None or (t0 - 0.05 <= r[0] <= t1 + 0.05)] or self.rows
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_case(args, name=None):
+    from tests import common
+    return common.make_case(name or args.workload, args.scale, args.weights)
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (the oracle as the timed baseline; the only place bench.py touches oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_case(args):
+    """Bounded sample of the workload: the same density/Dirac distribution at `cpu_sample` of the size
+    (N and the number of faces shrink together, so pieces per cell — the per-cell work — is unchanged)."""
+    from tests import common
+    scale = args.scale * args.cpu_sample
+    return common.make_case(args.workload, scale, args.weights), scale
+
+
+def run_cpu(case, nthreads, mode, repeats=1):
+    from oracle import oracle as O
+    from tests import common
+    orc = common.oracle_for(O, case, nthreads=nthreads)
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        orc.kantorovich(case["w"], mode=mode)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return case["N"] / best, best
+
+
+def cpu_baseline(args):
+    from oracle import oracle as O
+    O.build()
+    case, scale = cpu_sample_case(args)
+    cores = os.cpu_count() or 1
+    v_all, t_all = run_cpu(case, cores, O.MODE_PER_CELL, repeats=2)
+    v_one, t_one = run_cpu(case, 1, 0, repeats=1)  # the reference's own structure: serial global BFS
+    return {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{args.workload} at scale {scale:g}: {case['N']} Diracs, {case['cfg'].get('n', 2)}^2 grid, "
+                      f"one full evaluation, best of 2 ({t_all:.2f} s)",
+            "single_thread_bfs": {"value": v_one, "seconds": t_one, "cores": 1,
+                                  "note": "serial overlay BFS as in vti.hpp:219-313 (the reference is single-threaded)"}}
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    case, scale = cpu_sample_case(args)
+    cores = os.cpu_count() or 1
+    from tests import common
+    orc = common.oracle_for(O, case, nthreads=cores)
+    for _ in range(args.warmup):
+        orc.kantorovich(case["w"], mode=O.MODE_PER_CELL)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.kantorovich(case["w"], mode=O.MODE_PER_CELL)
+    dt = time.perf_counter() - t0
+    v = case["N"] * args.steps / dt
+    sample = (f"{args.workload} at scale {scale:g}: {case['N']} Diracs, {case['cfg'].get('n', 2)}^2 grid per step, "
+              f"OpenMP per-cell overlay on {cores} threads")
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(args), "sample": sample},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
+           "note": "CPU restatement of the reference path (oracle/ma_oracle.cpp); the reference itself needs "
+                   "CGAL/Eigen/Boost/CImg which are not in this image"}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# the engine
+# --------------------------------------------------------------------------------------------------
+def main_b200(args, rank, world, local_rank):
+    import torch
+    from mongeampere_b200 import capi
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    case = make_case(args)
+    N = case["N"]
+    ctx = capi.Context(local_rank)  # raises without the CUDA library / a device: no fallback
+    from tests import common
+    common.load_engine(ctx, case)
+    ctx.set_partition(rank, world)
+    ctx.set_weights(case["w"])
+    n_local = int(ctx.info("cell_hi") - ctx.info("cell_lo"))
+
+    # ---- counters of this input (algorithmic flops), one untimed evaluation with stats on ----
+    ctx.set_stats(True)
+    ctx.evaluate(True)
+    cnt = ctx.counters()
+    ctx.set_stats(False)
+    flops_local = capi.algorithmic_flops(cnt)
+    nnz_local = int(ctx.info("nnz"))
+    fp64_peak = ctx.fp64_peak()
+
+    # ---- device-resident evaluation: W warm-up + K timed steps ----
+    ctx.set_profiling(True)
+    for _ in range(args.warmup):
+        ctx.evaluate(True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    l0 = ctx.info("launches")
+    stage = {k: 0.0 for k in capi.TIMING_NAMES}
+    barrier()
+    t_wall0 = time.time()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        ctx.evaluate(True)
+        for k, v in ctx.timings().items():
+            stage[k] += v
+    ms_total = ctx.timer_stop()
+    barrier()
+    t_wall1 = time.time()
+    launches = int(ctx.info("launches") - l0)
+    ctx.set_profiling(False)
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = N / (ms_step * 1e-3)
+    k3_ms = stage["pieces"] / args.steps
+    k2_ms = stage["cells"] / args.steps
+    k4_ms = stage["csr"] / args.steps
+    flops_total = sum_over_ranks(flops_local)
+    nnz_total = int(sum_over_ranks(nnz_local))
+
+    # ---- end to end through the reference-facing call, host (pinned) buffers ----
+    w_h = torch.from_numpy(np.ascontiguousarray(case["w"])).pin_memory().numpy()
+    g_h = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
+    cap = int(nnz_local * 1.05) + 64
+    ptr_h = torch.empty(N + 1, dtype=torch.int32).pin_memory().numpy()
+    col_h = torch.empty(cap, dtype=torch.int32).pin_memory().numpy()
+    val_h = torch.empty(cap, dtype=torch.float64).pin_memory().numpy()
+    for _ in range(max(1, args.warmup)):
+        ctx.kantorovich_into(w_h, g_h, ptr_h, col_h, val_h)
+    e2e_steps = max(3, args.steps // 2)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        f_e2e, nnz_e2e = ctx.kantorovich_into(w_h, g_h, ptr_h, col_h, val_h)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    h2d = 8 * N
+    d2h = 8 * N + 4 * (N + 1) + 12 * nnz_e2e
+    mass_sum = sum_over_ranks(float(g_h.sum()))
+
+    # ---- metric 2: full Newton solve (single GPU engine; the multi-GPU solve is not built yet) ----
+    newton = None
+    if not args.no_newton and rank == 0:
+        nctx = capi.Context(local_rank)
+        ncase = make_case(args, args.newton_workload)
+        common.load_engine(nctx, ncase)
+        nu = np.full(ncase["N"], nctx.total_mass / ncase["N"])
+        t0 = time.perf_counter()
+        _, st, rc = nctx.ot_solve(nu, eps_g=1e-7, maxiter=100, verbose=False)
+        newton = {"workload": args.newton_workload, "N": ncase["N"], "seconds": time.perf_counter() - t0,
+                  "status": capi.STATUS_NAMES[rc], "niter": st["niter"], "neval": st["neval"],
+                  "cg_iters": st["cg_iters"], "final_norm": st["final_norm"], "gpus": 1}
+        nctx.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        peaks = load_peaks()
+        hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+        k4_bytes = 12.0 * nnz_local + 4.0 * (N + 1) + 4.0 * N  # CSR written + counts read
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "N": N, "faces": int(case["cfg"]["tri"].shape[0]),
+                       "weights": args.weights, "hessian": True, "nnz": nnz_total,
+                       "partition": f"{world} Morton tile(s) of Diracs, points/weights/mesh replicated",
+                       "l2": "no flush: one evaluation streams ~0.6 GB (201 MB of face coefficients + 0.4 GB of "
+                             "per-cell tables), larger than the 126 MB L2"},
+            "stages_ms": {"prep_K1": stage["prep"] / args.steps, "cells_K2": k2_ms, "pieces_K3": k3_ms,
+                          "reduce_scan": stage["reduce"] / args.steps, "csr_K4": k4_ms},
+            "roofline": {"bound": "fp64", "kernel": "k_pieces (K3: clipping + exact integration)",
+                         "achieved": flops_local / (k3_ms * 1e-3) / 1e12 if k3_ms > 0 else None,
+                         "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                         "frac": (flops_local / (k3_ms * 1e-3)) / fp64_peak if k3_ms > 0 else None,
+                         "traffic": None,
+                         "peak_source": "DFMA probe in this run (MEASURED_PEAKS.json has no fp64 figure)",
+                         "algorithmic_flops_per_launch": flops_local,
+                         "flops_per_cell": flops_total / N},
+            "roofline_hbm": {"bound": "hbm", "kernel": "k_csr_fill (K4)", "achieved": k4_bytes / (k4_ms * 1e-3) / 1e9
+                             if k4_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": k4_bytes / (k4_ms * 1e-3) / 1e9 / hbm_peak if k4_ms > 0 else None,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
+            "e2e": {"value": N / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "call": "ma_kantorovich + ma_get_hessian_csr, pinned host buffers"},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "check": {"mass_sum": mass_sum, "total_mass": ctx.total_mass,
+                      "rel_err": abs(mass_sum - ctx.total_mass) / ctx.total_mass if ctx.total_mass else None},
+            "counters_rank0": cnt,
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        if newton is not None:
+            out["newton"] = newton
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    main_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,12 @@ int ma_pieces_get(ma_ctx *ctx, int *cell, int *face, int *ptr, int *tag, double 
 int ma_set_weights(ma_ctx *ctx, const double *weights);
 int ma_evaluate(ma_ctx *ctx, int with_hessian);
 
+/* Multi-GPU: this context evaluates only the Morton tile `rank` of `nranks` of the Diracs (every cell is
+ * independent once points and weights are replicated, kantorovich.hpp:87-136 writes only g[idv] and
+ * row idv of h).  Masses and Hessian rows of the other tiles stay zero/empty in this context; fval,
+ * mass_sum and mass_min are the tile's partial values, to be combined by the caller (sum, sum, min). */
+int ma_set_partition(ma_ctx *ctx, int rank, int nranks);
+
 /* Laguerre adjacency found by the last evaluation (caller ordering, CSR): the neighbours whose
  * bisector supports an edge of (cell ∩ mesh bounding box). */
 int ma_get_adjacency(ma_ctx *ctx, int *ptr /* N+1 */, int *idx /* >= ptr[N] */, int capacity);
@@ -140,6 +146,9 @@ enum {
 /* CUDA-event times (ms) of the stages of the last ma_evaluate (profiling must be enabled). */
 int ma_set_profiling(ma_ctx *ctx, int on);
 int ma_get_timings(ma_ctx *ctx, float *ms /* MA_T_COUNT */);
+/* CUDA-event stopwatch on the context's own stream (torch.cuda.Event would not see it). */
+int ma_timer_start(ma_ctx *ctx);
+int ma_timer_stop(ma_ctx *ctx, float *ms);
 /* Counters of the last evaluation when stats are enabled: pieces, piece vertices, new vertices,
  * Laguerre edges, sum k_i, sum k_i*n_p, robust-predicate fallbacks, candidate triangles. */
 int ma_set_stats(ma_ctx *ctx, int on);

@@ -27,7 +27,7 @@ SYMBOLS = (
     "ma_set_image", "ma_set_points", "ma_kantorovich", "ma_get_hessian_csr", "ma_moments", "ma_lloyd",
     "ma_solve_laplacian", "ma_ot_solve", "ma_pieces_build", "ma_pieces_get", "ma_set_weights", "ma_evaluate",
     "ma_get_adjacency", "ma_set_profiling", "ma_get_timings", "ma_set_stats", "ma_get_counters", "ma_flush_l2",
-    "ma_measure_fp64_peak", "ma_set_option", "ma_get_info",
+    "ma_measure_fp64_peak", "ma_set_option", "ma_get_info", "ma_set_partition", "ma_timer_start", "ma_timer_stop",
 )
 
 
@@ -86,6 +86,9 @@ def load_library(path: str | None = None):
     L.ma_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.ma_get_info.argtypes = [vp, C.c_char_p]
     L.ma_get_info.restype = C.c_double
+    L.ma_set_partition.argtypes = [vp, C.c_int, C.c_int]
+    L.ma_timer_start.argtypes = [vp]
+    L.ma_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -187,6 +190,16 @@ class Context:
         H = sp.csr_matrix((val[:nnz.value], col[:nnz.value], ptr), shape=(self.N, self.N))
         return f.value, g, H
 
+    def kantorovich_into(self, w, g, rowptr, col, val):
+        """Same call with caller-owned (e.g. pinned) host buffers; col/val must hold >= nnz entries.
+        -> (fval, nnz)."""
+        f, nnz = C.c_double(), C.c_int()
+        self._ck(self.L.ma_kantorovich(self.h, _ptr(w), C.byref(f), _ptr(g), C.byref(nnz)))
+        if nnz.value > len(col):
+            raise MAError(MA_INVALID, f"Hessian has {nnz.value} entries, buffers hold {len(col)}")
+        self._ck(self.L.ma_get_hessian_csr(self.h, _ptr(rowptr), _ptr(col), _ptr(val)))
+        return f.value, nnz.value
+
     def moments(self, w, order=1):
         """first_moment / second_moment (lloyd.hpp:30-123) -> masses, m1 (N,2)[, m2 (N,3)]."""
         w = _f64(w)
@@ -253,6 +266,17 @@ class Context:
 
     def evaluate(self, hessian=True):
         self._ck(self.L.ma_evaluate(self.h, int(hessian)))
+
+    def set_partition(self, rank, nranks):
+        self._ck(self.L.ma_set_partition(self.h, rank, nranks))
+
+    def timer_start(self):
+        self._ck(self.L.ma_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.L.ma_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def adjacency(self):
         ptr = np.empty(self.N + 1, np.int32)

@@ -33,12 +33,16 @@ struct ma_ctx {
   int sm_count = 148;
 
   // options
-  int kmax = 16;
-  int bin_target = 2;  // average Diracs per leaf bin
+  int kmax = 16;       // current capacity class (16 / 32 / 64 neighbours per cell)
+  int kmax_base = 16;  // class every evaluation starts from
+  bool capacity_hit = false;  // last evaluation failed because a cell exceeded the largest class
+  int bin_target = 4;  // average Diracs per leaf bin (upper bound)
   double cg_rtol = 1e-12;
   int cg_maxit = 200000;
   double filter_tol = 1e-11;
   int profiling = 0, stats = 0;
+  int part_rank = 0, part_n = 1;  // Morton tile of the Diracs this context evaluates
+  long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
 
   // mesh
   int mesh_kind = MESH_NONE;
@@ -78,6 +82,7 @@ struct ma_ctx {
 
   // timing
   cudaEvent_t ev[MA_T_COUNT + 2] = {};
+  cudaEvent_t ev_user[2] = {};
   float t_ms[MA_T_COUNT] = {};
   int64_t host_counters[CNT_N] = {};
 };
@@ -131,6 +136,7 @@ int scan_i32(ma_ctx *c, const int *in, int *out, int n) {
   k_scan_tiles<<<nt, SCAN_NT, 0, c->stream>>>(in, out, ts, n);
   k_scan_sums<<<1, SCAN_NT, 0, c->stream>>>(ts, nt, ts + nt);
   k_scan_add<<<nt, SCAN_NT, 0, c->stream>>>(out, ts, n, ts + nt);
+  c->launches += 3;
   CK(cudaGetLastError());
   return MA_OK;
 }
@@ -141,6 +147,7 @@ int reduce4(ma_ctx *c, const double *a, const double *b, int n, double *out_dev)
   int nb = std::min(RED_BLOCKS, std::max(1, cdiv(n, RED_NT)));
   k_reduce_stage1<<<nb, RED_NT, 0, c->stream>>>(a, b, n, c->red_partial.as<double>());
   k_reduce_stage2<<<1, RED_NT, 0, c->stream>>>(c->red_partial.as<double>(), nb, out_dev);
+  c->launches += 2;
   CK(cudaGetLastError());
   return MA_OK;
 }
@@ -214,6 +221,7 @@ extern "C" int ma_create(ma_ctx **out, int device) {
   CK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+  for (auto &ev : c->ev_user) CK(cudaEventCreate(&ev));
   return MA_OK;
 }
 
@@ -232,6 +240,8 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
+      if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_user)
       if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
   }
@@ -253,7 +263,7 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   if (n == "kmax") {
     int k = (int)value;
     if (k != 16 && k != 32 && k != 64) return fail(c, MA_INVALID, "kmax must be 16, 32 or 64");
-    c->kmax = k;
+    c->kmax = c->kmax_base = k;
     invalidate_eval(c);
   } else if (n == "bin_target") c->bin_target = std::max(1, (int)value);
   else if (n == "cg_rtol") c->cg_rtol = value;
@@ -276,6 +286,10 @@ extern "C" double ma_get_info(ma_ctx *c, const char *name) {
   if (n == "mass_min") return c->mass_min;
   if (n == "cg_iters") return (double)c->last_cg_iters;
   if (n == "mesh_kind") return c->mesh_kind;
+  if (n == "launches") return (double)c->launches;
+  if (n == "fval") return c->fval;
+  if (n == "cell_lo") return (double)((long long)c->N * c->part_rank / c->part_n);
+  if (n == "cell_hi") return (double)((long long)c->N * (c->part_rank + 1) / c->part_n);
   return -1;
 }
 
@@ -472,6 +486,8 @@ namespace {
 int fill_params(ma_ctx *c, Params &p) {
   memset(&p, 0, sizeof p);
   p.N = c->N;
+  p.cell_lo = (int)((long long)c->N * c->part_rank / c->part_n);
+  p.cell_hi = (int)((long long)c->N * (c->part_rank + 1) / c->part_n);
   p.xs = c->xs.as<double>(); p.ys = c->ys.as<double>(); p.ws = c->ws.as<double>();
   p.L = c->L; p.px0 = c->px0; p.py0 = c->py0; p.ph = c->ph;
   p.bin_start = c->bin_start.as<int>();
@@ -499,14 +515,16 @@ int fill_params(ma_ctx *c, Params &p) {
 template <int MAXV, int NT> int launch_cells(ma_ctx *c, const Params &p) {
   size_t sm = cells_smem_bytes<MAXV, NT>();
   CK(cudaFuncSetAttribute(k_cells<MAXV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_cells<MAXV, NT><<<cdiv(p.N, NT), NT, sm, c->stream>>>(p);
+  k_cells<MAXV, NT><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
+  c->launches++;
   CK(cudaGetLastError());
   return MA_OK;
 }
 template <int KMAX, int MAXV, int MODE> int launch_pieces(ma_ctx *c, const Params &p) {
   size_t sm = pieces_warp_bytes<KMAX, MAXV>() * PIECES_WPB;
   CK(cudaFuncSetAttribute(k_pieces<KMAX, MAXV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_pieces<KMAX, MAXV, MODE><<<cdiv(p.N, PIECES_WPB), PIECES_WPB * 32, sm, c->stream>>>(p);
+  k_pieces<KMAX, MAXV, MODE><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, PIECES_WPB)), PIECES_WPB * 32, sm, c->stream>>>(p);
+  c->launches++;
   CK(cudaGetLastError());
   return MA_OK;
 }
@@ -550,6 +568,7 @@ int run_cells(ma_ctx *c, Params &p) {
   k_wmax_leaf<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(c->ws.as<double>(), c->bin_start.as<int>(), c->L,
                                                                c->wmax.as<double>());
   if (c->L >= 5) k_wmax_top<<<1, 1024, 0, c->stream>>>(c->L, c->wmax.as<double>());
+  c->launches += 2 + (c->L >= 5);
   CK(cudaGetLastError());
   if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PREP + 1], c->stream));
   CKR(launch_cells_kmax(c, p));
@@ -561,6 +580,8 @@ int run_cells(ma_ctx *c, Params &p) {
 template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
   if (c->mesh_kind == MESH_NONE) return fail(c, MA_INVALID, "no mesh set");
   if (c->N < 1) return fail(c, MA_INVALID, "no points set");
+  c->capacity_hit = false;
+  c->kmax = c->kmax_base;
   for (int attempt = 0; attempt < 3; ++attempt) {
     CKR(alloc_eval(c));
     if (MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) CKR(ensure(c, c->mom, (size_t)c->N * 48));
@@ -569,13 +590,23 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
     if (c->stats) CK(cudaMemsetAsync(c->counters.p, 0, CNT_N * 8, c->stream));
     if (c->profiling) CK(cudaEventRecord(c->ev[0], c->stream));
+    const int lo = p.cell_lo, nloc = p.cell_hi - p.cell_lo;
+    if (MODE == MODE_KANTOROVICH && c->part_n > 1) {
+      // rows outside this context's Morton tile are empty here (another GPU owns them)
+      const size_t N = c->N, hi = p.cell_hi;
+      auto zero = [&](Buf &b, size_t esz) {
+        if (lo) cudaMemsetAsync(b.p, 0, (size_t)lo * esz, c->stream);
+        if (hi < N) cudaMemsetAsync((char *)b.p + hi * esz, 0, (N - hi) * esz, c->stream);
+      };
+      zero(c->mass, 8); zero(c->fcell, 8); zero(c->touched, 8); zero(c->rowcnt, 4);
+    }
     CKR(run_cells(c, p));
     CKR(launch_pieces_mode<MODE>(c, p));
     if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
     if (MODE == MODE_KANTOROVICH) {
       if (with_hessian) CKR(scan_i32(c, c->rowcnt.as<int>(), c->rowptr.as<int>(), c->N));
-      CKR(reduce4(c, c->fcell.as<double>(), nullptr, c->N, c->red_out.as<double>()));
-      CKR(reduce4(c, c->mass.as<double>(), nullptr, c->N, c->red_out.as<double>() + 4));
+      CKR(reduce4(c, c->fcell.as<double>() + lo, nullptr, nloc, c->red_out.as<double>()));
+      CKR(reduce4(c, c->mass.as<double>() + lo, nullptr, nloc, c->red_out.as<double>() + 4));
     }
     int h_flags = 0;
     double red[8] = {0};
@@ -588,7 +619,10 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     }
     CK(cudaStreamSynchronize(c->stream));
     if (h_flags & (FLAG_CELL_OVERFLOW | FLAG_PIECE_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
-      if (c->kmax >= 64) return fail(c, MA_INVALID, "polygon capacity exceeded even at kmax=64 (flags=%d)", h_flags);
+      if (c->kmax >= 64) {
+        c->capacity_hit = true;
+        return fail(c, MA_INVALID, "polygon capacity exceeded even at kmax=64 (flags=%d)", h_flags);
+      }
       c->kmax *= 2;  // escalate to the next capacity class and redo the evaluation
       continue;
     }
@@ -608,6 +642,7 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
           case 32: k_csr_fill<32><<<cdiv(N, 128), 128, 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
           default: k_csr_fill<64><<<cdiv(N, 128), 128, 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
         }
+        c->launches++;
         CK(cudaGetLastError());
         if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CSR + 1], c->stream));
       }
@@ -639,6 +674,29 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
 
 }  // namespace
 
+extern "C" int ma_set_partition(ma_ctx *c, int rank, int nranks) {
+  if (!c) return MA_INVALID;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, MA_INVALID, "ma_set_partition: bad rank %d of %d", rank, nranks);
+  c->part_rank = rank;
+  c->part_n = nranks;
+  invalidate_eval(c);
+  return MA_OK;
+}
+
+extern "C" int ma_timer_start(ma_ctx *c) {
+  NEED_CTX();
+  CK(cudaEventRecord(c->ev_user[0], c->stream));
+  return MA_OK;
+}
+extern "C" int ma_timer_stop(ma_ctx *c, float *ms) {
+  NEED_CTX();
+  if (!ms) return MA_INVALID;
+  CK(cudaEventRecord(c->ev_user[1], c->stream));
+  CK(cudaEventSynchronize(c->ev_user[1]));
+  CK(cudaEventElapsedTime(ms, c->ev_user[0], c->ev_user[1]));
+  return MA_OK;
+}
+
 extern "C" int ma_set_weights(ma_ctx *c, const double *w) {
   NEED_CTX();
   if (!w || c->N < 1) return fail(c, MA_INVALID, "ma_set_weights: bad arguments");
@@ -661,6 +719,7 @@ extern "C" int ma_kantorovich(ma_ctx *c, const double *w, double *fval, double *
     CKR(ensure(c, c->cg_out, (size_t)c->N * 8));
     k_scatter_to_caller<<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->mass.as<double>(), c->perm.as<int>(), c->N,
                                                                c->cg_out.as<double>());
+    c->launches++;
     CK(cudaMemcpyAsync(g, c->cg_out.p, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
@@ -682,6 +741,7 @@ extern "C" int ma_get_hessian_csr(ma_ctx *c, int *rowptr, int *col, double *val)
   k_csr_to_caller<<<cdiv(N, 128), 128, 0, c->stream>>>(N, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(),
                                                        c->pos.as<int>(), c->perm.as<int>(), c->cptr.as<int>(),
                                                        c->ccol.as<int>(), c->cval.as<double>());
+  c->launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(rowptr, c->cptr.p, (size_t)(N + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (c->nnz) {
@@ -852,6 +912,7 @@ int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double 
   CK(cudaMemsetAsync(c->part_rz.p, 0, (size_t)2 * nblocks * 8, c->stream));
   k_pcg_init<<<nblocks, PCG_NT, 0, c->stream>>>(s, g, sign);
   k_pcg_init2<<<1, PCG_NT, 0, c->stream>>>(s);
+  c->launches += 2;
   CK(cudaGetLastError());
   double h_scal[4];
   int h_flag = 0;
@@ -882,6 +943,7 @@ int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double 
     const double tol2 = c->cg_rtol * c->cg_rtol * gg;
     while (it < c->cg_maxit) {
       CK(cudaGraphLaunch(exec, c->stream));
+      c->launches += 2 * batch + 1;
       CK(cudaMemcpyAsync(&rr, c->scal.as<double>() + 3, 8, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       it += batch;
@@ -961,9 +1023,18 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
   // f(x): evaluation + (m, g = m - nu, f - nu.x)   optimal_transport.hpp:110-120
   auto feval = [&]() -> int {
     ++neval;
-    CKR(evaluate_mode<MODE_KANTOROVICH>(c, true));
+    int rc_e = evaluate_mode<MODE_KANTOROVICH>(c, true);
+    if (rc_e != MA_OK && c->capacity_hit && neval > 1) {
+      // a trial point so wild that one cell has > 64 Laguerre neighbours: the reference would evaluate it and
+      // reject it (hidden neighbours => min m = 0 < eps0, optimal_transport.hpp:167); reject it here too
+      mmin = -1.0;
+      gnorm = 1e300;
+      return MA_OK;
+    }
+    CKR(rc_e);
     // ws is the sorted copy of the weights used by this evaluation
     k_sub<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->mass.as<double>(), c->nu_s.as<double>(), c->g_s.as<double>());
+    c->launches++;
     CKR(reduce4(c, c->g_s.as<double>(), nullptr, N, c->red_out.as<double>()));
     CKR(reduce4(c, c->ws.as<double>(), c->nu_s.as<double>(), N, c->red_out.as<double>() + 4));
     double red[8];
@@ -1017,6 +1088,7 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
                                                      c->scratch_d.as<double>());
       k_scatter_to_caller<<<cdiv(N, 256), 256, 0, c->stream>>>(c->scratch_d.as<double>(), c->perm.as<int>(), N,
                                                                c->w.as<double>());
+      c->launches += 2;
       CKR(feval());
       if (mmin >= eps0 && gnorm <= (1 - alpha / 2) * n0) break;
       alpha *= .5;

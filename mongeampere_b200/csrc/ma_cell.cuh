@@ -21,8 +21,9 @@ enum { CNT_PIECES = 0, CNT_VERTS = 1, CNT_NEWV = 2, CNT_LEDGES = 3, CNT_SUMK = 4
        CNT_CAND = 7, CNT_N = 8 };
 
 struct Params {
-  // Diracs, Morton-bin order
+  // Diracs, Morton-bin order; this context evaluates the cells [cell_lo, cell_hi) (its Morton tile)
   int N;
+  int cell_lo, cell_hi;
   const double *xs, *ys, *ws;
   // quadtree of bins over the Diracs: level l has 4^l nodes, node (l, code) covers a square of side
   // ph * 2^(L-l); wmax holds all levels, level l at offset (4^l - 1) / 3.
@@ -92,56 +93,93 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
     else { nx = 1; ny = 0; cl = bx0; }
   };
   const double NEG_INF = -1.0 / 0.0;
-  unsigned stk[52];
-  int sp = 0;
-  stk[sp++] = 0u;
-  while (sp > 0 && n > 0) {
-    unsigned e = stk[--sp];
-    int l = (int)(e >> 26);
-    unsigned code = e & 0x3ffffffu;
-    double wm = p.wmax[(((size_t)1 << (2 * l)) - 1) / 3 + code];
-    if (wm == NEG_INF) continue;
-    double S = p.ph * (double)(1u << (p.L - l));
-    double ox = p.px0 + (double)morton_compact1(code) * S - xi;
-    double oy = p.py0 + (double)morton_compact1(code >> 1) * S - yi;
-    double dx = fmax(fmax(ox, -(ox + S)), 0.0), dy = fmax(fmax(oy, -(oy + S)), 0.0);
-    double d2 = dx * dx + dy * dy;
-    if (d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) continue;
-    if (l < p.L) {
-      // children, nearest first (pushed in reverse)
-      double cx = ox + 0.5 * S, cy = oy + 0.5 * S;
-      unsigned q0 = (cx <= 0.0 ? 1u : 0u) | (cy <= 0.0 ? 2u : 0u);
-      bool xfirst = fabs(cx) < fabs(cy);
-      unsigned q1 = q0 ^ (xfirst ? 1u : 2u), q2 = q0 ^ (xfirst ? 2u : 1u), q3 = q0 ^ 3u;
-      unsigned base = ((unsigned)(l + 1) << 26) | (code << 2);
-      if (sp + 4 > 52) { *flags_out |= FLAG_STACK_OVERFLOW; return -1; }
-      stk[sp++] = base | q3; stk[sp++] = base | q2; stk[sp++] = base | q1; stk[sp++] = base | q0;
-      continue;
+  // ---- expanding-radius search over the quadtree ------------------------------------------------
+  // A plain nearest-first DFS degenerates for a Dirac next to a high-level quadrant boundary: until
+  // the polygon is cut on every side its security radius is the whole box, so nothing is pruned and
+  // the nearest quadrant is searched exhaustively.  Instead the tree is walked in passes with a
+  // distance cap that doubles: pass q handles exactly the sites with prev < |y_j - y_i| <= cap, and
+  // the search ends with one uncapped pass (pruned by the security test alone) once the polygon fits
+  // in the disk of radius cap/2.
+  // first cap: side of the deepest own ancestor holding >= 8 sites (counts come from the Morton prefix)
+  double cap;
+  {
+    const double pinv = 1.0 / p.ph;
+    const int G = 1 << p.L;
+    int bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1), by = min(max((int)((yi - p.py0) * pinv), 0), G - 1);
+    unsigned code = morton2((unsigned)bx, (unsigned)by);
+    int l = p.L;
+    while (l > 0) {
+      int sh = 2 * (p.L - l);
+      unsigned c0 = code >> sh;
+      if (p.bin_start[(c0 + 1u) << sh] - p.bin_start[c0 << sh] >= 8) break;
+      --l;
     }
-    const int b0 = p.bin_start[code], b1 = p.bin_start[code + 1];
-    for (int j = b0; j < b1 && n > 0; ++j) {
-      if (j == i) continue;
-      double Dx = p.xs[j] - xi, Dy = p.ys[j] - yi, wj = p.ws[j];
-      double dd2 = Dx * Dx + Dy * Dy;
-      if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
-        if (wj > wi || (wj == wi && j < i)) n = 0;
+    cap = 0.75 * p.ph * (double)(1u << (p.L - l));
+  }
+  double prev2 = -1.0;
+  unsigned stk[52];
+  for (int pass = 0; pass < 64 && n > 0; ++pass) {
+    const bool last = !(4.0 * R2 > cap * cap);  // polygon inside the disk of radius cap/2: finish uncapped
+    const double cap2 = last ? 1.0 / 0.0 : cap * cap;
+    int sp = 0;
+    stk[sp++] = 0u;
+    while (sp > 0 && n > 0) {
+      unsigned e = stk[--sp];
+      int l = (int)(e >> 26);
+      unsigned code = e & 0x3ffffffu;
+      double wm = p.wmax[(((size_t)1 << (2 * l)) - 1) / 3 + code];
+      if (wm == NEG_INF) continue;
+      double S = p.ph * (double)(1u << (p.L - l));
+      double ox = p.px0 + (double)morton_compact1(code) * S - xi;
+      double oy = p.py0 + (double)morton_compact1(code >> 1) * S - yi;
+      double dx = fmax(fmax(ox, -(ox + S)), 0.0), dy = fmax(fmax(oy, -(oy + S)), 0.0);
+      double d2 = dx * dx + dy * dy;
+      if (d2 > cap2) continue;
+      if (d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) continue;
+      {
+        double fx = fmax(fabs(ox), fabs(ox + S)), fy = fmax(fabs(oy), fabs(oy + S));
+        if (fx * fx + fy * fy <= prev2) continue;  // every site of this node was handled by an earlier pass
+      }
+      if (l < p.L) {
+        // children, nearest first (pushed in reverse)
+        double cx = ox + 0.5 * S, cy = oy + 0.5 * S;
+        unsigned q0 = (cx <= 0.0 ? 1u : 0u) | (cy <= 0.0 ? 2u : 0u);
+        bool xfirst = fabs(cx) < fabs(cy);
+        unsigned q1 = q0 ^ (xfirst ? 1u : 2u), q2 = q0 ^ (xfirst ? 2u : 1u), q3 = q0 ^ 3u;
+        unsigned base = ((unsigned)(l + 1) << 26) | (code << 2);
+        if (sp + 4 > 52) { *flags_out |= FLAG_STACK_OVERFLOW; return -1; }
+        stk[sp++] = base | q3; stk[sp++] = base | q2; stk[sp++] = base | q1; stk[sp++] = base | q0;
         continue;
       }
-      double s = dd2 + (wi - wj);
-      if (s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12)) continue;  // bisector beyond every vertex
-      double c = 0.5 * s;
-      unsigned long long in = 0ull;
-      for (int k = 0; k < n; ++k)
-        if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
-      unsigned long long full = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
-      if (in == full) continue;
-      if (in == 0ull) { n = 0; break; }
-      int n2 = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, j, lineof);
-      if (n2 < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
-      n = n2;
-      R2 = 0.0;
-      for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
+      const int b0 = p.bin_start[code], b1 = p.bin_start[code + 1];
+      for (int j = b0; j < b1 && n > 0; ++j) {
+        if (j == i) continue;
+        double Dx = p.xs[j] - xi, Dy = p.ys[j] - yi, wj = p.ws[j];
+        double dd2 = Dx * Dx + Dy * Dy;
+        if (dd2 <= prev2 || dd2 > cap2) continue;  // handled by an earlier pass / left to a later one
+        if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
+          if (wj > wi || (wj == wi && j < i)) n = 0;
+          continue;
+        }
+        double s = dd2 + (wi - wj);
+        if (s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12)) continue;  // bisector beyond every vertex
+        double c = 0.5 * s;
+        unsigned long long in = 0ull;
+        for (int k = 0; k < n; ++k)
+          if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
+        unsigned long long full = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+        if (in == full) continue;
+        if (in == 0ull) { n = 0; break; }
+        int n2 = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, j, lineof);
+        if (n2 < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
+        n = n2;
+        R2 = 0.0;
+        for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
+      }
     }
+    if (last) break;
+    prev2 = cap2;
+    cap *= 2.0;
   }
   return n;
 }

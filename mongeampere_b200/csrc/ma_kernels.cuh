@@ -263,8 +263,8 @@ template <int MAXV, int NT> __global__ void __launch_bounds__(NT) k_cells(Params
   double *sx = reinterpret_cast<double *>(smem_raw);
   double *sy = sx + MAXV * NT;
   int *st = reinterpret_cast<int *>(sy + MAXV * NT);
-  int i = blockIdx.x * NT + threadIdx.x;
-  if (i >= p.N) return;
+  int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
+  if (i >= p.cell_hi) return;
   PolyRef<NT> P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
   int fl = 0;
   int n = cell_build<NT>(p, i, P, MAXV, &fl);
@@ -285,8 +285,8 @@ template <int KMAX, int MAXV> constexpr size_t pieces_warp_bytes() {
 template <int KMAX, int MAXV, int MODE> __global__ void __launch_bounds__(PIECES_WPB * 32) k_pieces(Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * PIECES_WPB + warp;
-  if (i >= p.N) return;  // warp-uniform; no block-level barrier below
+  const int i = p.cell_lo + blockIdx.x * PIECES_WPB + warp;
+  if (i >= p.cell_hi) return;  // warp-uniform; no block-level barrier below
   unsigned char *base = smem_raw + (size_t)warp * pieces_warp_bytes<KMAX, MAXV>();
   double *d = reinterpret_cast<double *>(base);
   CellTable T;

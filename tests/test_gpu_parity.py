@@ -182,7 +182,7 @@ def test_ot_solve_matches_oracle_newton(gpu_ctx, oracle_mod):
 
 
 def test_solve_laplacian_matrix(gpu_ctx, oracle_mod):
-    case = common.make_case("c1", 0.1, "0.3")
+    case = common.make_case("c1", 0.1, "zero")  # Voronoi cells: none hidden, H non-singular once grounded
     orc = common.oracle_for(oracle_mod, case)
     f, g, H = orc.kantorovich(case["w"])
     rhs = g - g.mean()
