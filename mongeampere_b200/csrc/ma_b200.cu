@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,7 +41,7 @@ struct ma_ctx {
   double cg_rtol = 1e-12;
   int cg_maxit = 200000;
   double filter_tol = 1e-11;
-  int profiling = 0, stats = 0;
+  int profiling = 0, stats = 0, trace = 0;
   int part_rank = 0, part_n = 1;  // Morton tile of the Diracs this context evaluates
   long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
 
@@ -57,6 +58,8 @@ struct ma_ctx {
   // points
   int N = 0;
   Buf x, y, xs, ys, perm, pos, code, bin_count, bin_start, wmax;
+  Buf code_s, pre0, pre1, fs_tiles, nodeG, nodeA;  // per-node supporting planes (ma_geom.cuh)
+  bool abort_on_empty = false, aborted = false;
   int L = 0;
   double px0 = 0, py0 = 0, ph = 1;
 
@@ -152,6 +155,21 @@ int reduce4(ma_ctx *c, const double *a, const double *b, int n, double *out_dev)
   return MA_OK;
 }
 
+// prefix sums of the moment terms of SET over the Morton-sorted sites into out[K][n+1]
+template <int SET> int moment_scan(ma_ctx *c, double *out) {
+  constexpr int K = MomentTerms<SET>::K;
+  const int n = c->N, nt = std::max(1, cdiv(n, FS_TILE));
+  CKR(ensure(c, c->fs_tiles, (size_t)K * nt * 8));
+  const double cx = c->px0 + 0.5 * c->ph * (1 << c->L), cy = c->py0 + 0.5 * c->ph * (1 << c->L);
+  k_moment_scan_tiles<SET><<<nt, FS_NT, 0, c->stream>>>(c->xs.as<double>(), c->ys.as<double>(), c->ws.as<double>(), cx, cy,
+                                                        n, out, c->fs_tiles.as<double>());
+  k_moment_scan_sums<<<K, FS_NT, 0, c->stream>>>(c->fs_tiles.as<double>(), nt, n, out);
+  k_moment_scan_add<<<nt, FS_NT, 0, c->stream>>>(out, c->fs_tiles.as<double>(), n, K);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mesh
 // ---------------------------------------------------------------------------------------------
@@ -205,6 +223,8 @@ extern "C" int ma_create(ma_ctx **out, int device) {
   *out = nullptr;
   ma_ctx *c = new ma_ctx();
   c->device = device;
+  if (const char *t = getenv("MA_TRACE")) c->trace = atoi(t);
+  if (c->trace) c->profiling = 1;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
@@ -237,7 +257,8 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->scratch_d, &c->scratch_i, &c->cptr, &c->ccol, &c->cval, &c->cg_out, &c->pc_count, &c->pc_off,
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
-                  &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush};
+                  &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
+                  &c->nodeG, &c->nodeA};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
@@ -474,6 +495,16 @@ extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y)
                                                        c->xs.as<double>(), c->ys.as<double>(), c->pos.as<int>());
   CK(cudaMemsetAsync(c->w.p, 0, (size_t)N * 8, c->stream));
   CK(cudaGetLastError());
+  // per-node planes: sorted leaf codes + the geometric half of the moment prefix sums
+  const size_t nnodes = (4 * nb - 1) / 3;
+  CKR(ensure(c, c->code_s, (size_t)N * 4));
+  CKR(ensure(c, c->pre0, (size_t)5 * (N + 1) * 8));
+  CKR(ensure(c, c->pre1, (size_t)3 * (N + 1) * 8));
+  CKR(ensure(c, c->nodeG, nnodes * 16));
+  CKR(ensure(c, c->nodeA, nnodes * 8));
+  k_gather_u32<<<cdiv(N, 256), 256, 0, c->stream>>>(c->code.as<unsigned>(), c->perm.as<int>(), N, c->code_s.as<unsigned>());
+  CKR(moment_scan<0>(c, c->pre0.as<double>()));
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   return MA_OK;
 }
@@ -492,6 +523,10 @@ int fill_params(ma_ctx *c, Params &p) {
   p.L = c->L; p.px0 = c->px0; p.py0 = c->py0; p.ph = c->ph;
   p.bin_start = c->bin_start.as<int>();
   p.wmax = c->wmax.as<double>();
+  p.nodeG = c->nodeG.as<double>();
+  p.nodeA = c->nodeA.as<unsigned long long>();
+  p.abort_flag = c->flags.as<int>() + 1;
+  p.abort_on_empty = c->abort_on_empty ? 1 : 0;
   for (int k = 0; k < 4; ++k) p.bb[k] = c->bb[k];
   p.mesh_kind = c->mesh_kind;
   p.nF = c->nF;
@@ -569,6 +604,17 @@ int run_cells(ma_ctx *c, Params &p) {
                                                                c->wmax.as<double>());
   if (c->L >= 5) k_wmax_top<<<1, 1024, 0, c->stream>>>(c->L, c->wmax.as<double>());
   c->launches += 2 + (c->L >= 5);
+  CKR(moment_scan<1>(c, c->pre1.as<double>()));
+  {
+    const size_t nnodes = (4 * nb - 1) / 3;
+    k_node_fit<<<cdiv((long long)nnodes, 256), 256, 0, c->stream>>>(c->L, c->bin_start.as<int>(), N, c->pre0.as<double>(),
+                                                                    c->pre1.as<double>(), c->nodeG.as<double>(),
+                                                                    c->nodeA.as<unsigned long long>());
+    k_node_alpha<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->L, c->xs.as<double>(), c->ys.as<double>(), c->ws.as<double>(),
+                                                      c->code_s.as<unsigned>(), c->px0, c->py0, c->ph, c->nodeG.as<double>(),
+                                                      c->nodeA.as<unsigned long long>());
+    c->launches += 2;
+  }
   CK(cudaGetLastError());
   if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PREP + 1], c->stream));
   CKR(launch_cells_kmax(c, p));
@@ -601,6 +647,21 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       zero(c->mass, 8); zero(c->fcell, 8); zero(c->touched, 8); zero(c->rowcnt, 4);
     }
     CKR(run_cells(c, p));
+    c->aborted = false;
+    if (c->abort_on_empty) {
+      // line-search trial: an empty cell means min m = 0 < eps0, the point is rejected whatever the
+      // rest of the evaluation says (optimal_transport.hpp:167), so stop here
+      int h_abort = 0;
+      CK(cudaMemcpyAsync(&h_abort, c->flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (h_abort) {
+        c->aborted = true;
+        c->mass_min = 0.0;
+        invalidate_eval(c);
+        if (c->trace) fprintf(stderr, "[ma] eval aborted after K2: a cell is empty\n");
+        return MA_OK;
+      }
+    }
     CKR(launch_pieces_mode<MODE>(c, p));
     if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
     if (MODE == MODE_KANTOROVICH) {
@@ -619,6 +680,7 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     }
     CK(cudaStreamSynchronize(c->stream));
     if (h_flags & (FLAG_CELL_OVERFLOW | FLAG_PIECE_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
+      if (c->trace) fprintf(stderr, "[ma] eval kmax=%d overflow flags=%d\n", c->kmax, h_flags);
       if (c->kmax >= 64) {
         c->capacity_hit = true;
         return fail(c, MA_INVALID, "polygon capacity exceeded even at kmax=64 (flags=%d)", h_flags);
@@ -667,6 +729,10 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     }
     c->have_eval = true;
     c->have_hessian = (MODE == MODE_KANTOROVICH) && with_hessian;
+    if (c->trace)
+      fprintf(stderr, "[ma] eval kmax=%d attempt=%d total=%.3f prep=%.3f cells=%.3f pieces=%.3f reduce=%.3f csr=%.3f ms  mass_min=%g nnz=%d\n",
+              c->kmax, attempt, c->t_ms[MA_T_TOTAL], c->t_ms[MA_T_PREP], c->t_ms[MA_T_CELLS], c->t_ms[MA_T_PIECES],
+              c->t_ms[MA_T_REDUCE], c->t_ms[MA_T_CSR], c->mass_min, c->nnz);
     return MA_OK;
   }
   return fail(c, MA_INVALID, "evaluation failed after capacity escalation");
@@ -1023,7 +1089,14 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
   // f(x): evaluation + (m, g = m - nu, f - nu.x)   optimal_transport.hpp:110-120
   auto feval = [&]() -> int {
     ++neval;
+    c->abort_on_empty = neval > 1;  // every evaluation after the first is a line-search trial
     int rc_e = evaluate_mode<MODE_KANTOROVICH>(c, true);
+    c->abort_on_empty = false;
+    if (rc_e == MA_OK && c->aborted) {
+      mmin = 0.0;
+      gnorm = 1e300;
+      return MA_OK;
+    }
     if (rc_e != MA_OK && c->capacity_hit && neval > 1) {
       // a trial point so wild that one cell has > 64 Laguerre neighbours: the reference would evaluate it and
       // reject it (hidden neighbours => min m = 0 < eps0, optimal_transport.hpp:167); reject it here too

@@ -31,6 +31,10 @@ struct Params {
   double px0, py0, ph;
   const int *bin_start;
   const double *wmax;
+  const double *nodeG;                // 2 per node: least-squares weight gradient (ma_geom.cuh)
+  const unsigned long long *nodeA;    // per node: dkey(alpha_B)
+  const int *abort_flag;              // != 0: another cell is already known to be empty, stop (line search)
+  int abort_on_empty;
   // mesh bounding box
   double bb[4];
   // source mesh
@@ -98,8 +102,14 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
   // the polygon is cut on every side its security radius is the whole box, so nothing is pruned and
   // the nearest quadrant is searched exhaustively.  Instead the tree is walked in passes with a
   // distance cap that doubles: pass q handles exactly the sites with prev < |y_j - y_i| <= cap, and
-  // the search ends with one uncapped pass (pruned by the security test alone) once the polygon fits
-  // in the disk of radius cap/2.
+  // the search ends with one uncapped pass (pruned by the security tests alone) once the polygon fits
+  // in the disk of radius cap/2 or a whole pass went by without a cut.
+  // Security tests for a node B, both conservative ("no site of B can take any vertex p of the
+  // polygon from i", i.e. pow_j(p) >= pow_i(p) for every j in B and every vertex p):
+  //   (a) disk around y_i with the node's maximum weight;
+  //   (b) the node's supporting plane (ma_geom.cuh) against every vertex.
+  // (b) is what keeps the search local once the weights have a gradient: the cell then lies far from
+  // its own Dirac and (a), which measures from y_i, would keep a disk of radius ~|grad w| alive.
   // first cap: side of the deepest own ancestor holding >= 8 sites (counts come from the Morton prefix)
   double cap;
   {
@@ -118,8 +128,11 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
   }
   double prev2 = -1.0;
   unsigned stk[52];
+  bool cut_in_pass = true;
   for (int pass = 0; pass < 64 && n > 0; ++pass) {
-    const bool last = !(4.0 * R2 > cap * cap);  // polygon inside the disk of radius cap/2: finish uncapped
+    const bool last = !(4.0 * R2 > cap * cap) || !cut_in_pass;
+    cut_in_pass = false;
+    if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return 0;
     const double cap2 = last ? 1.0 / 0.0 : cap * cap;
     int sp = 0;
     stk[sp++] = 0u;
@@ -135,10 +148,24 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
       double dx = fmax(fmax(ox, -(ox + S)), 0.0), dy = fmax(fmax(oy, -(oy + S)), 0.0);
       double d2 = dx * dx + dy * dy;
       if (d2 > cap2) continue;
-      if (d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) continue;
       {
         double fx = fmax(fabs(ox), fabs(ox + S)), fy = fmax(fabs(oy), fabs(oy + S));
         if (fx * fx + fy * fy <= prev2) continue;  // every site of this node was handled by an earlier pass
+      }
+      if (d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) continue;  // (a)
+      {
+        const size_t node = level_offset(l) + code;
+        const double Gx = p.nodeG[2 * node], Gy = p.nodeG[2 * node + 1], al = dkey_inv(p.nodeA[node]);
+        const double hs = 0.5 * S, Zx = ox + hs, Zy = oy + hs;
+        bool can = false;
+        for (int k = 0; k < n; ++k) {  // (b) supporting plane of the node vs every vertex
+          double ux = P.X(k), uy = P.Y(k), Px = ux - Zx, Py = uy - Zy;
+          double pp = Px * Px + Py * Py, slop = (fabs(2.0 * Px + Gx) + fabs(2.0 * Py + Gy)) * hs;
+          double r2 = ux * ux + uy * uy;
+          double lb = pp + al - slop;
+          if (!(lb >= (r2 - wi) + 1e-10 * (pp + fabs(al) + slop + r2 + fabs(wi)))) { can = true; break; }
+        }
+        if (!can) continue;
       }
       if (l < p.L) {
         // children, nearest first (pushed in reverse)
@@ -173,6 +200,7 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
         int n2 = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, j, lineof);
         if (n2 < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
         n = n2;
+        cut_in_pass = true;
         R2 = 0.0;
         for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
       }

@@ -216,4 +216,42 @@ MA_DEV bool cannot_cut(double d2, double dw, double R2) {
   return s > 0.0 && s * s >= 4.0 * R2 * d2 * (1.0 + 1e-9);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Per-node supporting planes of the lifted sites (the "per-bin max-weight bound" made gradient-aware).
+// For node B with centre zc and any vector G,   alpha_B = min_{j in B} ( |t_j|^2 - w_j + G . t_j ),
+// t_j = y_j - zc, gives for every point p (P = p - zc) and every site j of B
+//   pow_j(p) = |P - t_j|^2 - w_j = |P|^2 - (2P + G) . t_j + (|t_j|^2 - w_j + G . t_j)
+//            >= |P|^2 + alpha_B - (|2 Px + Gx| + |2 Py + Gy|) * S/2 .
+// With G = the least-squares gradient of the weights over B the bound stays tight when the weights
+// have a gradient (then a Laguerre cell lies far from its own Dirac and any bound made of
+// "max weight + distance to the box" alone keeps a disk of radius ~|grad w| alive).
+// ------------------------------------------------------------------------------------------------
+union dbits { double d; unsigned long long u; };
+// order-preserving map double -> uint64 (so that atomicMin on the key is a min on the double)
+MA_DEV unsigned long long dkey(double v) {
+  dbits b; b.d = v;
+  return (b.u >> 63) ? ~b.u : (b.u | 0x8000000000000000ull);
+}
+MA_DEV double dkey_inv(unsigned long long k) {
+  dbits b;
+  b.u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return b.d;
+}
+// least-squares gradient of w over a node from its moment sums (about any common origin);
+// false when the node holds too few / too degenerate sites (the caller then inherits the parent's)
+MA_DEV bool node_gradient(double n, double sx, double sy, double sxx, double syy, double sxy, double sw, double sxw,
+                          double syw, double &Gx, double &Gy) {
+  if (n < 6.0) return false;
+  double inv = 1.0 / n;
+  double cxx = sxx - sx * sx * inv, cyy = syy - sy * sy * inv, cxy = sxy - sx * sy * inv;
+  double cxw = sxw - sx * sw * inv, cyw = syw - sy * sw * inv;
+  double det = cxx * cyy - cxy * cxy;
+  if (!(cxx > 0.0) || !(cyy > 0.0) || !(det > 1e-2 * cxx * cyy)) return false;
+  Gx = (cxw * cyy - cyw * cxy) / det;
+  Gy = (cyw * cxx - cxw * cxy) / det;
+  return Gx - Gx == 0.0 && Gy - Gy == 0.0;  // finite
+}
+MA_DEV size_t level_offset(int l) { return (((size_t)1 << (2 * l)) - 1) / 3; }
+
 }  // namespace ma

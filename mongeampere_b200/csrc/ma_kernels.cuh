@@ -205,6 +205,11 @@ __global__ void k_gather_points(const double *__restrict__ x, const double *__re
   ys[k] = y[i];
   pos[i] = k;
 }
+__global__ void k_gather_u32(const unsigned *__restrict__ src, const int *__restrict__ perm, int n,
+                             unsigned *__restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[perm[k]];
+}
 // dst[k] = src[perm[k]]
 __global__ void k_gather(const double *__restrict__ src, const int *__restrict__ perm, int n, double *__restrict__ dst) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,6 +261,178 @@ __global__ void __launch_bounds__(1024) k_wmax_top(int L, double *__restrict__ w
 }
 
 // ================================================================================================
+// K1 (continued): per-node supporting planes of the lifted sites (ma_geom.cuh).
+//   * inclusive-exclusive prefix sums over the Morton-sorted sites of the moment terms
+//       SET 0 (once per point set):  x, y, x^2, y^2, x y        (coordinates relative to (cx, cy))
+//       SET 1 (every evaluation):    w, x w, y w
+//     out[c * (n + 1) + k] = sum_{j < k} term_c(j); a node's sums are differences of two entries
+//     because the sites of a quadtree node are contiguous in Morton order;
+//   * k_node_fit: least-squares weight gradient G per node (inherits the nearest valid ancestor's);
+//   * k_node_alpha: alpha_B = min_j (|t_j|^2 - w_j + G.t_j) by atomicMin on order-preserving keys.
+// ================================================================================================
+constexpr int FS_NT = 256, FS_ITEMS = 4, FS_TILE = FS_NT * FS_ITEMS;
+
+template <int SET> struct MomentTerms;
+template <> struct MomentTerms<0> { static constexpr int K = 5; };
+template <> struct MomentTerms<1> { static constexpr int K = 3; };
+
+template <int SET>
+__device__ __forceinline__ void moment_terms(const double *__restrict__ xs, const double *__restrict__ ys,
+                                             const double *__restrict__ ws, double cx, double cy, int j, double *v) {
+  double x = xs[j] - cx, y = ys[j] - cy;
+  if (SET == 0) { v[0] = x; v[1] = y; v[2] = x * x; v[3] = y * y; v[4] = x * y; }
+  else { double w = ws[j]; v[0] = w; v[1] = x * w; v[2] = y * w; }
+}
+
+// block-wide exclusive scan of one double per thread (FS_NT threads); total to *total
+__device__ __forceinline__ double block_exclusive_scan_f64(double v, double *total, double *sh /* FS_NT/32 + 1 */) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) sh[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    constexpr int NW = FS_NT / 32;
+    double s = lane < NW ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 1; o < NW; o <<= 1) {
+      double y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    if (lane < NW) sh[lane] = s;
+  }
+  __syncthreads();
+  *total = sh[FS_NT / 32 - 1];
+  double res = x - v + (warp > 0 ? sh[warp - 1] : 0.0);
+  __syncthreads();
+  return res;
+}
+
+template <int SET>
+__global__ void __launch_bounds__(FS_NT) k_moment_scan_tiles(const double *__restrict__ xs, const double *__restrict__ ys,
+                                                              const double *__restrict__ ws, double cx, double cy, int n,
+                                                              double *__restrict__ out, double *__restrict__ tile_sums) {
+  constexpr int K = MomentTerms<SET>::K;
+  __shared__ double sh[FS_NT / 32 + 1];
+  const int base = blockIdx.x * FS_TILE + threadIdx.x * FS_ITEMS;
+  double v[FS_ITEMS][K], s[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) s[c] = 0.0;
+#pragma unroll
+  for (int q = 0; q < FS_ITEMS; ++q) {
+    if (base + q < n) moment_terms<SET>(xs, ys, ws, cx, cy, base + q, v[q]);
+    else
+#pragma unroll
+      for (int c = 0; c < K; ++c) v[q][c] = 0.0;
+#pragma unroll
+    for (int c = 0; c < K; ++c) s[c] += v[q][c];
+  }
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    double total;
+    double ex = block_exclusive_scan_f64(s[c], &total, sh);
+    double *o = out + (size_t)c * (n + 1);
+#pragma unroll
+    for (int q = 0; q < FS_ITEMS; ++q) {
+      if (base + q < n) o[base + q] = ex;
+      ex += v[q][c];
+    }
+    if (threadIdx.x == 0) tile_sums[(size_t)c * gridDim.x + blockIdx.x] = total;
+  }
+}
+// one block per component: exclusive scan of that component's tile sums in place; grand total to out[c*(n+1)+n]
+__global__ void __launch_bounds__(FS_NT) k_moment_scan_sums(double *__restrict__ tile_sums, int nt, int n,
+                                                             double *__restrict__ out) {
+  __shared__ double sh[FS_NT / 32 + 1];
+  double *ts = tile_sums + (size_t)blockIdx.x * nt;
+  double carry = 0.0;
+  for (int base = 0; base < nt; base += FS_NT) {
+    int idx = base + threadIdx.x;
+    double v = idx < nt ? ts[idx] : 0.0, total;
+    double ex = block_exclusive_scan_f64(v, &total, sh);
+    if (idx < nt) ts[idx] = ex + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0) out[(size_t)blockIdx.x * (n + 1) + n] = carry;
+}
+__global__ void __launch_bounds__(FS_NT) k_moment_scan_add(double *__restrict__ out, const double *__restrict__ tile_sums,
+                                                            int n, int K) {
+  const int base = blockIdx.x * FS_TILE + threadIdx.x * FS_ITEMS;
+  for (int c = 0; c < K; ++c) {
+    double off = tile_sums[(size_t)c * gridDim.x + blockIdx.x];
+    double *o = out + (size_t)c * (n + 1);
+#pragma unroll
+    for (int q = 0; q < FS_ITEMS; ++q)
+      if (base + q < n) o[base + q] += off;
+  }
+}
+
+// gradient of node (l, code) from the prefix sums; false if the node cannot support a fit
+__device__ __forceinline__ bool node_fit_one(int L, int l, unsigned code, const int *__restrict__ bin_start, int n,
+                                             const double *__restrict__ pre0, const double *__restrict__ pre1,
+                                             double &Gx, double &Gy) {
+  const int sh = 2 * (L - l);
+  const int s = bin_start[(size_t)code << sh], e = bin_start[((size_t)code + 1) << sh];
+  if (e - s < 6) return false;
+  const size_t st = (size_t)n + 1;
+  double m[8];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) m[c] = pre0[c * st + e] - pre0[c * st + s];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) m[5 + c] = pre1[c * st + e] - pre1[c * st + s];
+  return node_gradient((double)(e - s), m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], Gx, Gy);
+}
+__global__ void k_node_fit(int L, const int *__restrict__ bin_start, int n, const double *__restrict__ pre0,
+                           const double *__restrict__ pre1, double *__restrict__ nodeG,
+                           unsigned long long *__restrict__ nodeA) {
+  const size_t nnodes = level_offset(L + 1);
+  size_t node = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= nnodes) return;
+  int l = 0;
+  while (level_offset(l + 1) <= node) ++l;
+  unsigned code = (unsigned)(node - level_offset(l));
+  double Gx = 0.0, Gy = 0.0;
+  for (int a = l; a >= 0; --a) {  // own fit, else the nearest ancestor's
+    if (node_fit_one(L, a, code >> (2 * (l - a)), bin_start, n, pre0, pre1, Gx, Gy)) break;
+    Gx = Gy = 0.0;
+  }
+  nodeG[2 * node] = Gx;
+  nodeG[2 * node + 1] = Gy;
+  nodeA[node] = dkey(1.0 / 0.0);
+}
+// one thread per site: fold the site into alpha of its node at every level
+__global__ void k_node_alpha(int n, int L, const double *__restrict__ xs, const double *__restrict__ ys,
+                             const double *__restrict__ ws, const unsigned *__restrict__ code_s, double px0, double py0,
+                             double ph, const double *__restrict__ nodeG, unsigned long long *__restrict__ nodeA) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < n;
+  const unsigned leaf = live ? code_s[j] : 0u;
+  const double x = live ? xs[j] : 0.0, y = live ? ys[j] : 0.0, w = live ? ws[j] : 0.0;
+  for (int l = L; l >= 0; --l) {
+    const unsigned code = leaf >> (2 * (L - l));
+    const size_t node = level_offset(l) + code;
+    const double S = ph * (double)(1u << (L - l));
+    const double tx = x - (px0 + ((double)morton_compact1(code) + 0.5) * S);
+    const double ty = y - (py0 + ((double)morton_compact1(code >> 1) + 0.5) * S);
+    double v = 1.0 / 0.0;
+    if (live) v = tx * tx + ty * ty - w + nodeG[2 * node] * tx + nodeG[2 * node + 1] * ty;
+    // warp-aggregate when the whole warp sits in one node (sites are Morton-contiguous)
+    const unsigned c0 = __shfl_sync(0xffffffffu, code, 0);
+    const bool uniform = __all_sync(0xffffffffu, !live || code == c0);
+    if (uniform) {
+      v = warp_min(v);
+      if ((threadIdx.x & 31) == 0 && v < 1.0 / 0.0) atomicMin(&nodeA[level_offset(l) + c0], dkey(v));
+    } else if (live) {
+      atomicMin(&nodeA[node], dkey(v));
+    }
+  }
+}
+
+// ================================================================================================
 // K2: one thread per cell
 // ================================================================================================
 template <int MAXV, int NT> __global__ void __launch_bounds__(NT) k_cells(Params p) {
@@ -269,6 +446,7 @@ template <int MAXV, int NT> __global__ void __launch_bounds__(NT) k_cells(Params
   int fl = 0;
   int n = cell_build<NT>(p, i, P, MAXV, &fl);
   if (fl) atomicOr(p.flags, fl);
+  if (n == 0 && p.abort_on_empty) p.flags[1] = 1;  // an empty cell: the line search rejects this trial point
   if (n < 0) n = 0;
   cell_emit<NT>(p, i, P, n);
 }

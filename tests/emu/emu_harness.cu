@@ -117,7 +117,46 @@ extern "C" int emu_eval(int mesh_kind,
       wmax[(nl - 1) / 3 + c] = std::max(std::max(ch[0], ch[1]), std::max(ch[2], ch[3]));
     }
   }
+  // per-node supporting planes (the host twin of k_node_fit / k_node_alpha)
+  const size_t nnodes = (4 * nb - 1) / 3;
+  std::vector<double> nodeG(2 * nnodes, 0.0);
+  std::vector<unsigned long long> nodeA(nnodes, dkey(std::numeric_limits<double>::infinity()));
+  {
+    const double cx = bx0 + 0.5 * ext, cy = by0 + 0.5 * ext;
+    auto fit = [&](int l, unsigned c, double &Gx, double &Gy) {
+      int sh = 2 * (L - l);
+      int s = bin_start[(size_t)c << sh], e = bin_start[((size_t)c + 1) << sh];
+      double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = s; j < e; ++j) {
+        double X = xs[j] - cx, Y = ys[j] - cy, W = ws[j];
+        m[0] += X; m[1] += Y; m[2] += X * X; m[3] += Y * Y; m[4] += X * Y; m[5] += W; m[6] += X * W; m[7] += Y * W;
+      }
+      return node_gradient((double)(e - s), m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], Gx, Gy);
+    };
+    for (int l = 0; l <= L; ++l)
+      for (unsigned c = 0; c < (1u << (2 * l)); ++c) {
+        double Gx = 0, Gy = 0;
+        for (int a = l; a >= 0; --a) {
+          if (fit(a, c >> (2 * (l - a)), Gx, Gy)) break;
+          Gx = Gy = 0;
+        }
+        size_t node = level_offset(l) + c;
+        nodeG[2 * node] = Gx; nodeG[2 * node + 1] = Gy;
+        int sh = 2 * (L - l);
+        double S = (ext / G) * (double)(1u << (L - l));
+        double zx = bx0 + (morton_compact1(c) + 0.5) * S, zy = by0 + (morton_compact1(c >> 1) + 0.5) * S;
+        double al = std::numeric_limits<double>::infinity();
+        for (int j = bin_start[(size_t)c << sh]; j < bin_start[((size_t)c + 1) << sh]; ++j) {
+          double tx = xs[j] - zx, ty = ys[j] - zy;
+          al = std::min(al, tx * tx + ty * ty - ws[j] + Gx * tx + Gy * ty);
+        }
+        nodeA[node] = dkey(al);
+      }
+  }
+  int no_abort = 0;
+  p.nodeG = nodeG.data(); p.nodeA = nodeA.data(); p.abort_flag = &no_abort; p.abort_on_empty = 0;
   p.N = N; p.xs = xs.data(); p.ys = ys.data(); p.ws = ws.data();
+  p.cell_lo = 0; p.cell_hi = N;
   p.bin_start = bin_start.data(); p.wmax = wmax.data();
   // ---- outputs ----
   std::vector<double> cell_bb((size_t)4 * N);
