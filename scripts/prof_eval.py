@@ -1,0 +1,17 @@
+"""Minimal driver for ncu captures: loads a workload and runs a few device-resident evaluations."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mongeampere_b200 import capi
+from tests import common
+name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+nev = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+weights = sys.argv[4] if len(sys.argv) > 4 else "zero"
+case = common.make_case(name, scale, weights)
+ctx = capi.Context(0)
+common.load_engine(ctx, case)
+ctx.set_weights(case["w"])
+for _ in range(nev):
+    ctx.evaluate(True)
+print("nnz", ctx.info("nnz"), "mass_sum", ctx.info("mass_sum"))
+ctx.close()
