@@ -42,6 +42,7 @@ struct ma_ctx {
   int cg_maxit = 200000;
   double filter_tol = 1e-11;
   int profiling = 0, stats = 0, trace = 0;
+  int strategy = 0;  // 0 auto (grid mesh: fused segment kernel, general mesh: pieces), 2: pieces always
   int part_rank = 0, part_n = 1;  // Morton tile of the Diracs this context evaluates
   long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
 
@@ -290,6 +291,12 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "cg_rtol") c->cg_rtol = value;
   else if (n == "cg_maxit") c->cg_maxit = (int)value;
   else if (n == "filter_tol") c->filter_tol = value;
+  else if (n == "strategy") {
+    int v = (int)value;
+    if (v != 0 && v != 2) return fail(c, MA_INVALID, "strategy must be 0 (auto) or 2 (pieces)");
+    c->strategy = v;
+    invalidate_eval(c);
+  }
   else return fail(c, MA_INVALID, "unknown option %s", name);
   return MA_OK;
 }
@@ -308,6 +315,7 @@ extern "C" double ma_get_info(ma_ctx *c, const char *name) {
   if (n == "cg_iters") return (double)c->last_cg_iters;
   if (n == "mesh_kind") return c->mesh_kind;
   if (n == "launches") return (double)c->launches;
+  if (n == "strategy") return c->strategy;
   if (n == "fval") return c->fval;
   if (n == "cell_lo") return (double)((long long)c->N * c->part_rank / c->part_n);
   if (n == "cell_hi") return (double)((long long)c->N * (c->part_rank + 1) / c->part_n);
@@ -577,6 +585,26 @@ int launch_cells_kmax(ma_ctx *c, const Params &p) {
     default: return launch_cells<64, 32>(c, p);
   }
 }
+template <int MAXV, int NT, int MODE> int launch_cells_seg(ma_ctx *c, const Params &p) {
+  size_t sm = cells_smem_bytes<MAXV, NT>();
+  CK(cudaFuncSetAttribute(k_cells_seg<MAXV, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_cells_seg<MAXV, NT, MODE><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
+  c->launches++;
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+template <int MODE> int launch_cells_seg_kmax(ma_ctx *c, const Params &p) {
+  switch (c->kmax) {
+    case 16: return launch_cells_seg<20, 128, MODE>(c, p);
+    case 32: return launch_cells_seg<36, 64, MODE>(c, p);
+    default: return launch_cells_seg<64, 32, MODE>(c, p);
+  }
+}
+// the fused segment kernel handles grid meshes in the integrating modes
+template <int MODE> bool use_seg(const ma_ctx *c) {
+  return c->mesh_kind == MESH_GRID && c->strategy == 0 && !c->stats &&
+         (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2);
+}
 
 int alloc_eval(ma_ctx *c) {
   const size_t N = c->N, K = c->kmax;
@@ -596,7 +624,7 @@ int alloc_eval(ma_ctx *c) {
 }
 
 // K1 per-eval part + K2 on the current device weights (c->w, caller order)
-int run_cells(ma_ctx *c, Params &p) {
+template <int FUSED_MODE = -1> int run_cells(ma_ctx *c, Params &p) {
   const int N = c->N;
   k_gather<<<cdiv(N, 256), 256, 0, c->stream>>>(c->w.as<double>(), c->perm.as<int>(), N, c->ws.as<double>());
   const size_t nb = (size_t)1 << (2 * c->L);
@@ -617,7 +645,8 @@ int run_cells(ma_ctx *c, Params &p) {
   }
   CK(cudaGetLastError());
   if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PREP + 1], c->stream));
-  CKR(launch_cells_kmax(c, p));
+  if (FUSED_MODE >= 0) CKR(launch_cells_seg_kmax<(FUSED_MODE >= 0 ? FUSED_MODE : 0)>(c, p));
+  else CKR(launch_cells_kmax(c, p));
   if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CELLS + 1], c->stream));
   return MA_OK;
 }
@@ -646,7 +675,10 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       };
       zero(c->mass, 8); zero(c->fcell, 8); zero(c->touched, 8); zero(c->rowcnt, 4);
     }
-    CKR(run_cells(c, p));
+    constexpr int SEG_MODE = (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) ? MODE : 0;
+    const bool seg = use_seg<MODE>(c);
+    if (seg) CKR(run_cells<SEG_MODE>(c, p));
+    else CKR(run_cells(c, p));
     c->aborted = false;
     if (c->abort_on_empty) {
       // line-search trial: an empty cell means min m = 0 < eps0, the point is rejected whatever the
@@ -662,7 +694,7 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
         return MA_OK;
       }
     }
-    CKR(launch_pieces_mode<MODE>(c, p));
+    if (!seg) CKR(launch_pieces_mode<MODE>(c, p));
     if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
     if (MODE == MODE_KANTOROVICH) {
       if (with_hessian) CKR(scan_i32(c, c->rowcnt.as<int>(), c->rowptr.as<int>(), c->N));

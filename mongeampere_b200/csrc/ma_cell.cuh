@@ -96,44 +96,104 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
     else if (tag == -3) { nx = 0; ny = 1; cl = by1; }
     else { nx = 1; ny = 0; cl = bx0; }
   };
-  const double NEG_INF = -1.0 / 0.0;
-  // ---- expanding-radius search over the quadtree ------------------------------------------------
+  const double NEG_INF = -1.0 / 0.0, POS_INF = 1.0 / 0.0;
+  if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return 0;
+  // ---- one candidate site: clip the polygon by its bisector (both phases) ----------------------
+  // status: 0 ok, -1 polygon capacity overflow.  Sites with |y_j - y_i|^2 outside (lo2, hi2] are skipped.
+  int status = 0;
+  bool cut_in_pass = true;
+  auto site = [&](int j, double lo2, double hi2) {
+    if (j == i) return;
+    const double Dx = p.xs[j] - xi, Dy = p.ys[j] - yi, wj = p.ws[j];
+    const double dd2 = Dx * Dx + Dy * Dy;
+    if (dd2 <= lo2 || dd2 > hi2) return;  // handled by an earlier pass / left to a later one
+    if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
+      if (wj > wi || (wj == wi && j < i)) n = 0;
+      return;
+    }
+    const double s = dd2 + (wi - wj);
+    if (s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12)) return;  // bisector beyond every vertex
+    const double c = 0.5 * s;
+    unsigned long long in = 0ull;
+    for (int k = 0; k < n; ++k)
+      if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
+    const unsigned long long full = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    if (in == full) return;
+    if (in == 0ull) { n = 0; return; }
+    const int n2 = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, j, lineof);
+    if (n2 < 0) { status = -1; n = 0; return; }
+    n = n2;
+    cut_in_pass = true;
+    R2 = 0.0;
+    for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
+  };
+  // ---- phase 1: square rings of leaf bins around the Dirac's own bin --------------------------
+  // Every lane of a warp walks the same ring pattern (consecutive cells share bins), nearest bins
+  // first, so the polygon is tight after a few dozen sites.  After ring r every site inside the
+  // (2r+1)^2 block has been seen, hence every site within rho = distance(y_i, block boundary); the
+  // search is over when no site at distance >= rho can cut, whatever its weight (global maximum
+  // weight, SURVEY §7.2 security radius).  If that certificate cannot work (weights with a gradient),
+  // phase 2 takes over with the per-node bounds.
+  const int G = 1 << p.L;
+  const double pinv = 1.0 / p.ph;
+  const int bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1), by = min(max((int)((yi - p.py0) * pinv), 0), G - 1);
+  const double dw_glob = wi - p.wmax[0];  // <= 0
+  int rdone = -1;          // rings 0..rdone are done
+  double rho2 = -1.0;      // every site with |y_j - y_i|^2 <= rho2 is done
+  const int RMAX = 3;
+  for (int r = 0; r <= RMAX && n > 0; ++r) {
+    for (int oy = -r; oy <= r; ++oy) {
+      const int cy = by + oy;
+      if (cy < 0 || cy >= G) continue;
+      const int step = (oy == -r || oy == r || r == 0) ? 1 : 2 * r;
+      for (int ox = -r; ox <= r; ox += step) {
+        const int cx = bx + ox;
+        if (cx < 0 || cx >= G) continue;
+        const unsigned code = morton2((unsigned)cx, (unsigned)cy);
+        const int b0 = p.bin_start[code], b1 = p.bin_start[code + 1];
+        for (int j = b0; j < b1 && n > 0; ++j) site(j, -1.0, POS_INF);
+      }
+    }
+    rdone = r;
+    if (status < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
+    if (n == 0) return 0;
+    // distance from y_i to the part of the block boundary that has bins behind it
+    double rho = POS_INF;
+    if (bx - r > 0) rho = fmin(rho, xi - (p.px0 + (double)(bx - r) * p.ph));
+    if (bx + r < G - 1) rho = fmin(rho, (p.px0 + (double)(bx + r + 1) * p.ph) - xi);
+    if (by - r > 0) rho = fmin(rho, yi - (p.py0 + (double)(by - r) * p.ph));
+    if (by + r < G - 1) rho = fmin(rho, (p.py0 + (double)(by + r + 1) * p.ph) - yi);
+    if (rho == POS_INF) return n;  // the block covers every bin
+    rho = fmax(rho, 0.0);
+    rho2 = rho * rho;
+    if (cannot_cut(rho2, dw_glob, R2)) return n;
+    // can one more ring certify anything?  not if even a tiny polygon fails: (rho+ph)^2 + dw <= 0
+    const double rn = rho + p.ph;
+    if (rn * rn + dw_glob <= 0.0) break;
+  }
+  // ---- phase 2: expanding-radius search over the quadtree ---------------------------------------
   // A plain nearest-first DFS degenerates for a Dirac next to a high-level quadrant boundary: until
   // the polygon is cut on every side its security radius is the whole box, so nothing is pruned and
   // the nearest quadrant is searched exhaustively.  Instead the tree is walked in passes with a
   // distance cap that doubles: pass q handles exactly the sites with prev < |y_j - y_i| <= cap, and
   // the search ends with one uncapped pass (pruned by the security tests alone) once the polygon fits
-  // in the disk of radius cap/2 or a whole pass went by without a cut.
+  // in the disk of radius cap/2 or a whole pass went by without a cut.  Sites of the phase-1 block
+  // are skipped (they were all seen).
   // Security tests for a node B, both conservative ("no site of B can take any vertex p of the
   // polygon from i", i.e. pow_j(p) >= pow_i(p) for every j in B and every vertex p):
   //   (a) disk around y_i with the node's maximum weight;
   //   (b) the node's supporting plane (ma_geom.cuh) against every vertex.
   // (b) is what keeps the search local once the weights have a gradient: the cell then lies far from
   // its own Dirac and (a), which measures from y_i, would keep a disk of radius ~|grad w| alive.
-  // first cap: side of the deepest own ancestor holding >= 8 sites (counts come from the Morton prefix)
-  double cap;
-  {
-    const double pinv = 1.0 / p.ph;
-    const int G = 1 << p.L;
-    int bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1), by = min(max((int)((yi - p.py0) * pinv), 0), G - 1);
-    unsigned code = morton2((unsigned)bx, (unsigned)by);
-    int l = p.L;
-    while (l > 0) {
-      int sh = 2 * (p.L - l);
-      unsigned c0 = code >> sh;
-      if (p.bin_start[(c0 + 1u) << sh] - p.bin_start[c0 << sh] >= 8) break;
-      --l;
-    }
-    cap = 0.75 * p.ph * (double)(1u << (p.L - l));
-  }
-  double prev2 = -1.0;
+  double cap = 2.0 * fmax(sqrt(rho2 > 0.0 ? rho2 : 0.0), p.ph);
+  double prev2 = rho2;
   unsigned stk[52];
-  bool cut_in_pass = true;
+  cut_in_pass = true;
   for (int pass = 0; pass < 64 && n > 0; ++pass) {
     const bool last = !(4.0 * R2 > cap * cap) || !cut_in_pass;
     cut_in_pass = false;
     if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return 0;
-    const double cap2 = last ? 1.0 / 0.0 : cap * cap;
+    const double cap2 = last ? POS_INF : cap * cap;
     int sp = 0;
     stk[sp++] = 0u;
     while (sp > 0 && n > 0) {
@@ -142,6 +202,11 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
       unsigned code = e & 0x3ffffffu;
       double wm = p.wmax[(((size_t)1 << (2 * l)) - 1) / 3 + code];
       if (wm == NEG_INF) continue;
+      {  // node inside the phase-1 block: all its sites are done
+        const int sh = p.L - l;
+        const int X0 = (int)morton_compact1(code) << sh, Y0 = (int)morton_compact1(code >> 1) << sh, W = 1 << sh;
+        if (X0 >= bx - rdone && X0 + W - 1 <= bx + rdone && Y0 >= by - rdone && Y0 + W - 1 <= by + rdone) continue;
+      }
       double S = p.ph * (double)(1u << (p.L - l));
       double ox = p.px0 + (double)morton_compact1(code) * S - xi;
       double oy = p.py0 + (double)morton_compact1(code >> 1) * S - yi;
@@ -179,31 +244,8 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
         continue;
       }
       const int b0 = p.bin_start[code], b1 = p.bin_start[code + 1];
-      for (int j = b0; j < b1 && n > 0; ++j) {
-        if (j == i) continue;
-        double Dx = p.xs[j] - xi, Dy = p.ys[j] - yi, wj = p.ws[j];
-        double dd2 = Dx * Dx + Dy * Dy;
-        if (dd2 <= prev2 || dd2 > cap2) continue;  // handled by an earlier pass / left to a later one
-        if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
-          if (wj > wi || (wj == wi && j < i)) n = 0;
-          continue;
-        }
-        double s = dd2 + (wi - wj);
-        if (s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12)) continue;  // bisector beyond every vertex
-        double c = 0.5 * s;
-        unsigned long long in = 0ull;
-        for (int k = 0; k < n; ++k)
-          if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
-        unsigned long long full = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
-        if (in == full) continue;
-        if (in == 0ull) { n = 0; break; }
-        int n2 = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, j, lineof);
-        if (n2 < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
-        n = n2;
-        cut_in_pass = true;
-        R2 = 0.0;
-        for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
-      }
+      for (int j = b0; j < b1 && n > 0; ++j) site(j, prev2, cap2);
+      if (status < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
     }
     if (last) break;
     prev2 = cap2;

@@ -1,7 +1,7 @@
 // ma_kernels.cuh — __global__ kernels of the evaluation path (K1 binning, K2 cells, K3 pieces,
 // K4 CSR) and small utility kernels (scan, reductions, gathers).  sm_100a, fp64 CUDA-core work.
 #pragma once
-#include "ma_cell.cuh"
+#include "ma_seg.cuh"
 
 namespace ma {
 
@@ -451,6 +451,46 @@ template <int MAXV, int NT> __global__ void __launch_bounds__(NT) k_cells(Params
   cell_emit<NT>(p, i, P, n);
 }
 template <int MAXV, int NT> constexpr size_t cells_smem_bytes() { return (size_t)MAXV * NT * (8 + 8 + 4); }
+
+// ================================================================================================
+// K2+K3 fused for grid meshes: one thread per cell builds the cell (K2) and integrates it over the
+// boundary segments (ma_seg.cuh) while the polygon is still in shared memory.
+// ================================================================================================
+template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT) k_cells_seg(Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sx = reinterpret_cast<double *>(smem_raw);
+  double *sy = sx + MAXV * NT;
+  int *st = reinterpret_cast<int *>(sy + MAXV * NT);
+  int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
+  if (i >= p.cell_hi) return;
+  PolyRef<NT> P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+  int fl = 0;
+  int n = cell_build<NT>(p, i, P, MAXV, &fl);
+  if (fl) atomicOr(p.flags, fl);
+  if (n == 0 && p.abort_on_empty) p.flags[1] = 1;
+  if (n < 0) n = 0;
+  cell_emit<NT>(p, i, P, n);
+  // line-search trial with an empty cell somewhere: the point is rejected whatever the integrals say
+  if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return;
+  SegAcc acc;
+  unsigned long long touched = cell_integrate_grid<NT, MODE>(p, i, P, n, acc, p.hslot + (size_t)i * p.kmax);
+  if (MODE == MODE_KANTOROVICH) {
+    p.mass[i] = acc.mass;
+    p.fcell[i] = acc.mass * p.ws[i] - acc.cost;
+    p.touched[i] = touched;
+    int c = __popcll(touched);
+    p.rowcnt[i] = c ? c + 1 : 0;
+  } else {
+    const double xi = p.xs[i], yi = p.ys[i], mass = acc.mass;
+    double *o = p.mom + 6 * (size_t)i;
+    o[0] = mass;
+    o[1] = acc.m[0] + xi * mass;  // ∫ρ x = ∫ρ (xi + ux)
+    o[2] = acc.m[1] + yi * mass;
+    o[3] = acc.m[2] + 2 * xi * acc.m[0] + xi * xi * mass;
+    o[4] = acc.m[3] + 2 * yi * acc.m[1] + yi * yi * mass;
+    o[5] = acc.m[4] + xi * acc.m[1] + yi * acc.m[0] + xi * yi * mass;
+  }
+}
 
 // ================================================================================================
 // K3: one warp per cell; lanes take candidate faces round-robin

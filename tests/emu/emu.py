@@ -16,7 +16,7 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_HERE, "emu_harness.cu")
-    deps = [src] + [os.path.join(_ROOT, "mongeampere_b200", "csrc", f) for f in ("ma_cell.cuh", "ma_geom.cuh")]
+    deps = [src] + [os.path.join(_ROOT, "mongeampere_b200", "csrc", f) for f in ("ma_cell.cuh", "ma_geom.cuh", "ma_seg.cuh")]
     if not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(d) for d in deps):
         return _LIB
     os.makedirs(os.path.dirname(_LIB), exist_ok=True)
@@ -33,7 +33,7 @@ def lib():
     return _lib
 
 
-def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_target=2, nlanes=32):
+def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_target=2, nlanes=32, seg=False):
     """mesh: dict(kind='grid', n, m, x0, y0, x1, y1, abc) or dict(kind='mesh', vx, vy, tri, abc).
     Returns dict(f, g, H, mom, counters, flags, adjacency)."""
     X = np.asarray(X, np.float64)
@@ -58,7 +58,7 @@ def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_t
                  tri.ctypes.data_as(C.c_void_p))
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib().emu_eval(*gargs, p(abc), N, p(x), p(y), p(w), kmax, maxv_piece, mode, C.c_double(filter_tol),
-                        bin_target, nlanes, p(perm), p(mass), p(fcell), p(nbr_cnt), p(nbr), p(hslot), p(touched),
+                        bin_target, nlanes, int(bool(seg) and mesh["kind"] == "grid"), p(perm), p(mass), p(fcell), p(nbr_cnt), p(nbr), p(hslot), p(touched),
                         p(mom), p(counters), C.byref(flags))
     assert rc == 0
     g = np.zeros(N); g[perm] = mass

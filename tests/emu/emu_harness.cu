@@ -12,7 +12,7 @@
 #include <limits>
 #include <vector>
 
-#include "../../mongeampere_b200/csrc/ma_cell.cuh"
+#include "../../mongeampere_b200/csrc/ma_seg.cuh"
 
 using namespace ma;
 
@@ -26,7 +26,7 @@ extern "C" int emu_eval(int mesh_kind,
                         // Diracs
                         int N, const double *x, const double *y, const double *w,
                         // knobs
-                        int kmax, int maxv_piece, int mode, double filter_tol, int bin_target, int nlanes,
+                        int kmax, int maxv_piece, int mode, double filter_tol, int bin_target, int nlanes, int use_seg,
                         // outputs (internal order) + permutation
                         int *perm_out, double *mass, double *fcell, int *nbr_cnt, int *nbr, double *hslot,
                         unsigned long long *touched, double *mom, long long *counters, int *flags_out) {
@@ -177,10 +177,28 @@ extern "C" int emu_eval(int mesh_kind,
       flags |= fl;
       if (n < 0) n = 0;
       cell_emit<1>(p, i, P, n);
+      if (use_seg) {  // what k_cells_seg does after K2
+        SegAcc acc;
+        unsigned long long tch = 0;
+        if (mode == MODE_KANTOROVICH) tch = cell_integrate_grid<1, MODE_KANTOROVICH>(p, i, P, n, acc, hslot + (size_t)i * kmax);
+        else if (mode == MODE_MOMENTS1) cell_integrate_grid<1, MODE_MOMENTS1>(p, i, P, n, acc, nullptr);
+        else cell_integrate_grid<1, MODE_MOMENTS2>(p, i, P, n, acc, nullptr);
+        mass[i] = acc.mass;
+        fcell[i] = acc.mass * ws[i] - acc.cost;
+        touched[i] = tch;
+        if (mom) {
+          const double xi = xs[i], yi = ys[i], m = acc.mass;
+          double *o = mom + 6 * (size_t)i;
+          o[0] = m; o[1] = acc.m[0] + xi * m; o[2] = acc.m[1] + yi * m;
+          o[3] = acc.m[2] + 2 * xi * acc.m[0] + xi * xi * m;
+          o[4] = acc.m[3] + 2 * yi * acc.m[1] + yi * yi * m;
+          o[5] = acc.m[4] + xi * acc.m[1] + yi * acc.m[0] + xi * yi * m;
+        }
+      }
     }
   }
   // ---- K3 ----
-  {
+  if (!use_seg) {
     std::vector<double> tDx(kmax), tDy(kmax), tC(kmax), tS(kmax), hacc((size_t)kmax * nlanes);
     std::vector<int> tJ(kmax);
     std::vector<double> px(maxv_piece), py(maxv_piece);

@@ -18,16 +18,19 @@ def test_kantorovich_matches_oracle(gpu_ctx, oracle_mod, name, scale, weights):
     orc = common.oracle_for(oracle_mod, case)
     f0, g0, H0 = orc.kantorovich(case["w"])
     common.load_engine(gpu_ctx, case)
-    gpu_ctx.set_stats(True)
-    f1, g1, H1 = gpu_ctx.kantorovich(case["w"])
     gscale = np.abs(g0).max()
-    assert abs(f1 - f0) <= 1e-10 * max(abs(f0), 1e-300), (f0, f1)
-    assert np.abs(g1 - g0).max() <= 1e-10 * gscale
-    assert common.same_pattern(H0, H1), (H0.nnz, H1.nnz)
-    # Hessian entries: 1e-10 relative to the diagonal scale.  (Relative to each row's OWN diagonal the
-    # oracle itself is only good to ~1e-9 on near-hidden cells, because it follows the reference's
-    # global-coordinate CGAL::radical_axis; see test_tiny_cell_arbitration_exact.)
-    assert abs(H0 - H1).max() <= 1e-10 * np.abs(H0.diagonal()).max()
+    # stats off: the default path (grid meshes: fused boundary-segment kernel k_cells_seg; general
+    # meshes: k_cells + k_pieces); stats on: always k_cells + k_pieces, which also counts the pieces
+    for stats in (False, True):
+        gpu_ctx.set_stats(stats)
+        f1, g1, H1 = gpu_ctx.kantorovich(case["w"])
+        assert abs(f1 - f0) <= 1e-10 * max(abs(f0), 1e-300), (stats, f0, f1)
+        assert np.abs(g1 - g0).max() <= 1e-10 * gscale, stats
+        assert common.same_pattern(H0, H1), (stats, H0.nnz, H1.nnz)
+        # Hessian entries: 1e-10 relative to the diagonal scale.  (Relative to each row's OWN diagonal the
+        # oracle itself is only good to ~1e-9 on near-hidden cells, because it follows the reference's
+        # global-coordinate CGAL::radical_axis; see test_tiny_cell_arbitration_exact.)
+        assert abs(H0 - H1).max() <= 1e-10 * np.abs(H0.diagonal()).max(), stats
     co, cg = orc.counters(), gpu_ctx.counters()
     for k in ("pieces", "piece_vertices", "new_vertices", "laguerre_edges", "sum_k", "sum_k_np"):
         assert co[k] == cg[k], (k, co[k], cg[k])
