@@ -65,6 +65,7 @@ struct ma_ctx {
   double px0 = 0, py0 = 0, ph = 1;
 
   // evaluation state
+  Buf poly_x, poly_y, poly_t, poly_n;
   Buf w, ws, nbr, nbr_cnt, cell_bb, mass, fcell, hslot, touched, rowcnt, rowptr, col, val, mom;
   Buf scan_tmp, red_partial, red_out, counters, flags, scratch_d, scratch_i;
   Buf cptr, ccol, cval, cg_out;  // caller-order copies
@@ -259,7 +260,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
-                  &c->nodeG, &c->nodeA};
+                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
@@ -545,6 +546,8 @@ int fill_params(ma_ctx *c, Params &p) {
   p.tbin_ptr = c->tbin_ptr.as<int>(); p.tbin_face = c->tbin_face.as<int>();
   p.kmax = c->kmax;
   p.nbr = c->nbr.as<int>(); p.nbr_cnt = c->nbr_cnt.as<int>(); p.cell_bb = c->cell_bb.as<double>();
+  p.poly_x = c->poly_x.as<double>(); p.poly_y = c->poly_y.as<double>();
+  p.poly_t = c->poly_t.as<int>(); p.poly_n = c->poly_n.as<int>();
   p.mass = c->mass.as<double>(); p.fcell = c->fcell.as<double>(); p.hslot = c->hslot.as<double>();
   p.touched = c->touched.as<unsigned long long>(); p.rowcnt = c->rowcnt.as<int>();
   p.mom = c->mom.as<double>();
@@ -555,10 +558,12 @@ int fill_params(ma_ctx *c, Params &p) {
   return MA_OK;
 }
 
-template <int MAXV, int NT> int launch_cells(ma_ctx *c, const Params &p) {
+constexpr int cells_maxv(int kmax) { return kmax == 16 ? 16 : (kmax == 32 ? 36 : 64); }
+
+template <int MAXV, int NT, bool POLY> int launch_cells(ma_ctx *c, const Params &p) {
   size_t sm = cells_smem_bytes<MAXV, NT>();
-  CK(cudaFuncSetAttribute(k_cells<MAXV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_cells<MAXV, NT><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
+  CK(cudaFuncSetAttribute(k_cells<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_cells<MAXV, NT, POLY><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
   c->launches++;
   CK(cudaGetLastError());
   return MA_OK;
@@ -578,29 +583,29 @@ template <int MODE> int launch_pieces_mode(ma_ctx *c, const Params &p) {
     default: return launch_pieces<64, 40, MODE>(c, p);
   }
 }
-int launch_cells_kmax(ma_ctx *c, const Params &p) {
+template <bool POLY> int launch_cells_kmax(ma_ctx *c, const Params &p) {
   switch (c->kmax) {
-    case 16: return launch_cells<20, 128>(c, p);
-    case 32: return launch_cells<36, 64>(c, p);
-    default: return launch_cells<64, 32>(c, p);
+    case 16: return launch_cells<16, 128, POLY>(c, p);
+    case 32: return launch_cells<36, 64, POLY>(c, p);
+    default: return launch_cells<64, 32, POLY>(c, p);
   }
 }
-template <int MAXV, int NT, int MODE> int launch_cells_seg(ma_ctx *c, const Params &p) {
+template <int MAXV, int NT, int MODE> int launch_seg(ma_ctx *c, const Params &p) {
   size_t sm = cells_smem_bytes<MAXV, NT>();
-  CK(cudaFuncSetAttribute(k_cells_seg<MAXV, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_cells_seg<MAXV, NT, MODE><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
+  CK(cudaFuncSetAttribute(k_seg<MAXV, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_seg<MAXV, NT, MODE><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
   c->launches++;
   CK(cudaGetLastError());
   return MA_OK;
 }
-template <int MODE> int launch_cells_seg_kmax(ma_ctx *c, const Params &p) {
+template <int MODE> int launch_seg_kmax(ma_ctx *c, const Params &p) {
   switch (c->kmax) {
-    case 16: return launch_cells_seg<20, 128, MODE>(c, p);
-    case 32: return launch_cells_seg<36, 64, MODE>(c, p);
-    default: return launch_cells_seg<64, 32, MODE>(c, p);
+    case 16: return launch_seg<16, 128, MODE>(c, p);
+    case 32: return launch_seg<36, 64, MODE>(c, p);
+    default: return launch_seg<64, 32, MODE>(c, p);
   }
 }
-// the fused segment kernel handles grid meshes in the integrating modes
+// the boundary-segment kernel handles grid meshes in the integrating modes
 template <int MODE> bool use_seg(const ma_ctx *c) {
   return c->mesh_kind == MESH_GRID && c->strategy == 0 && !c->stats &&
          (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2);
@@ -624,7 +629,7 @@ int alloc_eval(ma_ctx *c) {
 }
 
 // K1 per-eval part + K2 on the current device weights (c->w, caller order)
-template <int FUSED_MODE = -1> int run_cells(ma_ctx *c, Params &p) {
+template <bool POLY = false> int run_cells(ma_ctx *c, Params &p) {
   const int N = c->N;
   k_gather<<<cdiv(N, 256), 256, 0, c->stream>>>(c->w.as<double>(), c->perm.as<int>(), N, c->ws.as<double>());
   const size_t nb = (size_t)1 << (2 * c->L);
@@ -645,8 +650,7 @@ template <int FUSED_MODE = -1> int run_cells(ma_ctx *c, Params &p) {
   }
   CK(cudaGetLastError());
   if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PREP + 1], c->stream));
-  if (FUSED_MODE >= 0) CKR(launch_cells_seg_kmax<(FUSED_MODE >= 0 ? FUSED_MODE : 0)>(c, p));
-  else CKR(launch_cells_kmax(c, p));
+  CKR(launch_cells_kmax<POLY>(c, p));
   if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CELLS + 1], c->stream));
   return MA_OK;
 }
@@ -660,6 +664,11 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
   for (int attempt = 0; attempt < 3; ++attempt) {
     CKR(alloc_eval(c));
     if (MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) CKR(ensure(c, c->mom, (size_t)c->N * 48));
+    if (use_seg<MODE>(c)) {
+      const size_t slots = (size_t)cells_maxv(c->kmax) * c->N;
+      CKR(ensure(c, c->poly_x, slots * 8)); CKR(ensure(c, c->poly_y, slots * 8));
+      CKR(ensure(c, c->poly_t, slots * 4)); CKR(ensure(c, c->poly_n, (size_t)c->N * 4));
+    }
     Params p;
     fill_params(c, p);
     CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
@@ -677,8 +686,8 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     }
     constexpr int SEG_MODE = (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) ? MODE : 0;
     const bool seg = use_seg<MODE>(c);
-    if (seg) CKR(run_cells<SEG_MODE>(c, p));
-    else CKR(run_cells(c, p));
+    if (seg) CKR(run_cells<true>(c, p));
+    else CKR(run_cells<false>(c, p));
     c->aborted = false;
     if (c->abort_on_empty) {
       // line-search trial: an empty cell means min m = 0 < eps0, the point is rejected whatever the
@@ -694,7 +703,8 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
         return MA_OK;
       }
     }
-    if (!seg) CKR(launch_pieces_mode<MODE>(c, p));
+    if (seg) CKR(launch_seg_kmax<SEG_MODE>(c, p));
+    else CKR(launch_pieces_mode<MODE>(c, p));
     if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
     if (MODE == MODE_KANTOROVICH) {
       if (with_hessian) CKR(scan_i32(c, c->rowcnt.as<int>(), c->rowptr.as<int>(), c->N));

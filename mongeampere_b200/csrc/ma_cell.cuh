@@ -55,6 +55,10 @@ struct Params {
   int *nbr;         // N * kmax, -1 padded, CCW
   int *nbr_cnt;     // N, -1 = empty cell
   double *cell_bb;  // N * 4 (absolute xmin, ymin, xmax, ymax)
+  // cell polygons for the boundary-segment kernel (grid meshes): vertex k of cell i at [k * N + i],
+  // local coordinates, tag = site index or < 0 for a side of the mesh box; poly_n[i] vertices
+  double *poly_x, *poly_y;
+  int *poly_t, *poly_n;
   // K3 outputs
   double *mass;     // N
   double *fcell;    // N: m_i w_i - cost_i
@@ -77,9 +81,10 @@ struct Params {
 // ------------------------------------------------------------------------------------------------
 // K2: power cell of Dirac i in the mesh box.  Returns n (0 = empty, -1 = capacity overflow).
 // ------------------------------------------------------------------------------------------------
-template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT> &P, int maxv, int *flags_out) {
+template <class Poly> MA_DEV int cell_build(const Params &p, int i, Poly &P, int maxv, int *flags_out) {
   const double xi = p.xs[i], yi = p.ys[i], wi = p.ws[i];
   const double bx0 = p.bb[0] - xi, by0 = p.bb[1] - yi, bx1 = p.bb[2] - xi, by1 = p.bb[3] - yi;
+  if (Poly::PACK) { P.ord = 0x3210ull; P.used = 0xfu; }
   P.X(0) = bx0; P.Y(0) = by0; P.T(0) = -1;  // bottom
   P.X(1) = bx1; P.Y(1) = by0; P.T(1) = -2;  // right
   P.X(2) = bx1; P.Y(2) = by1; P.T(2) = -3;  // top
@@ -97,165 +102,215 @@ template <int NT> MA_DEV int cell_build(const Params &p, int i, const PolyRef<NT
     else { nx = 1; ny = 0; cl = bx0; }
   };
   const double NEG_INF = -1.0 / 0.0, POS_INF = 1.0 / 0.0;
-  if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return 0;
-  // ---- one candidate site: clip the polygon by its bisector (both phases) ----------------------
-  // status: 0 ok, -1 polygon capacity overflow.  Sites with |y_j - y_i|^2 outside (lo2, hi2] are skipped.
-  int status = 0;
-  bool cut_in_pass = true;
-  auto site = [&](int j, double lo2, double hi2) {
-    if (j == i) return;
-    const double Dx = p.xs[j] - xi, Dy = p.ys[j] - yi, wj = p.ws[j];
-    const double dd2 = Dx * Dx + Dy * Dy;
-    if (dd2 <= lo2 || dd2 > hi2) return;  // handled by an earlier pass / left to a later one
-    if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
-      if (wj > wi || (wj == wi && j < i)) n = 0;
-      return;
-    }
-    const double s = dd2 + (wi - wj);
-    if (s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12)) return;  // bisector beyond every vertex
-    const double c = 0.5 * s;
-    unsigned long long in = 0ull;
-    for (int k = 0; k < n; ++k)
-      if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
-    const unsigned long long full = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
-    if (in == full) return;
-    if (in == 0ull) { n = 0; return; }
-    const int n2 = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, j, lineof);
-    if (n2 < 0) { status = -1; n = 0; return; }
-    n = n2;
-    cut_in_pass = true;
-    R2 = 0.0;
-    for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
-  };
-  // ---- phase 1: square rings of leaf bins around the Dirac's own bin --------------------------
-  // Every lane of a warp walks the same ring pattern (consecutive cells share bins), nearest bins
-  // first, so the polygon is tight after a few dozen sites.  After ring r every site inside the
-  // (2r+1)^2 block has been seen, hence every site within rho = distance(y_i, block boundary); the
-  // search is over when no site at distance >= rho can cut, whatever its weight (global maximum
-  // weight, SURVEY §7.2 security radius).  If that certificate cannot work (weights with a gradient),
-  // phase 2 takes over with the per-node bounds.
-  const int G = 1 << p.L;
-  const double pinv = 1.0 / p.ph;
-  const int bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1), by = min(max((int)((yi - p.py0) * pinv), 0), G - 1);
-  const double dw_glob = wi - p.wmax[0];  // <= 0
-  int rdone = -1;          // rings 0..rdone are done
-  double rho2 = -1.0;      // every site with |y_j - y_i|^2 <= rho2 is done
-  const int RMAX = 3;
-  for (int r = 0; r <= RMAX && n > 0; ++r) {
-    for (int oy = -r; oy <= r; ++oy) {
-      const int cy = by + oy;
-      if (cy < 0 || cy >= G) continue;
-      const int step = (oy == -r || oy == r || r == 0) ? 1 : 2 * r;
-      for (int ox = -r; ox <= r; ox += step) {
-        const int cx = bx + ox;
-        if (cx < 0 || cx >= G) continue;
-        const unsigned code = morton2((unsigned)cx, (unsigned)cy);
-        const int b0 = p.bin_start[code], b1 = p.bin_start[code + 1];
-        for (int j = b0; j < b1 && n > 0; ++j) site(j, -1.0, POS_INF);
-      }
-    }
-    rdone = r;
-    if (status < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
-    if (n == 0) return 0;
-    // distance from y_i to the part of the block boundary that has bins behind it
-    double rho = POS_INF;
-    if (bx - r > 0) rho = fmin(rho, xi - (p.px0 + (double)(bx - r) * p.ph));
-    if (bx + r < G - 1) rho = fmin(rho, (p.px0 + (double)(bx + r + 1) * p.ph) - xi);
-    if (by - r > 0) rho = fmin(rho, yi - (p.py0 + (double)(by - r) * p.ph));
-    if (by + r < G - 1) rho = fmin(rho, (p.py0 + (double)(by + r + 1) * p.ph) - yi);
-    if (rho == POS_INF) return n;  // the block covers every bin
-    rho = fmax(rho, 0.0);
-    rho2 = rho * rho;
-    if (cannot_cut(rho2, dw_glob, R2)) return n;
-    // can one more ring certify anything?  not if even a tiny polygon fails: (rho+ph)^2 + dw <= 0
-    const double rn = rho + p.ph;
-    if (rn * rn + dw_glob <= 0.0) break;
-  }
-  // ---- phase 2: expanding-radius search over the quadtree ---------------------------------------
-  // A plain nearest-first DFS degenerates for a Dirac next to a high-level quadrant boundary: until
-  // the polygon is cut on every side its security radius is the whole box, so nothing is pruned and
-  // the nearest quadrant is searched exhaustively.  Instead the tree is walked in passes with a
-  // distance cap that doubles: pass q handles exactly the sites with prev < |y_j - y_i| <= cap, and
-  // the search ends with one uncapped pass (pruned by the security tests alone) once the polygon fits
-  // in the disk of radius cap/2 or a whole pass went by without a cut.  Sites of the phase-1 block
-  // are skipped (they were all seen).
+  // The search is written as
+  //     for (;;) { SEARCH, one small step at a time, until every lane holds a cutting site; CLIP; }
+  // with warp votes / syncs between the steps: the lanes of a warp find their cutting sites at
+  // different moments, and the compiler does not reconverge them on its own, so each step is
+  // straight-line code (no break / continue / early return) and the whole warp moves from step to
+  // step together.  (On the CPU emulation the votes are the identity.)
+  //
+  // SEARCH, phase 0: square rings of leaf bins around the Dirac's own bin.  Every lane walks the same
+  // ring pattern (consecutive cells share bins), nearest bins first, so the polygon is tight after a
+  // few dozen sites.  After ring r every site inside the (2r+1)^2 block has been seen, hence every
+  // site within rho = distance(y_i, block boundary); the search is over when no site at distance
+  // >= rho can cut, whatever its weight (global maximum weight, SURVEY §7.2 security radius).  If
+  // that certificate cannot work (weights with a gradient), phase 1 takes over.
+  //
+  // SEARCH, phase 1: expanding-radius walk over the quadtree.  A plain nearest-first DFS degenerates
+  // for a Dirac next to a high-level quadrant boundary: until the polygon is cut on every side its
+  // security radius is the whole box, so nothing is pruned and the nearest quadrant is searched
+  // exhaustively.  Instead the tree is walked in passes with a distance cap that doubles: a pass
+  // handles exactly the sites with prev < |y_j - y_i| <= cap, and the search ends with one uncapped
+  // pass (pruned by the security tests alone) once the polygon fits in the disk of radius cap/2 or a
+  // whole pass went by without a cut.  Nodes inside the phase-0 block are skipped (all seen).
   // Security tests for a node B, both conservative ("no site of B can take any vertex p of the
   // polygon from i", i.e. pow_j(p) >= pow_i(p) for every j in B and every vertex p):
   //   (a) disk around y_i with the node's maximum weight;
   //   (b) the node's supporting plane (ma_geom.cuh) against every vertex.
   // (b) is what keeps the search local once the weights have a gradient: the cell then lies far from
   // its own Dirac and (a), which measures from y_i, would keep a disk of radius ~|grad w| alive.
-  double cap = 2.0 * fmax(sqrt(rho2 > 0.0 ? rho2 : 0.0), p.ph);
-  double prev2 = rho2;
+  const int G = 1 << p.L;
+  const double pinv = 1.0 / p.ph;
+  const int bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1), by = min(max((int)((yi - p.py0) * pinv), 0), G - 1);
+  const double dw_glob = wi - p.wmax[0];  // <= 0
+  const int RMAX = 3;
+  int status = 0;
+  int phase = 0;              // 0 rings, 1 tree, 2 finished
+  if (p.abort_on_empty && *(volatile const int *)p.abort_flag) { n = 0; phase = 2; }
+  int r = 0, q = 0, nq = 1;   // ring r: next position q of nq
+  int j = 0, jend = 0;        // remaining sites of the current leaf bin
+  double lo2 = -1.0, hi2 = POS_INF;  // only sites with lo2 < |y_j - y_i|^2 <= hi2 are looked at
+  int rdone = -1;             // rings 0..rdone are complete
   unsigned stk[52];
-  cut_in_pass = true;
-  for (int pass = 0; pass < 64 && n > 0; ++pass) {
-    const bool last = !(4.0 * R2 > cap * cap) || !cut_in_pass;
-    cut_in_pass = false;
-    if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return 0;
-    const double cap2 = last ? POS_INF : cap * cap;
-    int sp = 0;
-    stk[sp++] = 0u;
-    while (sp > 0 && n > 0) {
-      unsigned e = stk[--sp];
-      int l = (int)(e >> 26);
-      unsigned code = e & 0x3ffffffu;
-      double wm = p.wmax[(((size_t)1 << (2 * l)) - 1) / 3 + code];
-      if (wm == NEG_INF) continue;
-      {  // node inside the phase-1 block: all its sites are done
-        const int sh = p.L - l;
-        const int X0 = (int)morton_compact1(code) << sh, Y0 = (int)morton_compact1(code >> 1) << sh, W = 1 << sh;
-        if (X0 >= bx - rdone && X0 + W - 1 <= bx + rdone && Y0 >= by - rdone && Y0 + W - 1 <= by + rdone) continue;
-      }
-      double S = p.ph * (double)(1u << (p.L - l));
-      double ox = p.px0 + (double)morton_compact1(code) * S - xi;
-      double oy = p.py0 + (double)morton_compact1(code >> 1) * S - yi;
-      double dx = fmax(fmax(ox, -(ox + S)), 0.0), dy = fmax(fmax(oy, -(oy + S)), 0.0);
-      double d2 = dx * dx + dy * dy;
-      if (d2 > cap2) continue;
-      {
-        double fx = fmax(fabs(ox), fabs(ox + S)), fy = fmax(fabs(oy), fabs(oy + S));
-        if (fx * fx + fy * fy <= prev2) continue;  // every site of this node was handled by an earlier pass
-      }
-      if (d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) continue;  // (a)
-      {
-        const size_t node = level_offset(l) + code;
-        const double Gx = p.nodeG[2 * node], Gy = p.nodeG[2 * node + 1], al = dkey_inv(p.nodeA[node]);
-        const double hs = 0.5 * S, Zx = ox + hs, Zy = oy + hs;
-        bool can = false;
-        for (int k = 0; k < n; ++k) {  // (b) supporting plane of the node vs every vertex
-          double ux = P.X(k), uy = P.Y(k), Px = ux - Zx, Py = uy - Zy;
-          double pp = Px * Px + Py * Py, slop = (fabs(2.0 * Px + Gx) + fabs(2.0 * Py + Gy)) * hs;
-          double r2 = ux * ux + uy * uy;
-          double lb = pp + al - slop;
-          if (!(lb >= (r2 - wi) + 1e-10 * (pp + fabs(al) + slop + r2 + fabs(wi)))) { can = true; break; }
+  int sp = 0, pass = 0;
+  double cap = 0.0, prev2 = -1.0, cap2 = POS_INF;
+  bool last = false, cut_in_pass = true;
+  int jc = -1;                // the cutting site found by the search
+  double cDx = 0.0, cDy = 0.0, cc = 0.0;
+  unsigned long long cin = 0ull;
+  for (;;) {
+    for (;;) {
+      // keep searching while more lanes are searching than are holding a cutting site: both the
+      // search steps and the clips then run with at least half of the unfinished lanes
+      const int n_search = MA_WARP_COUNT(jc < 0 && phase < 2), n_hold = MA_WARP_COUNT(jc >= 0);
+      if (n_search == 0 || n_hold >= n_search) break;
+      if (jc < 0 && phase < 2) {
+        if (j < jend) {
+          // ---- step kind 1: the next site of the current bin
+          const int jj = j++;
+          const double Dx = p.xs[jj] - xi, Dy = p.ys[jj] - yi, wj = p.ws[jj];
+          const double dd2 = Dx * Dx + Dy * Dy;
+          if (jj != i && dd2 > lo2 && dd2 <= hi2) {  // else: itself / an earlier pass's / a later pass's
+            if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
+              if (wj > wi || (wj == wi && jj < i)) { n = 0; phase = 2; }
+            } else {
+              const double s = dd2 + (wi - wj);
+              if (!(s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12))) {  // else: bisector beyond every vertex
+                const double c = 0.5 * s;
+                unsigned long long in = 0ull;
+                for (int k = 0; k < n; ++k)
+                  if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
+                const unsigned long long full = lowmask64(n);
+                if (in == 0ull) { n = 0; phase = 2; }
+                else if (in != full) { jc = jj; cDx = Dx; cDy = Dy; cc = c; cin = in; }
+              }
+            }
+          }
+        } else if (phase == 0) {
+          // ---- step kind 2: the next bin of the ring walk
+          if (q == nq) {  // ring r is complete
+            rdone = r;
+            // distance from y_i to the part of the block boundary that has bins behind it
+            double rho = POS_INF;
+            if (bx - r > 0) rho = fmin(rho, xi - (p.px0 + (double)(bx - r) * p.ph));
+            if (bx + r < G - 1) rho = fmin(rho, (p.px0 + (double)(bx + r + 1) * p.ph) - xi);
+            if (by - r > 0) rho = fmin(rho, yi - (p.py0 + (double)(by - r) * p.ph));
+            if (by + r < G - 1) rho = fmin(rho, (p.py0 + (double)(by + r + 1) * p.ph) - yi);
+            const double rhoc = fmax(rho, 0.0), rho2 = rhoc * rhoc, rn = rhoc + p.ph;
+            if (rho == POS_INF || cannot_cut(rho2, dw_glob, R2)) {
+              phase = 2;  // the block covers every bin / nothing farther than rho can cut
+            } else if (r == RMAX || rn * rn + dw_glob <= 0.0) {
+              // (one more ring could not certify anything if even a tiny polygon fails)
+              phase = 1;  // first tree pass: everything within rho is done
+              prev2 = rho2;
+              cap = 2.0 * fmax(rhoc, p.ph);
+              cut_in_pass = true;
+              pass = 0;
+              sp = -1;  // "begin a pass"
+            } else {
+              ++r; q = 0; nq = 8 * r;
+            }
+          } else {
+            int ox, oy;  // position q of ring r: top row, bottom row, then the two columns
+            const int side = 2 * r + 1;
+            if (q < side) { ox = q - r; oy = -r; }
+            else if (q < 2 * side) { ox = q - side - r; oy = r; }
+            else { const int t = q - 2 * side; ox = (t & 1) ? r : -r; oy = (t >> 1) - r + 1; }
+            ++q;
+            const int cx = bx + ox, cy = by + oy;
+            if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
+              const unsigned code = morton2((unsigned)cx, (unsigned)cy);
+              j = p.bin_start[code]; jend = p.bin_start[code + 1];
+            }
+          }
+        } else {
+          // ---- step kind 3: the next node of the tree walk
+          if (sp <= 0) {
+            bool go = true;
+            if (sp == 0) {  // the pass is over
+              if (last || ++pass >= 64) { phase = 2; go = false; }
+              prev2 = cap2;
+              cap *= 2.0;
+            }
+            if (go && p.abort_on_empty && *(volatile const int *)p.abort_flag) { n = 0; phase = 2; go = false; }
+            if (go) {
+              last = !(4.0 * R2 > cap * cap) || !cut_in_pass;
+              cut_in_pass = false;
+              cap2 = last ? POS_INF : cap * cap;
+              lo2 = prev2; hi2 = cap2;
+              sp = 0;
+              stk[sp++] = 0u;
+            }
+          }
+          if (phase == 1) {
+            const unsigned e = stk[--sp];
+            const int l = (int)(e >> 26);
+            const unsigned code = e & 0x3ffffffu;
+            const double wm = p.wmax[(((size_t)1 << (2 * l)) - 1) / 3 + code];
+            bool alive = wm != NEG_INF;
+            {  // node inside the phase-0 block: all its sites are done
+              const int sh = p.L - l;
+              const int X0 = (int)morton_compact1(code) << sh, Y0 = (int)morton_compact1(code >> 1) << sh, W = 1 << sh;
+              if (X0 >= bx - rdone && X0 + W - 1 <= bx + rdone && Y0 >= by - rdone && Y0 + W - 1 <= by + rdone) alive = false;
+            }
+            const double S = p.ph * (double)(1u << (p.L - l));
+            const double ox = p.px0 + (double)morton_compact1(code) * S - xi;
+            const double oy = p.py0 + (double)morton_compact1(code >> 1) * S - yi;
+            const double dx = fmax(fmax(ox, -(ox + S)), 0.0), dy = fmax(fmax(oy, -(oy + S)), 0.0);
+            const double d2 = dx * dx + dy * dy;
+            if (d2 > cap2) alive = false;
+            {
+              const double fx = fmax(fabs(ox), fabs(ox + S)), fy = fmax(fabs(oy), fabs(oy + S));
+              if (fx * fx + fy * fy <= prev2) alive = false;  // every site of this node was handled by an earlier pass
+            }
+            if (alive && d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) alive = false;  // (a)
+            if (alive) {
+              const size_t node = level_offset(l) + code;
+              const double Gx = p.nodeG[2 * node], Gy = p.nodeG[2 * node + 1], al = dkey_inv(p.nodeA[node]);
+              const double hs = 0.5 * S, Zx = ox + hs, Zy = oy + hs;
+              bool can = false;
+              for (int k = 0; k < n; ++k) {  // (b) supporting plane of the node vs every vertex
+                const double ux = P.X(k), uy = P.Y(k), Px = ux - Zx, Py = uy - Zy;
+                const double pp = Px * Px + Py * Py, slop = (fabs(2.0 * Px + Gx) + fabs(2.0 * Py + Gy)) * hs;
+                const double r2 = ux * ux + uy * uy;
+                const double lb = pp + al - slop;
+                can = can || !(lb >= (r2 - wi) + 1e-10 * (pp + fabs(al) + slop + r2 + fabs(wi)));
+              }
+              alive = can;
+            }
+            if (alive) {
+              if (l < p.L) {
+                // children, nearest first (pushed in reverse)
+                const double cx = ox + 0.5 * S, cy = oy + 0.5 * S;
+                const unsigned q0 = (cx <= 0.0 ? 1u : 0u) | (cy <= 0.0 ? 2u : 0u);
+                const bool xfirst = fabs(cx) < fabs(cy);
+                const unsigned q1 = q0 ^ (xfirst ? 1u : 2u), q2 = q0 ^ (xfirst ? 2u : 1u), q3 = q0 ^ 3u;
+                const unsigned base = ((unsigned)(l + 1) << 26) | (code << 2);
+                if (sp + 4 > 52) { status = FLAG_STACK_OVERFLOW; n = 0; phase = 2; }
+                else { stk[sp++] = base | q3; stk[sp++] = base | q2; stk[sp++] = base | q1; stk[sp++] = base | q0; }
+              } else {
+                j = p.bin_start[code]; jend = p.bin_start[code + 1];
+              }
+            }
+          }
         }
-        if (!can) continue;
       }
-      if (l < p.L) {
-        // children, nearest first (pushed in reverse)
-        double cx = ox + 0.5 * S, cy = oy + 0.5 * S;
-        unsigned q0 = (cx <= 0.0 ? 1u : 0u) | (cy <= 0.0 ? 2u : 0u);
-        bool xfirst = fabs(cx) < fabs(cy);
-        unsigned q1 = q0 ^ (xfirst ? 1u : 2u), q2 = q0 ^ (xfirst ? 2u : 1u), q3 = q0 ^ 3u;
-        unsigned base = ((unsigned)(l + 1) << 26) | (code << 2);
-        if (sp + 4 > 52) { *flags_out |= FLAG_STACK_OVERFLOW; return -1; }
-        stk[sp++] = base | q3; stk[sp++] = base | q2; stk[sp++] = base | q1; stk[sp++] = base | q0;
-        continue;
-      }
-      const int b0 = p.bin_start[code], b1 = p.bin_start[code + 1];
-      for (int j = b0; j < b1 && n > 0; ++j) site(j, prev2, cap2);
-      if (status < 0) { *flags_out |= FLAG_CELL_OVERFLOW; return -1; }
+      MA_WARP_SYNC();
     }
-    if (last) break;
-    prev2 = cap2;
-    cap *= 2.0;
+    // warp-uniform exit: nobody holds a site and (see the loop above) nobody is searching
+    if (!MA_WARP_ANY(jc >= 0)) break;
+    if (jc >= 0) {
+      // ---- CLIP by site jc ---------------------------------------------------------------------
+      int n2;
+      if constexpr (Poly::PACK) n2 = clip_packed(P, n, maxv, cin, cDx, cDy, cc, jc, lineof);
+      else n2 = clip_rebuild(P, n, maxv, cin, cDx, cDy, cc, jc, lineof);
+      if (n2 < 0) { status = FLAG_CELL_OVERFLOW; n = 0; phase = 2; }
+      else {
+        n = n2;
+        cut_in_pass = true;
+        R2 = 0.0;
+        for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
+      }
+      jc = -1;
+    }
+    MA_WARP_SYNC();
   }
+  if (status) { *flags_out |= status; return -1; }
   return n;
 }
 
 // writes the neighbour list / bounding box of a built cell
-template <int NT> MA_DEV void cell_emit(const Params &p, int i, const PolyRef<NT> &P, int n) {
+template <class Poly> MA_DEV void cell_emit(const Params &p, int i, const Poly &P, int n) {
   const double xi = p.xs[i], yi = p.ys[i];
   int *nb = p.nbr + (size_t)i * p.kmax;
   int cnt = 0;
@@ -366,7 +421,7 @@ MA_DEV int piece_clip(const Params &p, const PolyRef<NT> &P, int maxv, const Cel
     unsigned long long full = (1ull << n) - 1ull;
     if (in == full) continue;
     if (in == 0ull) { n = 0; break; }
-    n = clip_rebuild<NT>(P, n, maxv, in, Dx, Dy, c, s, lineof);
+    n = clip_rebuild(P, n, maxv, in, Dx, Dy, c, s, lineof);
     if (n < 0) return -1;
   }
   return n;

@@ -18,14 +18,46 @@
 namespace ma {
 
 #define MA_DEV __host__ __device__ __forceinline__
+// Warp votes used as explicit reconvergence points in the per-thread loops (the compiler does not
+// reliably reconverge lanes that leave a data-dependent loop at different times).  On the host (the
+// CPU emulation of tests/emu runs one "lane" at a time) they are the identity.
+#ifdef __CUDA_ARCH__
+#define MA_WARP_ANY(pred) __any_sync(0xffffffffu, (pred))
+#define MA_WARP_COUNT(pred) __popc(__ballot_sync(0xffffffffu, (pred)))
+#define MA_WARP_SYNC() __syncwarp()
+#else
+#define MA_WARP_ANY(pred) (pred)
+#define MA_WARP_COUNT(pred) ((pred) ? 1 : 0)
+#define MA_WARP_SYNC() ((void)0)
+#endif
 
-template <int NT> struct PolyRef {
+// PACKED = false: vertex k lives in slot k (a clip shifts the array).
+// PACKED = true (capacity <= 16): vertex data never moves; the cyclic order of the slots is a packed
+// list of 4-bit slot numbers held in a register, so that a clip is a handful of bit operations with
+// no data-dependent control flow (what the SIMT lanes of K2 need to stay converged).
+template <int NT, bool PACKED = false> struct PolyRef {
+  static constexpr bool PACK = PACKED;
   double *x, *y;  // base pointers already offset by the thread's column
   int *tag;
-  MA_DEV double &X(int k) const { return x[k * NT]; }
-  MA_DEV double &Y(int k) const { return y[k * NT]; }
-  MA_DEV int &T(int k) const { return tag[k * NT]; }
+  unsigned long long ord;  // PACKED: slot of vertex k in bits [4k, 4k+4)
+  unsigned used;           // PACKED: bit s set <=> slot s holds a vertex
+  MA_DEV int slot(int k) const { return PACKED ? (int)((ord >> (4 * k)) & 15ull) : k; }
+  MA_DEV double &X(int k) const { return x[slot(k) * NT]; }
+  MA_DEV double &Y(int k) const { return y[slot(k) * NT]; }
+  MA_DEV int &T(int k) const { return tag[slot(k) * NT]; }
+  MA_DEV double &SX(int s) const { return x[s * NT]; }  // by slot
+  MA_DEV double &SY(int s) const { return y[s * NT]; }
+  MA_DEV int &ST(int s) const { return tag[s * NT]; }
 };
+
+MA_DEV unsigned long long lowmask64(int bits) { return bits >= 64 ? ~0ull : ((1ull << bits) - 1ull); }
+MA_DEV int ctz64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
 
 // Solve { u.D = c } ∩ { u.n = cl }.
 MA_DEV void line_isect(double Dx, double Dy, double c, double nx, double ny, double cl, double &ux, double &uy) {
@@ -39,8 +71,8 @@ MA_DEV void line_isect(double Dx, double Dy, double c, double nx, double ny, dou
 //   in   : bit k set  <=>  vertex k is strictly inside the half-plane (decided by the caller)
 //   lineof(tag, nx, ny, cl) returns the supporting line { u.n = cl } of an existing edge.
 // Returns the new vertex count (0: empty), or -1 on capacity overflow.
-template <int NT, class LineOf>
-MA_DEV int clip_rebuild(const PolyRef<NT> &P, int n, int maxv, unsigned long long in, double Dx, double Dy, double c,
+template <class Poly, class LineOf>
+MA_DEV int clip_rebuild(const Poly &P, int n, int maxv, unsigned long long in, double Dx, double Dy, double c,
                         int newtag, LineOf lineof) {
   // locate the (single, after sanitising) run of outside vertices: [start, start + r)
   int start = -1;
@@ -88,6 +120,53 @@ MA_DEV int clip_rebuild(const PolyRef<NT> &P, int n, int maxv, unsigned long lon
     }
   }
   return m;
+}
+
+// The same pass on a PACKED polygon, without data-dependent branches: the run of outside vertices
+// [start, start + r) is located with bit operations on `in`, its first slot is reused for the vertex
+// where the polygon leaves the half-plane, its last slot (or a free one when r = 1) for the vertex
+// where it re-enters, and the new cyclic order is the inside run followed by those two.
+template <class Poly, class LineOf>
+MA_DEV int clip_packed(Poly &P, int n, int maxv, unsigned long long in, double Dx, double Dy, double c, int newtag,
+                       LineOf lineof) {
+  const unsigned long long full = lowmask64(n), out = ~in & full;
+  const unsigned long long prev = ((out << 1) | (out >> (n - 1))) & full;  // bit k = out[k-1]
+  const unsigned long long starts = out & ~prev;
+  if (starts == 0ull) return n;  // cannot happen when 0 < popcount(in) < n
+  const int start = ctz64(starts);
+  const unsigned long long rot = start ? (((out >> start) | (out << (n - start))) & full) : out;
+  const int r = ctz64(~rot);  // length of the outside run
+  int A = start - 1; if (A < 0) A += n;
+  int last = start + r - 1; if (last >= n) last -= n;
+  const int sS = P.slot(start), sL = P.slot(last);
+  const int tA = P.T(A), tL = P.ST(sL);
+  double nx, ny, cl, Xx, Xy, Yx, Yy;
+  lineof(tA, nx, ny, cl);
+  line_isect(Dx, Dy, c, nx, ny, cl, Xx, Xy);
+  lineof(tL, nx, ny, cl);
+  line_isect(Dx, Dy, c, nx, ny, cl, Yx, Yy);
+  unsigned used = P.used;
+  for (int t = 1; t + 1 < r; ++t) {  // slots strictly inside the run become free
+    int k = start + t; if (k >= n) k -= n;
+    used &= ~(1u << P.slot(k));
+  }
+  int sY = sL;
+  if (r == 1) {
+    const unsigned fr = ~used & (unsigned)lowmask64(maxv);
+    if (fr == 0u) return -1;
+    sY = ctz64((unsigned long long)fr);
+    used |= 1u << sY;
+  }
+  const int m = n - r;  // inside vertices
+  if (m + 2 > maxv) return -1;
+  P.SX(sS) = Xx; P.SY(sS) = Xy; P.ST(sS) = newtag;
+  P.SX(sY) = Yx; P.SY(sY) = Yy; P.ST(sY) = tL;
+  int s0 = last + 1; if (s0 >= n) s0 -= n;  // first inside vertex
+  const unsigned long long o = P.ord & lowmask64(4 * n);
+  const unsigned long long ro = s0 ? (((o >> (4 * s0)) | (o << (4 * (n - s0)))) & lowmask64(4 * n)) : o;
+  P.ord = (ro & lowmask64(4 * m)) | ((unsigned long long)sS << (4 * m)) | ((unsigned long long)sY << (4 * (m + 1)));
+  P.used = used;
+  return m + 2;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -433,47 +433,56 @@ __global__ void k_node_alpha(int n, int L, const double *__restrict__ xs, const 
 }
 
 // ================================================================================================
-// K2: one thread per cell
+// K2: one thread per cell.  POLY: also store the cell polygon for k_seg (grid meshes).
 // ================================================================================================
-template <int MAXV, int NT> __global__ void __launch_bounds__(NT) k_cells(Params p) {
+template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT) k_cells(Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
   double *sy = sx + MAXV * NT;
   int *st = reinterpret_cast<int *>(sy + MAXV * NT);
   int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
-  if (i >= p.cell_hi) return;
-  PolyRef<NT> P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+  // cell_build votes across the warp: lanes past the end redo the last cell and write nothing
+  const bool valid = i < p.cell_hi;
+  if (!valid) i = p.cell_hi - 1;
+  PolyRef<NT, (MAXV <= 16)> P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
   int fl = 0;
-  int n = cell_build<NT>(p, i, P, MAXV, &fl);
+  int n = cell_build(p, i, P, MAXV, &fl);
+  MA_WARP_SYNC();
+  if (!valid) return;
   if (fl) atomicOr(p.flags, fl);
   if (n == 0 && p.abort_on_empty) p.flags[1] = 1;  // an empty cell: the line search rejects this trial point
   if (n < 0) n = 0;
-  cell_emit<NT>(p, i, P, n);
+  cell_emit(p, i, P, n);
+  if (POLY) {
+    p.poly_n[i] = n;
+    for (int k = 0; k < n; ++k) {
+      const size_t o = (size_t)k * p.N + i;
+      p.poly_x[o] = P.X(k); p.poly_y[o] = P.Y(k); p.poly_t[o] = P.T(k);
+    }
+  }
 }
 template <int MAXV, int NT> constexpr size_t cells_smem_bytes() { return (size_t)MAXV * NT * (8 + 8 + 4); }
 
 // ================================================================================================
-// K2+K3 fused for grid meshes: one thread per cell builds the cell (K2) and integrates it over the
-// boundary segments (ma_seg.cuh) while the polygon is still in shared memory.
+// K3 for grid meshes: one thread per cell integrates the cell over its boundary segments
+// (ma_seg.cuh); the polygon comes from K2 and is staged in shared memory (the chords of part B
+// revisit every vertex).
 // ================================================================================================
-template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT) k_cells_seg(Params p) {
+template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT) k_seg(Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
   double *sy = sx + MAXV * NT;
   int *st = reinterpret_cast<int *>(sy + MAXV * NT);
-  int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
+  const int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
   if (i >= p.cell_hi) return;
-  PolyRef<NT> P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
-  int fl = 0;
-  int n = cell_build<NT>(p, i, P, MAXV, &fl);
-  if (fl) atomicOr(p.flags, fl);
-  if (n == 0 && p.abort_on_empty) p.flags[1] = 1;
-  if (n < 0) n = 0;
-  cell_emit<NT>(p, i, P, n);
-  // line-search trial with an empty cell somewhere: the point is rejected whatever the integrals say
-  if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return;
+  PolyRef<NT, false> P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+  const int n = p.poly_n[i];
+  for (int k = 0; k < n; ++k) {
+    const size_t o = (size_t)k * p.N + i;
+    P.X(k) = p.poly_x[o]; P.Y(k) = p.poly_y[o]; P.T(k) = p.poly_t[o];
+  }
   SegAcc acc;
-  unsigned long long touched = cell_integrate_grid<NT, MODE>(p, i, P, n, acc, p.hslot + (size_t)i * p.kmax);
+  unsigned long long touched = cell_integrate_grid<MODE>(p, i, P, n, acc, p.hslot + (size_t)i * p.kmax);
   if (MODE == MODE_KANTOROVICH) {
     p.mass[i] = acc.mass;
     p.fcell[i] = acc.mass * p.ws[i] - acc.cost;

@@ -97,8 +97,8 @@ MA_DEV void seg_family_init(double u0, double sl, int &kn, int &stp, double &inv
 // supporting line is named by tag k: site index >= 0, or < 0 for a side of the mesh bounding box).
 // MODE_KANTOROVICH additionally writes, for every Laguerre edge in polygon order (= the order of
 // cell_emit's neighbour list), hslot = ∫_edge rho ds / (2 |y_i - y_j|)  and returns the touched mask.
-template <int NT, int MODE>
-MA_DEV unsigned long long cell_integrate_grid(const Params &p, int i, const PolyRef<NT> &P, int n, SegAcc &acc,
+template <int MODE, class Poly>
+MA_DEV unsigned long long cell_integrate_grid(const Params &p, int i, const Poly &P, int n, SegAcc &acc,
                                               double *hslot_row) {
   const double xi = p.xs[i], yi = p.ys[i];
   const double inv_dx = 1.0 / p.gdx, inv_dy = 1.0 / p.gdy;

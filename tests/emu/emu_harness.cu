@@ -170,19 +170,22 @@ extern "C" int emu_eval(int mesh_kind,
   {
     std::vector<double> px(maxv_cell), py(maxv_cell);
     std::vector<int> pt(maxv_cell);
-    PolyRef<1> P{px.data(), py.data(), pt.data()};
     for (int i = 0; i < N; ++i) {
       int fl = 0;
-      int n = cell_build<1>(p, i, P, maxv_cell, &fl);
+      // kmax = 16 is the packed-polygon class of the GPU (capacity 16), the larger ones shift arrays
+      PolyRef<1, true> PP{px.data(), py.data(), pt.data()};
+      PolyRef<1, false> PA{px.data(), py.data(), pt.data()};
+      int n = (kmax == 16) ? cell_build(p, i, PP, 16, &fl) : cell_build(p, i, PA, maxv_cell, &fl);
       flags |= fl;
       if (n < 0) n = 0;
-      cell_emit<1>(p, i, P, n);
+      auto finish = [&](auto &P) {
+      cell_emit(p, i, P, n);
       if (use_seg) {  // what k_cells_seg does after K2
         SegAcc acc;
         unsigned long long tch = 0;
-        if (mode == MODE_KANTOROVICH) tch = cell_integrate_grid<1, MODE_KANTOROVICH>(p, i, P, n, acc, hslot + (size_t)i * kmax);
-        else if (mode == MODE_MOMENTS1) cell_integrate_grid<1, MODE_MOMENTS1>(p, i, P, n, acc, nullptr);
-        else cell_integrate_grid<1, MODE_MOMENTS2>(p, i, P, n, acc, nullptr);
+        if (mode == MODE_KANTOROVICH) tch = cell_integrate_grid<MODE_KANTOROVICH>(p, i, P, n, acc, hslot + (size_t)i * kmax);
+        else if (mode == MODE_MOMENTS1) cell_integrate_grid<MODE_MOMENTS1>(p, i, P, n, acc, nullptr);
+        else cell_integrate_grid<MODE_MOMENTS2>(p, i, P, n, acc, nullptr);
         mass[i] = acc.mass;
         fcell[i] = acc.mass * ws[i] - acc.cost;
         touched[i] = tch;
@@ -195,6 +198,8 @@ extern "C" int emu_eval(int mesh_kind,
           o[5] = acc.m[4] + xi * acc.m[1] + yi * acc.m[0] + xi * yi * m;
         }
       }
+      };
+      if (kmax == 16) finish(PP); else finish(PA);
     }
   }
   // ---- K3 ----
