@@ -1,0 +1,109 @@
+// tests/cpp/test_dropin.cpp — the reference's driver flows (tests/test_opttransport.cpp,
+// tests/test_lloyd.cpp, tests/test_voronoi_tri.cpp, tests/test_quantization.cpp) written against THIS
+// repository's include/MA with the MA::lite stand-ins for Eigen / CGAL / CImg.  Prints one
+// "key value" line per checked quantity; tests/test_cpp_dropin.py compares them with the C-ABI
+// results obtained through Python and with the invariants the reference's drivers print.
+//
+// build: g++ -std=c++14 -O2 -I include tests/cpp/test_dropin.cpp -L mongeampere_b200 -lma_b200 -Wl,-rpath,...
+#include <MA/lloyd.hpp>
+#include <MA/optimal_transport.hpp>
+#include <MA/voronoi_triangulation_intersection.hpp>
+
+#include <cstdio>
+#include <cstdlib>
+
+typedef MA::lite::Kernel K;
+typedef MA::lite::Point Point;
+typedef MA::lite::Vector VectorXd;
+typedef MA::lite::Matrix MatrixXd;
+typedef MA::lite::SparseMatrix SparseMatrix;
+typedef MA::lite::Triangulation T;
+
+static double rr() { return 2 * double(rand() / (RAND_MAX + 1.0)) - 1; }  // tests/test_opttransport.cpp:19-22
+
+int main(int argc, const char **argv) {
+  const size_t N = argc > 1 ? atoi(argv[1]) : 1000;
+  const int n = argc > 2 ? atoi(argv[2]) : 32;
+  // a synthetic "image": two Gaussian bumps quantised to 8 bits (functions.hpp:102 adds 1e-3)
+  MA::lite::Image image(n, n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double x = -1 + 2.0 * i / (n - 1), y = -1 + 2.0 * j / (n - 1);
+      double v = 200 * std::exp(-((x - 0.3) * (x - 0.3) + (y + 0.2) * (y + 0.2)) / 0.08) +
+                 120 * std::exp(-((x + 0.4) * (x + 0.4) + (y - 0.4) * (y - 0.4)) / 0.02);
+      image(i, j) = std::floor(std::min(v, 255.0));
+    }
+  T t;
+  std::map<T::Face_handle, MA::Linear_function<K>> functions;
+  double total_mass = MA::image_to_pl_function(image, t, functions);
+  printf("total_mass %.17g\n", total_mass);
+
+  MatrixXd X(N, 2);
+  VectorXd masses(N), weights = VectorXd::Zero(N);
+  for (size_t i = 0; i < N; ++i) {
+    X(i, 0) = 0.999 * rr();
+    X(i, 1) = 0.999 * rr();
+    masses(i) = total_mass / N;
+  }
+  // ---- kantorovich at w = 0 (kantorovich.hpp:35-42) ----
+  VectorXd g;
+  SparseMatrix h;
+  double f = MA::kantorovich(t, functions, X, weights, g, h);
+  printf("f0 %.17g\n", f);
+  printf("sum_g0 %.17g\n", g.sum());
+  printf("nnz0 %zu\n", h.nonZeros());
+  {
+    VectorXd ones = VectorXd::Constant(N, 1.0), r = h * ones;  // Laplacian rows sum to zero
+    double mx = 0;
+    for (size_t i = 0; i < N; ++i) mx = std::max(mx, std::fabs(r(i)));
+    printf("max_rowsum0 %.3g\n", mx);
+  }
+  // ---- solve_laplacian_matrix (optimal_transport.hpp:41-87) ----
+  {
+    VectorXd gg = g - masses;
+    VectorXd d = MA::solve_laplacian_matrix(h, gg);
+    VectorXd r = h * d - gg;
+    double mx = 0;
+    for (size_t i = 0; i + 1 < N; ++i) mx = std::max(mx, std::fabs(r(i)));
+    printf("laplace_residual %.3g\n", mx / std::max(gg.norm(), 1e-300));
+    printf("laplace_last %.17g\n", d(N - 1));
+  }
+  // ---- ot_solve (optimal_transport.hpp:89-193) ----
+  VectorXd res;
+  MA::Statistics stats;
+  MA::ot_solve(t, functions, X, masses, res, 1e-9, 100, false, &stats);
+  printf("niter %zu\nneval %zu\n", stats.niter, stats.neval);
+  {
+    VectorXd g2;
+    SparseMatrix h2;
+    double f2 = MA::kantorovich(t, functions, X, res, g2, h2);
+    printf("f_final %.17g\n", f2);
+    printf("final_norm %.3g\n", (g2 - masses).norm());
+    printf("w_first %.17g\nw_last %.17g\n", res(0), res(N - 1));
+  }
+  // ---- lloyd / moments (lloyd.hpp:30-144) ----
+  {
+    VectorXd m;
+    MatrixXd c, c1, inertia;
+    MA::lloyd(t, functions, X, res, m, c);
+    printf("lloyd_mass_sum %.17g\n", m.sum());
+    printf("lloyd_c0 %.17g %.17g\n", c(0, 0), c(0, 1));
+    MA::second_moment(t, functions, X, res, m, c1, inertia);
+    printf("second_moment0 %.17g %.17g %.17g\n", inertia(0, 0), inertia(0, 1), inertia(0, 2));
+    printf("first_moment0 %.17g %.17g\n", c1(0, 0), c1(0, 1));
+  }
+  // ---- voronoi_triangulation_intersection (vti.hpp:315-343; tests/test_voronoi_tri.cpp:41-67) ----
+  {
+    MA::lite::Weighted_sites dt(X, res);
+    double area = 0;
+    size_t pieces = 0;
+    std::vector<double> cell_area(N, 0.0);
+    MA::voronoi_triangulation_intersection(t, dt, [&](const MA::lite::Polygon &p, T::Face_handle, MA::lite::Weighted_sites::Vertex_handle v) {
+      area += p.area();
+      cell_area[v->info()] += p.area();
+      ++pieces;
+    });
+    printf("area_sum %.17g\npieces %zu\ncell_area0 %.17g\n", area, pieces, cell_area[0]);
+  }
+  return 0;
+}
