@@ -50,7 +50,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None:
         return _lib
-    path = path or _build.LIB_PATH
+    path = path or os.environ.get("MA_B200_LIB") or _build.LIB_PATH  # MA_B200_LIB: experiments with build variants
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(nvcc, sm_100a). There is no CPU fallback.")

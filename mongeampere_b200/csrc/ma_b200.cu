@@ -42,6 +42,8 @@ struct ma_ctx {
   int cg_maxit = 200000;
   double filter_tol = 1e-11;
   int profiling = 0, stats = 0, trace = 0;
+  int clip_a = 2, clip_b = 1, refill_at = 8;
+  int persist = 1, persist_waves = 3, persist_min_chunk = 64;  // K2 with persistent lanes (k_cells_persist)
   int strategy = 0;  // 0 auto (grid mesh: fused segment kernel, general mesh: pieces), 2: pieces always
   int part_rank = 0, part_n = 1;  // Morton tile of the Diracs this context evaluates
   long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
@@ -292,6 +294,12 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "cg_rtol") c->cg_rtol = value;
   else if (n == "cg_maxit") c->cg_maxit = (int)value;
   else if (n == "filter_tol") c->filter_tol = value;
+  else if (n == "persist") c->persist = (int)value;
+  else if (n == "clip_a") c->clip_a = std::max(1, (int)value);
+  else if (n == "clip_b") c->clip_b = std::max(1, (int)value);
+  else if (n == "refill_at") c->refill_at = std::min(32, std::max(1, (int)value));
+  else if (n == "persist_waves") c->persist_waves = std::max(1, (int)value);
+  else if (n == "persist_min_chunk") c->persist_min_chunk = std::max(32, (int)value);
   else if (n == "strategy") {
     int v = (int)value;
     if (v != 0 && v != 2) return fail(c, MA_INVALID, "strategy must be 0 (auto) or 2 (pieces)");
@@ -536,6 +544,7 @@ int fill_params(ma_ctx *c, Params &p) {
   p.nodeA = c->nodeA.as<unsigned long long>();
   p.abort_flag = c->flags.as<int>() + 1;
   p.abort_on_empty = c->abort_on_empty ? 1 : 0;
+  p.clip_a = c->clip_a; p.clip_b = c->clip_b; p.refill_at = c->refill_at;
   for (int k = 0; k < 4; ++k) p.bb[k] = c->bb[k];
   p.mesh_kind = c->mesh_kind;
   p.nF = c->nF;
@@ -562,8 +571,20 @@ constexpr int cells_maxv(int kmax) { return kmax == 16 ? 16 : (kmax == 32 ? 36 :
 
 template <int MAXV, int NT, bool POLY> int launch_cells(ma_ctx *c, const Params &p) {
   size_t sm = cells_smem_bytes<MAXV, NT>();
-  CK(cudaFuncSetAttribute(k_cells<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_cells<MAXV, NT, POLY><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
+  const int ncells = p.cell_hi - p.cell_lo;
+  if (c->persist) {
+    // persistent lanes: each warp owns `chunk` consecutive cells; about 3 waves of resident blocks
+    CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cells_persist<MAXV, NT, POLY>, NT, sm));
+    const long long warps_target = (long long)c->sm_count * std::max(per_sm, 1) * (NT / 32) * c->persist_waves;
+    int chunk = (int)std::max<long long>(c->persist_min_chunk, (ncells + warps_target - 1) / warps_target);
+    const int nwarps = std::max(1, cdiv(ncells, chunk));
+    k_cells_persist<MAXV, NT, POLY><<<cdiv(nwarps, NT / 32), NT, sm, c->stream>>>(p, chunk);
+  } else {
+    CK(cudaFuncSetAttribute(k_cells<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_cells<MAXV, NT, POLY><<<std::max(1, cdiv(ncells, NT)), NT, sm, c->stream>>>(p);
+  }
   c->launches++;
   CK(cudaGetLastError());
   return MA_OK;

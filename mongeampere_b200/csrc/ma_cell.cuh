@@ -33,6 +33,8 @@ struct Params {
   const double *wmax;
   const double *nodeG;                // 2 per node: least-squares weight gradient (ma_geom.cuh)
   const unsigned long long *nodeA;    // per node: dkey(alpha_B)
+  int refill_at;                      // k_cells_persist refills when this many lanes have finished
+  int clip_a, clip_b;                 // K2 clips when n_hold * clip_a >= n_search * clip_b (warp vote policy)
   const int *abort_flag;              // != 0: another cell is already known to be empty, stop (line search)
   int abort_on_empty;
   // mesh bounding box
@@ -79,19 +81,63 @@ struct Params {
 };
 
 // ------------------------------------------------------------------------------------------------
-// K2: power cell of Dirac i in the mesh box.  Returns n (0 = empty, -1 = capacity overflow).
+// K2: power cell of Dirac i in the mesh box, as a resumable per-lane state machine.
+//
+// The search is written as
+//     for (;;) { SEARCH, one small step at a time, until every lane holds a cutting site; CLIP; }
+// with warp votes / syncs between the steps: the lanes of a warp find their cutting sites at
+// different moments, and the compiler does not reconverge them on its own, so each step is
+// straight-line code (no break / continue / early return) and the whole warp moves from step to
+// step together.  (On the CPU emulation the votes are the identity.)
+//
+// SEARCH, phase 0: square rings of leaf bins around the Dirac's own bin.  Every lane walks the same
+// ring pattern (consecutive cells share bins), nearest bins first, so the polygon is tight after a
+// few dozen sites.  After ring r every site inside the (2r+1)^2 block has been seen, hence every
+// site within rho = distance(y_i, block boundary); the search is over when no site at distance
+// >= rho can cut, whatever its weight (global maximum weight, SURVEY §7.2 security radius).  If
+// that certificate cannot work (weights with a gradient), phase 1 takes over.
+//
+// SEARCH, phase 1: expanding-radius walk over the quadtree.  A plain nearest-first DFS degenerates
+// for a Dirac next to a high-level quadrant boundary: until the polygon is cut on every side its
+// security radius is the whole box, so nothing is pruned and the nearest quadrant is searched
+// exhaustively.  Instead the tree is walked in passes with a distance cap that doubles: a pass
+// handles exactly the sites with prev < |y_j - y_i| <= cap, and the search ends with one uncapped
+// pass (pruned by the security tests alone) once the polygon fits in the disk of radius cap/2 or a
+// whole pass went by without a cut.  Nodes inside the phase-0 block are skipped (all seen).
+// Security tests for a node B, both conservative ("no site of B can take any vertex p of the
+// polygon from i", i.e. pow_j(p) >= pow_i(p) for every j in B and every vertex p):
+//   (a) disk around y_i with the node's maximum weight;
+//   (b) the node's supporting plane (ma_geom.cuh) against every vertex.
+// (b) is what keeps the search local once the weights have a gradient: the cell then lies far from
+// its own Dirac and (a), which measures from y_i, would keep a disk of radius ~|grad w| alive.
+//
+// CellSearch holds one lane's state.  A lane is `searching()` (needs search steps), `holding()` (has
+// found a cutting site and waits for the clip) or `done()`.  Drivers: cell_build() below (one cell
+// per lane, used by k_cells and the CPU emulation) and k_cells_persist (lanes fetch new cells as
+// they finish, ma_kernels.cuh).
 // ------------------------------------------------------------------------------------------------
-template <class Poly> MA_DEV int cell_build(const Params &p, int i, Poly &P, int maxv, int *flags_out) {
-  const double xi = p.xs[i], yi = p.ys[i], wi = p.ws[i];
-  const double bx0 = p.bb[0] - xi, by0 = p.bb[1] - yi, bx1 = p.bb[2] - xi, by1 = p.bb[3] - yi;
-  if (Poly::PACK) { P.ord = 0x3210ull; P.used = 0xfu; }
-  P.X(0) = bx0; P.Y(0) = by0; P.T(0) = -1;  // bottom
-  P.X(1) = bx1; P.Y(1) = by0; P.T(1) = -2;  // right
-  P.X(2) = bx1; P.Y(2) = by1; P.T(2) = -3;  // top
-  P.X(3) = bx0; P.Y(3) = by1; P.T(3) = -4;  // left
-  int n = 4;
-  double R2 = fmax(bx0 * bx0, bx1 * bx1) + fmax(by0 * by0, by1 * by1);
-  auto lineof = [&](int tag, double &nx, double &ny, double &cl) {
+constexpr int CELL_STACK = 52;
+template <class Poly> struct CellSearch {
+  int i, n, status, phase;   // phase: 0 rings, 1 tree, 2 finished
+  double xi, yi, wi, bx0, by0, bx1, by1, R2;
+  int bx, by;                // the Dirac's own leaf bin
+  double dw_glob;            // w_i - max weight (<= 0)
+  int r, q, nq;              // ring r: next position q of nq
+  int j, jend;               // remaining sites of the current leaf bin
+  double lo2, hi2;           // only sites with lo2 < |y_j - y_i|^2 <= hi2 are looked at
+  int rdone;                 // rings 0..rdone are complete
+  int sp, pass;              // tree walk: stack pointer (the stack itself is the caller's, CELL_STACK entries)
+  double cap, prev2, cap2;
+  bool last, cut_in_pass;
+  int jc;                    // the cutting site found by the search (-1: none)
+  double cDx, cDy, cc;
+  unsigned long long cin;
+
+  MA_DEV bool searching() const { return jc < 0 && phase < 2; }
+  MA_DEV bool holding() const { return jc >= 0; }
+  MA_DEV bool done() const { return jc < 0 && phase >= 2; }
+
+  MA_DEV void lineof(const Params &p, int tag, double &nx, double &ny, double &cl) const {
     if (tag >= 0) {
       double Dx = p.xs[tag] - xi, Dy = p.ys[tag] - yi;
       nx = Dx; ny = Dy;
@@ -100,213 +146,216 @@ template <class Poly> MA_DEV int cell_build(const Params &p, int i, Poly &P, int
     else if (tag == -2) { nx = 1; ny = 0; cl = bx1; }
     else if (tag == -3) { nx = 0; ny = 1; cl = by1; }
     else { nx = 1; ny = 0; cl = bx0; }
-  };
-  const double NEG_INF = -1.0 / 0.0, POS_INF = 1.0 / 0.0;
-  // The search is written as
-  //     for (;;) { SEARCH, one small step at a time, until every lane holds a cutting site; CLIP; }
-  // with warp votes / syncs between the steps: the lanes of a warp find their cutting sites at
-  // different moments, and the compiler does not reconverge them on its own, so each step is
-  // straight-line code (no break / continue / early return) and the whole warp moves from step to
-  // step together.  (On the CPU emulation the votes are the identity.)
-  //
-  // SEARCH, phase 0: square rings of leaf bins around the Dirac's own bin.  Every lane walks the same
-  // ring pattern (consecutive cells share bins), nearest bins first, so the polygon is tight after a
-  // few dozen sites.  After ring r every site inside the (2r+1)^2 block has been seen, hence every
-  // site within rho = distance(y_i, block boundary); the search is over when no site at distance
-  // >= rho can cut, whatever its weight (global maximum weight, SURVEY §7.2 security radius).  If
-  // that certificate cannot work (weights with a gradient), phase 1 takes over.
-  //
-  // SEARCH, phase 1: expanding-radius walk over the quadtree.  A plain nearest-first DFS degenerates
-  // for a Dirac next to a high-level quadrant boundary: until the polygon is cut on every side its
-  // security radius is the whole box, so nothing is pruned and the nearest quadrant is searched
-  // exhaustively.  Instead the tree is walked in passes with a distance cap that doubles: a pass
-  // handles exactly the sites with prev < |y_j - y_i| <= cap, and the search ends with one uncapped
-  // pass (pruned by the security tests alone) once the polygon fits in the disk of radius cap/2 or a
-  // whole pass went by without a cut.  Nodes inside the phase-0 block are skipped (all seen).
-  // Security tests for a node B, both conservative ("no site of B can take any vertex p of the
-  // polygon from i", i.e. pow_j(p) >= pow_i(p) for every j in B and every vertex p):
-  //   (a) disk around y_i with the node's maximum weight;
-  //   (b) the node's supporting plane (ma_geom.cuh) against every vertex.
-  // (b) is what keeps the search local once the weights have a gradient: the cell then lies far from
-  // its own Dirac and (a), which measures from y_i, would keep a disk of radius ~|grad w| alive.
-  const int G = 1 << p.L;
-  const double pinv = 1.0 / p.ph;
-  const int bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1), by = min(max((int)((yi - p.py0) * pinv), 0), G - 1);
-  const double dw_glob = wi - p.wmax[0];  // <= 0
-  const int RMAX = 3;
-  int status = 0;
-  int phase = 0;              // 0 rings, 1 tree, 2 finished
-  if (p.abort_on_empty && *(volatile const int *)p.abort_flag) { n = 0; phase = 2; }
-  int r = 0, q = 0, nq = 1;   // ring r: next position q of nq
-  int j = 0, jend = 0;        // remaining sites of the current leaf bin
-  double lo2 = -1.0, hi2 = POS_INF;  // only sites with lo2 < |y_j - y_i|^2 <= hi2 are looked at
-  int rdone = -1;             // rings 0..rdone are complete
-  unsigned stk[52];
-  int sp = 0, pass = 0;
-  double cap = 0.0, prev2 = -1.0, cap2 = POS_INF;
-  bool last = false, cut_in_pass = true;
-  int jc = -1;                // the cutting site found by the search
-  double cDx = 0.0, cDy = 0.0, cc = 0.0;
-  unsigned long long cin = 0ull;
+  }
+
+  MA_DEV void init(const Params &p, int cell, Poly &P) {
+    i = cell;
+    xi = p.xs[i]; yi = p.ys[i]; wi = p.ws[i];
+    bx0 = p.bb[0] - xi; by0 = p.bb[1] - yi; bx1 = p.bb[2] - xi; by1 = p.bb[3] - yi;
+    if (Poly::PACK) { P.ord = 0x3210ull; P.used = 0xfu; }
+    P.X(0) = bx0; P.Y(0) = by0; P.T(0) = -1;  // bottom
+    P.X(1) = bx1; P.Y(1) = by0; P.T(1) = -2;  // right
+    P.X(2) = bx1; P.Y(2) = by1; P.T(2) = -3;  // top
+    P.X(3) = bx0; P.Y(3) = by1; P.T(3) = -4;  // left
+    n = 4;
+    R2 = fmax(bx0 * bx0, bx1 * bx1) + fmax(by0 * by0, by1 * by1);
+    const int G = 1 << p.L;
+    const double pinv = 1.0 / p.ph;
+    bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1);
+    by = min(max((int)((yi - p.py0) * pinv), 0), G - 1);
+    dw_glob = wi - p.wmax[0];
+    status = 0;
+    phase = 0;
+    if (p.abort_on_empty && *(volatile const int *)p.abort_flag) { n = 0; phase = 2; }
+    r = 0; q = 0; nq = 1;
+    j = 0; jend = 0;
+    lo2 = -1.0; hi2 = 1.0 / 0.0;
+    rdone = -1;
+    sp = 0; pass = 0;
+    cap = 0.0; prev2 = -1.0; cap2 = 1.0 / 0.0;
+    last = false; cut_in_pass = true;
+    jc = -1; cDx = cDy = cc = 0.0; cin = 0ull;
+  }
+
+  // one search step (requires searching()); straight-line code
+  MA_DEV void search_step(const Params &p, const Poly &P, unsigned *stk) {
+    const double NEG_INF = -1.0 / 0.0, POS_INF = 1.0 / 0.0;
+    const int G = 1 << p.L;
+    const int RMAX = 3;
+    if (phase == 0 && j >= jend) {
+      // ring walk: move on to the next non-empty bin of ring r (a few cheap iterations), so that the
+      // step below handles a site in (almost) every call
+      while (q < nq && j >= jend) {
+        int ox, oy;  // position q of ring r: top row, bottom row, then the two columns
+        const int side = 2 * r + 1;
+        if (q < side) { ox = q - r; oy = -r; }
+        else if (q < 2 * side) { ox = q - side - r; oy = r; }
+        else { const int t = q - 2 * side; ox = (t & 1) ? r : -r; oy = (t >> 1) - r + 1; }
+        ++q;
+        const int cx = bx + ox, cy = by + oy;
+        if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
+          const unsigned code = morton2((unsigned)cx, (unsigned)cy);
+          j = p.bin_start[code]; jend = p.bin_start[code + 1];
+        }
+      }
+    }
+    if (j < jend) {
+      // ---- step kind 1: the next site of the current bin
+      const int jj = j++;
+      const double Dx = p.xs[jj] - xi, Dy = p.ys[jj] - yi, wj = p.ws[jj];
+      const double dd2 = Dx * Dx + Dy * Dy;
+      if (jj != i && dd2 > lo2 && dd2 <= hi2) {  // else: itself / an earlier pass's / a later pass's
+        if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
+          if (wj > wi || (wj == wi && jj < i)) { n = 0; phase = 2; }
+        } else {
+          const double s = dd2 + (wi - wj);
+          if (!(s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12))) {  // else: bisector beyond every vertex
+            const double c = 0.5 * s;
+            unsigned long long in = 0ull;
+            for (int k = 0; k < n; ++k)
+              if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
+            const unsigned long long full = lowmask64(n);
+            if (in == 0ull) { n = 0; phase = 2; }
+            else if (in != full) { jc = jj; cDx = Dx; cDy = Dy; cc = c; cin = in; }
+          }
+        }
+      }
+    } else if (phase == 0) {
+      // ---- step kind 2: the next bin of the ring walk
+      if (q == nq) {  // ring r is complete
+        rdone = r;
+        // distance from y_i to the part of the block boundary that has bins behind it
+        double rho = POS_INF;
+        if (bx - r > 0) rho = fmin(rho, xi - (p.px0 + (double)(bx - r) * p.ph));
+        if (bx + r < G - 1) rho = fmin(rho, (p.px0 + (double)(bx + r + 1) * p.ph) - xi);
+        if (by - r > 0) rho = fmin(rho, yi - (p.py0 + (double)(by - r) * p.ph));
+        if (by + r < G - 1) rho = fmin(rho, (p.py0 + (double)(by + r + 1) * p.ph) - yi);
+        const double rhoc = fmax(rho, 0.0), rho2 = rhoc * rhoc, rn = rhoc + p.ph;
+        if (rho == POS_INF || cannot_cut(rho2, dw_glob, R2)) {
+          phase = 2;  // the block covers every bin / nothing farther than rho can cut
+        } else if (r == RMAX || rn * rn + dw_glob <= 0.0) {
+          // (one more ring could not certify anything if even a tiny polygon fails)
+          phase = 1;  // first tree pass: everything within rho is done
+          prev2 = rho2;
+          cap = 2.0 * fmax(rhoc, p.ph);
+          cut_in_pass = true;
+          pass = 0;
+          sp = -1;  // "begin a pass"
+        } else {
+          ++r; q = 0; nq = 8 * r;
+        }
+      }
+    } else {
+      // ---- step kind 3: the next node of the tree walk
+      if (sp <= 0) {
+        bool go = true;
+        if (sp == 0) {  // the pass is over
+          if (last || ++pass >= 64) { phase = 2; go = false; }
+          prev2 = cap2;
+          cap *= 2.0;
+        }
+        if (go && p.abort_on_empty && *(volatile const int *)p.abort_flag) { n = 0; phase = 2; go = false; }
+        if (go) {
+          last = !(4.0 * R2 > cap * cap) || !cut_in_pass;
+          cut_in_pass = false;
+          cap2 = last ? POS_INF : cap * cap;
+          lo2 = prev2; hi2 = cap2;
+          sp = 0;
+          stk[sp++] = 0u;
+        }
+      }
+      if (phase == 1) {
+        const unsigned e = stk[--sp];
+        const int l = (int)(e >> 26);
+        const unsigned code = e & 0x3ffffffu;
+        const double wm = p.wmax[(((size_t)1 << (2 * l)) - 1) / 3 + code];
+        bool alive = wm != NEG_INF;
+        {  // node inside the phase-0 block: all its sites are done
+          const int sh = p.L - l;
+          const int X0 = (int)morton_compact1(code) << sh, Y0 = (int)morton_compact1(code >> 1) << sh, W = 1 << sh;
+          if (X0 >= bx - rdone && X0 + W - 1 <= bx + rdone && Y0 >= by - rdone && Y0 + W - 1 <= by + rdone) alive = false;
+        }
+        const double S = p.ph * (double)(1u << (p.L - l));
+        const double ox = p.px0 + (double)morton_compact1(code) * S - xi;
+        const double oy = p.py0 + (double)morton_compact1(code >> 1) * S - yi;
+        const double dx = fmax(fmax(ox, -(ox + S)), 0.0), dy = fmax(fmax(oy, -(oy + S)), 0.0);
+        const double d2 = dx * dx + dy * dy;
+        if (d2 > cap2) alive = false;
+        {
+          const double fx = fmax(fabs(ox), fabs(ox + S)), fy = fmax(fabs(oy), fabs(oy + S));
+          if (fx * fx + fy * fy <= prev2) alive = false;  // every site of this node was handled by an earlier pass
+        }
+        if (alive && d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) alive = false;  // (a)
+        if (alive) {
+          const size_t node = level_offset(l) + code;
+          const double Gx = p.nodeG[2 * node], Gy = p.nodeG[2 * node + 1], al = dkey_inv(p.nodeA[node]);
+          const double hs = 0.5 * S, Zx = ox + hs, Zy = oy + hs;
+          bool can = false;
+          for (int k = 0; k < n; ++k) {  // (b) supporting plane of the node vs every vertex
+            const double ux = P.X(k), uy = P.Y(k), Px = ux - Zx, Py = uy - Zy;
+            const double pp = Px * Px + Py * Py, slop = (fabs(2.0 * Px + Gx) + fabs(2.0 * Py + Gy)) * hs;
+            const double r2 = ux * ux + uy * uy;
+            const double lb = pp + al - slop;
+            can = can || !(lb >= (r2 - wi) + 1e-10 * (pp + fabs(al) + slop + r2 + fabs(wi)));
+          }
+          alive = can;
+        }
+        if (alive) {
+          if (l < p.L) {
+            // children, nearest first (pushed in reverse)
+            const double cx = ox + 0.5 * S, cy = oy + 0.5 * S;
+            const unsigned q0 = (cx <= 0.0 ? 1u : 0u) | (cy <= 0.0 ? 2u : 0u);
+            const bool xfirst = fabs(cx) < fabs(cy);
+            const unsigned q1 = q0 ^ (xfirst ? 1u : 2u), q2 = q0 ^ (xfirst ? 2u : 1u), q3 = q0 ^ 3u;
+            const unsigned base = ((unsigned)(l + 1) << 26) | (code << 2);
+            if (sp + 4 > CELL_STACK) { status = FLAG_STACK_OVERFLOW; n = 0; phase = 2; }
+            else { stk[sp++] = base | q3; stk[sp++] = base | q2; stk[sp++] = base | q1; stk[sp++] = base | q0; }
+          } else {
+            j = p.bin_start[code]; jend = p.bin_start[code + 1];
+          }
+        }
+      }
+    }
+  }
+
+  // clip by the held site (requires holding())
+  MA_DEV void clip(const Params &p, Poly &P, int maxv) {
+    auto lo = [&](int tag, double &nx, double &ny, double &cl) { lineof(p, tag, nx, ny, cl); };
+    int n2;
+    if constexpr (Poly::PACK) n2 = clip_packed(P, n, maxv, cin, cDx, cDy, cc, jc, lo);
+    else n2 = clip_rebuild(P, n, maxv, cin, cDx, cDy, cc, jc, lo);
+    if (n2 < 0) { status = FLAG_CELL_OVERFLOW; n = 0; phase = 2; }
+    else {
+      n = n2;
+      cut_in_pass = true;
+      R2 = 0.0;
+      for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
+    }
+    jc = -1;
+  }
+};
+
+// One cell per lane.  Returns n (0 = empty, -1 = capacity overflow).
+template <class Poly> MA_DEV int cell_build(const Params &p, int i, Poly &P, int maxv, int *flags_out) {
+  CellSearch<Poly> S;
+  unsigned stk[CELL_STACK];
+  S.init(p, i, P);
   for (;;) {
     for (;;) {
       // keep searching while more lanes are searching than are holding a cutting site: both the
       // search steps and the clips then run with at least half of the unfinished lanes
-      const int n_search = MA_WARP_COUNT(jc < 0 && phase < 2), n_hold = MA_WARP_COUNT(jc >= 0);
-      if (n_search == 0 || n_hold >= n_search) break;
-      if (jc < 0 && phase < 2) {
-        if (j < jend) {
-          // ---- step kind 1: the next site of the current bin
-          const int jj = j++;
-          const double Dx = p.xs[jj] - xi, Dy = p.ys[jj] - yi, wj = p.ws[jj];
-          const double dd2 = Dx * Dx + Dy * Dy;
-          if (jj != i && dd2 > lo2 && dd2 <= hi2) {  // else: itself / an earlier pass's / a later pass's
-            if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
-              if (wj > wi || (wj == wi && jj < i)) { n = 0; phase = 2; }
-            } else {
-              const double s = dd2 + (wi - wj);
-              if (!(s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12))) {  // else: bisector beyond every vertex
-                const double c = 0.5 * s;
-                unsigned long long in = 0ull;
-                for (int k = 0; k < n; ++k)
-                  if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
-                const unsigned long long full = lowmask64(n);
-                if (in == 0ull) { n = 0; phase = 2; }
-                else if (in != full) { jc = jj; cDx = Dx; cDy = Dy; cc = c; cin = in; }
-              }
-            }
-          }
-        } else if (phase == 0) {
-          // ---- step kind 2: the next bin of the ring walk
-          if (q == nq) {  // ring r is complete
-            rdone = r;
-            // distance from y_i to the part of the block boundary that has bins behind it
-            double rho = POS_INF;
-            if (bx - r > 0) rho = fmin(rho, xi - (p.px0 + (double)(bx - r) * p.ph));
-            if (bx + r < G - 1) rho = fmin(rho, (p.px0 + (double)(bx + r + 1) * p.ph) - xi);
-            if (by - r > 0) rho = fmin(rho, yi - (p.py0 + (double)(by - r) * p.ph));
-            if (by + r < G - 1) rho = fmin(rho, (p.py0 + (double)(by + r + 1) * p.ph) - yi);
-            const double rhoc = fmax(rho, 0.0), rho2 = rhoc * rhoc, rn = rhoc + p.ph;
-            if (rho == POS_INF || cannot_cut(rho2, dw_glob, R2)) {
-              phase = 2;  // the block covers every bin / nothing farther than rho can cut
-            } else if (r == RMAX || rn * rn + dw_glob <= 0.0) {
-              // (one more ring could not certify anything if even a tiny polygon fails)
-              phase = 1;  // first tree pass: everything within rho is done
-              prev2 = rho2;
-              cap = 2.0 * fmax(rhoc, p.ph);
-              cut_in_pass = true;
-              pass = 0;
-              sp = -1;  // "begin a pass"
-            } else {
-              ++r; q = 0; nq = 8 * r;
-            }
-          } else {
-            int ox, oy;  // position q of ring r: top row, bottom row, then the two columns
-            const int side = 2 * r + 1;
-            if (q < side) { ox = q - r; oy = -r; }
-            else if (q < 2 * side) { ox = q - side - r; oy = r; }
-            else { const int t = q - 2 * side; ox = (t & 1) ? r : -r; oy = (t >> 1) - r + 1; }
-            ++q;
-            const int cx = bx + ox, cy = by + oy;
-            if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
-              const unsigned code = morton2((unsigned)cx, (unsigned)cy);
-              j = p.bin_start[code]; jend = p.bin_start[code + 1];
-            }
-          }
-        } else {
-          // ---- step kind 3: the next node of the tree walk
-          if (sp <= 0) {
-            bool go = true;
-            if (sp == 0) {  // the pass is over
-              if (last || ++pass >= 64) { phase = 2; go = false; }
-              prev2 = cap2;
-              cap *= 2.0;
-            }
-            if (go && p.abort_on_empty && *(volatile const int *)p.abort_flag) { n = 0; phase = 2; go = false; }
-            if (go) {
-              last = !(4.0 * R2 > cap * cap) || !cut_in_pass;
-              cut_in_pass = false;
-              cap2 = last ? POS_INF : cap * cap;
-              lo2 = prev2; hi2 = cap2;
-              sp = 0;
-              stk[sp++] = 0u;
-            }
-          }
-          if (phase == 1) {
-            const unsigned e = stk[--sp];
-            const int l = (int)(e >> 26);
-            const unsigned code = e & 0x3ffffffu;
-            const double wm = p.wmax[(((size_t)1 << (2 * l)) - 1) / 3 + code];
-            bool alive = wm != NEG_INF;
-            {  // node inside the phase-0 block: all its sites are done
-              const int sh = p.L - l;
-              const int X0 = (int)morton_compact1(code) << sh, Y0 = (int)morton_compact1(code >> 1) << sh, W = 1 << sh;
-              if (X0 >= bx - rdone && X0 + W - 1 <= bx + rdone && Y0 >= by - rdone && Y0 + W - 1 <= by + rdone) alive = false;
-            }
-            const double S = p.ph * (double)(1u << (p.L - l));
-            const double ox = p.px0 + (double)morton_compact1(code) * S - xi;
-            const double oy = p.py0 + (double)morton_compact1(code >> 1) * S - yi;
-            const double dx = fmax(fmax(ox, -(ox + S)), 0.0), dy = fmax(fmax(oy, -(oy + S)), 0.0);
-            const double d2 = dx * dx + dy * dy;
-            if (d2 > cap2) alive = false;
-            {
-              const double fx = fmax(fabs(ox), fabs(ox + S)), fy = fmax(fabs(oy), fabs(oy + S));
-              if (fx * fx + fy * fy <= prev2) alive = false;  // every site of this node was handled by an earlier pass
-            }
-            if (alive && d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) alive = false;  // (a)
-            if (alive) {
-              const size_t node = level_offset(l) + code;
-              const double Gx = p.nodeG[2 * node], Gy = p.nodeG[2 * node + 1], al = dkey_inv(p.nodeA[node]);
-              const double hs = 0.5 * S, Zx = ox + hs, Zy = oy + hs;
-              bool can = false;
-              for (int k = 0; k < n; ++k) {  // (b) supporting plane of the node vs every vertex
-                const double ux = P.X(k), uy = P.Y(k), Px = ux - Zx, Py = uy - Zy;
-                const double pp = Px * Px + Py * Py, slop = (fabs(2.0 * Px + Gx) + fabs(2.0 * Py + Gy)) * hs;
-                const double r2 = ux * ux + uy * uy;
-                const double lb = pp + al - slop;
-                can = can || !(lb >= (r2 - wi) + 1e-10 * (pp + fabs(al) + slop + r2 + fabs(wi)));
-              }
-              alive = can;
-            }
-            if (alive) {
-              if (l < p.L) {
-                // children, nearest first (pushed in reverse)
-                const double cx = ox + 0.5 * S, cy = oy + 0.5 * S;
-                const unsigned q0 = (cx <= 0.0 ? 1u : 0u) | (cy <= 0.0 ? 2u : 0u);
-                const bool xfirst = fabs(cx) < fabs(cy);
-                const unsigned q1 = q0 ^ (xfirst ? 1u : 2u), q2 = q0 ^ (xfirst ? 2u : 1u), q3 = q0 ^ 3u;
-                const unsigned base = ((unsigned)(l + 1) << 26) | (code << 2);
-                if (sp + 4 > 52) { status = FLAG_STACK_OVERFLOW; n = 0; phase = 2; }
-                else { stk[sp++] = base | q3; stk[sp++] = base | q2; stk[sp++] = base | q1; stk[sp++] = base | q0; }
-              } else {
-                j = p.bin_start[code]; jend = p.bin_start[code + 1];
-              }
-            }
-          }
-        }
-      }
+      const int n_search = MA_WARP_COUNT(S.searching()), n_hold = MA_WARP_COUNT(S.holding());
+      if (n_search == 0 || n_hold * p.clip_a >= n_search * p.clip_b) break;
+      if (S.searching()) S.search_step(p, P, stk);
       MA_WARP_SYNC();
     }
     // warp-uniform exit: nobody holds a site and (see the loop above) nobody is searching
-    if (!MA_WARP_ANY(jc >= 0)) break;
-    if (jc >= 0) {
-      // ---- CLIP by site jc ---------------------------------------------------------------------
-      int n2;
-      if constexpr (Poly::PACK) n2 = clip_packed(P, n, maxv, cin, cDx, cDy, cc, jc, lineof);
-      else n2 = clip_rebuild(P, n, maxv, cin, cDx, cDy, cc, jc, lineof);
-      if (n2 < 0) { status = FLAG_CELL_OVERFLOW; n = 0; phase = 2; }
-      else {
-        n = n2;
-        cut_in_pass = true;
-        R2 = 0.0;
-        for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
-      }
-      jc = -1;
-    }
+    if (!MA_WARP_ANY(S.holding())) break;
+    if (S.holding()) S.clip(p, P, maxv);
     MA_WARP_SYNC();
   }
-  if (status) { *flags_out |= status; return -1; }
-  return n;
+  if (S.status) { *flags_out |= S.status; return -1; }
+  return S.n;
 }
 
 // writes the neighbour list / bounding box of a built cell

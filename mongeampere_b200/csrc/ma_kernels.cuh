@@ -463,6 +463,78 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT) k_c
 }
 template <int MAXV, int NT> constexpr size_t cells_smem_bytes() { return (size_t)MAXV * NT * (8 + 8 + 4); }
 
+// K2 with persistent lanes: each warp owns a contiguous chunk of cells and its lanes fetch the next
+// cell of the chunk as soon as they finish one (ranks from a ballot, no atomics, so the assignment is
+// deterministic), instead of idling until the slowest cell of a fixed group of 32 is done.  Search
+// steps, clips and refills are each executed when enough lanes ask for them (warp votes).
+#ifndef MA_K2_MINBLOCKS
+#define MA_K2_MINBLOCKS 5  // 5 blocks of 128 threads per SM: <= 102 registers, 41 KB of polygons each
+#endif
+template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K2_MINBLOCKS : 1)) k_cells_persist(Params p, int chunk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sx = reinterpret_cast<double *>(smem_raw);
+  double *sy = sx + MAXV * NT;
+  int *st = reinterpret_cast<int *>(sy + MAXV * NT);
+  typedef PolyRef<NT, (MAXV <= 16)> Poly;
+  Poly P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+  const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+  const long long warp_global = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
+  long long first = (long long)p.cell_lo + warp_global * chunk;
+  int next = (int)(first < p.cell_hi ? first : p.cell_hi);                       // warp-uniform
+  const int end = (int)(first + chunk < p.cell_hi ? first + chunk : p.cell_hi);  // warp-uniform
+  CellSearch<Poly> S;
+  unsigned stk[CELL_STACK];
+  S.i = -1; S.jc = -1; S.phase = 2; S.n = 0; S.status = 0;  // "done, nothing to emit"
+  bool parked = false;  // no more cells for this lane
+  for (;;) {
+    // ---- refill: lanes whose cell is finished write it out and take the next cell of the chunk ----
+    const bool fin = !parked && S.done();
+    const unsigned finmask = __ballot_sync(0xffffffffu, fin);
+    const int n_fin = __popc(finmask);
+    const int n_busy = __popc(__ballot_sync(0xffffffffu, !parked && !S.done()));
+    if (n_fin > 0 && (n_fin >= p.refill_at || n_busy == 0)) {
+      if (fin) {
+        if (S.i >= 0) {
+          const int i = S.i;
+          int n = S.n;
+          if (S.status) { atomicOr(p.flags, S.status); n = 0; }
+          if (n == 0 && p.abort_on_empty) p.flags[1] = 1;  // an empty cell: the line search rejects this trial point
+          cell_emit(p, i, P, n);
+          if (POLY) {
+            p.poly_n[i] = n;
+            for (int k = 0; k < n; ++k) {
+              const size_t o = (size_t)k * p.N + i;
+              p.poly_x[o] = P.X(k); p.poly_y[o] = P.Y(k); p.poly_t[o] = P.T(k);
+            }
+          }
+        }
+        const int idx = next + __popc(finmask & lt_mask);
+        if (idx < end) S.init(p, idx, P);
+        else { parked = true; S.i = -1; }
+      }
+      next += n_fin;
+      __syncwarp();
+    }
+    if (__all_sync(0xffffffffu, parked)) break;
+    // ---- search: while more lanes search than hold a cutting site (and few wait for a refill) ----
+    for (;;) {
+      const bool se = !parked && S.searching();
+      const int n_search = __popc(__ballot_sync(0xffffffffu, se));
+      const int n_hold = __popc(__ballot_sync(0xffffffffu, !parked && S.holding()));
+      const int n_wait = __popc(__ballot_sync(0xffffffffu, !parked && S.done()));
+      if (n_search == 0 || n_hold * p.clip_a >= n_search * p.clip_b || n_wait >= p.refill_at) break;
+      if (se) S.search_step(p, P, stk);
+      __syncwarp();
+    }
+    // ---- clip ----
+    const bool ho = !parked && S.holding();
+    if (__any_sync(0xffffffffu, ho)) {
+      if (ho) S.clip(p, P, MAXV);
+      __syncwarp();
+    }
+  }
+}
+
 // ================================================================================================
 // K3 for grid meshes: one thread per cell integrates the cell over its boundary segments
 // (ma_seg.cuh); the polygon comes from K2 and is staged in shared memory (the chords of part B

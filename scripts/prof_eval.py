@@ -9,6 +9,9 @@ nev = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 weights = sys.argv[4] if len(sys.argv) > 4 else "zero"
 case = common.make_case(name, scale, weights)
 ctx = capi.Context(0)
+for kv in filter(None, os.environ.get("MA_OPTS", "").split(",")):  # e.g. MA_OPTS=persist=0,bin_target=2
+    k, v = kv.split("=")
+    ctx.set_option(k, float(v))
 common.load_engine(ctx, case)
 ctx.set_weights(case["w"])
 for _ in range(nev):
