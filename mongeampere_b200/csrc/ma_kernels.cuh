@@ -540,7 +540,10 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
 // (ma_seg.cuh); the polygon comes from K2 and is staged in shared memory (the chords of part B
 // revisit every vertex).
 // ================================================================================================
-template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT) k_seg(Params p) {
+#ifndef MA_K3_MINBLOCKS
+#define MA_K3_MINBLOCKS 5
+#endif
+template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K3_MINBLOCKS : 1)) k_seg(Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
   double *sy = sx + MAXV * NT;

@@ -182,21 +182,30 @@ MA_DEV unsigned long long cell_integrate_grid(const Params &p, int i, const Poly
     for (int k = k0; k <= k1; ++k) {
       double lo = 1e300, hi = -1e300;
       {
+        // a convex polygon crosses the line on (at most) two edges: find them without doing any
+        // arithmetic inside the divergent branch, then intersect both after the loop, all lanes together
         const double lev = (double)k;
         double Px = P.X(0) * inv_dx + ox, Py = P.Y(0) * inv_dy + oy;
         double gv = (fam == 0 ? Px : (fam == 1 ? Py : Px - Py)) - lev;
         double sv = fam == 0 ? Py : Px;
+        double g1a = 0, g1b = 1, s1a = 0, s1b = 0, g2a = 0, g2b = 1, s2a = 0, s2b = 0;
+        int ncross = 0;
         for (int v = 0; v < n; ++v) {
           const int vv = (v + 1 == n) ? 0 : v + 1;
           const double Qx = P.X(vv) * inv_dx + ox, Qy = P.Y(vv) * inv_dy + oy;
           const double gw = (fam == 0 ? Qx : (fam == 1 ? Qy : Qx - Qy)) - lev;
           const double sw = fam == 0 ? Qy : Qx;
-          if ((gv < 0.0) != (gw < 0.0)) {
-            const double t = gv / (gv - gw);
-            const double s = sv + t * (sw - sv);
-            lo = fmin(lo, s); hi = fmax(hi, s);
-          }
+          const bool cross = (gv < 0.0) != (gw < 0.0);
+          const bool first = cross && ncross == 0, second = cross && ncross > 0;
+          g1a = first ? gv : g1a; g1b = first ? gw : g1b; s1a = first ? sv : s1a; s1b = first ? sw : s1b;
+          g2a = second ? gv : g2a; g2b = second ? gw : g2b; s2a = second ? sv : s2a; s2b = second ? sw : s2b;
+          ncross += cross ? 1 : 0;
           gv = gw; sv = sw;
+        }
+        if (ncross >= 2) {
+          const double c1 = s1a + (g1a / (g1a - g1b)) * (s1b - s1a);
+          const double c2 = s2a + (g2a / (g2a - g2b)) * (s2b - s2a);
+          lo = fmin(c1, c2); hi = fmax(c1, c2);
         }
       }
       if (!(hi > lo)) continue;
