@@ -43,7 +43,7 @@ struct ma_ctx {
   double filter_tol = 1e-11;
   int profiling = 0, stats = 0, trace = 0;
   int clip_a = 2, clip_b = 1, refill_at = 8;
-  int persist = 1, persist_waves = 3, persist_min_chunk = 64;  // K2 with persistent lanes (k_cells_persist)
+  int persist = 1, persist_waves = 3, persist_min_chunk = 32;  // K2 with persistent lanes (k_cells_persist)
   int strategy = 0;  // 0 auto (grid mesh: fused segment kernel, general mesh: pieces), 2: pieces always
   int part_rank = 0, part_n = 1;  // Morton tile of the Diracs this context evaluates
   long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
@@ -61,7 +61,7 @@ struct ma_ctx {
   // points
   int N = 0;
   Buf x, y, xs, ys, perm, pos, code, bin_count, bin_start, wmax;
-  Buf code_s, pre0, pre1, fs_tiles, nodeG, nodeA;  // per-node supporting planes (ma_geom.cuh)
+  Buf code_s, pre0, pre1, fs_tiles, nodeG, nodeA, wstat;  // per-node supporting planes (ma_geom.cuh)
   bool abort_on_empty = false, aborted = false;
   int L = 0;
   double px0 = 0, py0 = 0, ph = 1;
@@ -262,7 +262,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
-                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n};
+                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
@@ -540,6 +540,7 @@ int fill_params(ma_ctx *c, Params &p) {
   p.L = c->L; p.px0 = c->px0; p.py0 = c->py0; p.ph = c->ph;
   p.bin_start = c->bin_start.as<int>();
   p.wmax = c->wmax.as<double>();
+  p.wstat = c->wstat.as<double>();
   p.nodeG = c->nodeG.as<double>();
   p.nodeA = c->nodeA.as<unsigned long long>();
   p.abort_flag = c->flags.as<int>() + 1;
@@ -646,6 +647,7 @@ int alloc_eval(ma_ctx *c) {
   CKR(ensure(c, c->counters, CNT_N * 8));
   CKR(ensure(c, c->flags, 16));
   CKR(ensure(c, c->red_out, 16 * sizeof(double)));
+  CKR(ensure(c, c->wstat, 4 * sizeof(double)));
   return MA_OK;
 }
 
@@ -657,6 +659,7 @@ template <bool POLY = false> int run_cells(ma_ctx *c, Params &p) {
   k_wmax_leaf<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(c->ws.as<double>(), c->bin_start.as<int>(), c->L,
                                                                c->wmax.as<double>());
   if (c->L >= 5) k_wmax_top<<<1, 1024, 0, c->stream>>>(c->L, c->wmax.as<double>());
+  CKR(reduce4(c, c->ws.as<double>(), nullptr, N, c->wstat.as<double>()));  // weight range (K2's choice of pruning disk)
   c->launches += 2 + (c->L >= 5);
   CKR(moment_scan<1>(c, c->pre1.as<double>()));
   {
@@ -763,9 +766,9 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
         if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
         const int N = c->N;
         switch (c->kmax) {
-          case 16: k_csr_fill<16><<<cdiv(N, 128), 128, 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
-          case 32: k_csr_fill<32><<<cdiv(N, 128), 128, 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
-          default: k_csr_fill<64><<<cdiv(N, 128), 128, 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+          case 16: k_csr_fill<16><<<cdiv(N, 32 * csr_wpb<16>()), 32 * csr_wpb<16>(), 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+          case 32: k_csr_fill<32><<<cdiv(N, 32 * csr_wpb<32>()), 32 * csr_wpb<32>(), 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+          default: k_csr_fill<64><<<cdiv(N, 32 * csr_wpb<64>()), 32 * csr_wpb<64>(), 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
         }
         c->launches++;
         CK(cudaGetLastError());
@@ -1150,7 +1153,12 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
   const double nu_min = nu_red[2];
 
   // f(x): evaluation + (m, g = m - nu, f - nu.x)   optimal_transport.hpp:110-120
-  auto feval = [&]() -> int {
+  double t_eval = 0, t_pcg = 0;  // wall seconds spent in evaluations / linear solves (trace only)
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  auto feval_inner = [&]() -> int {
     ++neval;
     c->abort_on_empty = neval > 1;  // every evaluation after the first is a line-search trial
     int rc_e = evaluate_mode<MODE_KANTOROVICH>(c, true);
@@ -1182,7 +1190,16 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
     fx = c->fval - x_dot_nu;
     return MA_OK;
   };
+  auto feval = [&]() -> int {
+    auto t0e = now();
+    int rc_f = feval_inner();
+    t_eval += secs(t0e, now());
+    return rc_f;
+  };
   auto finish = [&](int rc) {
+    if (c->trace)
+      fprintf(stderr, "[ma] ot_solve: niter=%zu neval=%zu cg=%zu  evaluations %.3f s, linear solves %.3f s\n", niter, neval,
+              cg_total, t_eval, t_pcg);
     if (stats) {
       stats->niter = niter; stats->neval = neval; stats->cg_iters = cg_total;
       stats->final_norm = gnorm; stats->fval = fx;
@@ -1208,8 +1225,10 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
     int it = 0;
     double relres = 0;
     // d = -solve_laplacian_matrix(h, g)   :153   (internal order)
+    auto t0p = now();
     int rc = pcg_solve(c, N, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(), c->g_s.as<double>(), -1.0,
                        ground, c->d_s.as<double>(), &it, &relres);
+    t_pcg += secs(t0p, now());
     cg_total += it;
     if (rc != MA_OK) return finish(rc);
     if (verbose && relres > 1e-7) fprintf(stderr, "WARNING: in solve_laplacian_matrix: relres=%g\n", relres);

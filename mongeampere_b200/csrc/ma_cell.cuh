@@ -31,6 +31,7 @@ struct Params {
   double px0, py0, ph;
   const int *bin_start;
   const double *wmax;
+  const double *wstat;                // {sum, sum of squares, min, max} of the weights of this evaluation
   const double *nodeG;                // 2 per node: least-squares weight gradient (ma_geom.cuh)
   const unsigned long long *nodeA;    // per node: dkey(alpha_B)
   int refill_at;                      // k_cells_persist refills when this many lanes have finished
@@ -120,6 +121,8 @@ constexpr int CELL_STACK = 52;
 template <class Poly> struct CellSearch {
   int i, n, status, phase;   // phase: 0 rings, 1 tree, 2 finished
   double xi, yi, wi, bx0, by0, bx1, by1, R2;
+  double mx, my, rc2;        // a disk (centre m, squared radius rc2, local coordinates) containing the polygon
+  bool use_m;                // weights vary enough to displace cells from their Diracs: prune with that disk
   int bx, by;                // the Dirac's own leaf bin
   double dw_glob;            // w_i - max weight (<= 0)
   int r, q, nq;              // ring r: next position q of nq
@@ -159,6 +162,12 @@ template <class Poly> struct CellSearch {
     P.X(3) = bx0; P.Y(3) = by1; P.T(3) = -4;  // left
     n = 4;
     R2 = fmax(bx0 * bx0, bx1 * bx1) + fmax(by0 * by0, by1 * by1);
+    mx = 0.5 * (bx0 + bx1); my = 0.5 * (by0 + by1);
+    rc2 = 0.25 * ((bx1 - bx0) * (bx1 - bx0) + (by1 - by0) * (by1 - by0));
+    // a cell sits about |grad w| / 2 away from its Dirac: with a weight range below (ph/2)^2 no cell
+    // leaves the neighbourhood of its own bin and the disk around y_i (R2) is the tighter bound
+    use_m = (p.wstat[3] - p.wstat[2]) > 0.25 * p.ph * p.ph;
+    if (!use_m) { mx = my = 0.0; rc2 = R2; }
     const int G = 1 << p.L;
     const double pinv = 1.0 / p.ph;
     bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1);
@@ -208,9 +217,13 @@ template <class Poly> struct CellSearch {
         if (dd2 == 0.0) {  // coincident sites: the heavier (then the earlier) one keeps the cell
           if (wj > wi || (wj == wi && jj < i)) { n = 0; phase = 2; }
         } else {
-          const double s = dd2 + (wi - wj);
-          if (!(s >= 0.0 && s * s >= 4.0 * R2 * dd2 * (1.0 + 1e-12))) {  // else: bisector beyond every vertex
-            const double c = 0.5 * s;
+          // the bisector { u.D = c } misses the disk (m, rc) that contains the polygon  =>  it cannot cut.
+          // (Measured from the polygon, not from y_i: once the weights have a gradient the cell lies far
+          // from its Dirac and a disk around y_i would reject nothing.)
+          // (use_m = false: m = 0 and rc2 = R2, the disk around y_i)
+          const double c = 0.5 * (dd2 + (wi - wj));
+          const double e = c - (mx * Dx + my * Dy);
+          if (!(e >= 0.0 && e * e >= rc2 * dd2 * (1.0 + 1e-12))) {
             unsigned long long in = 0ull;
             for (int k = 0; k < n; ++k)
               if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
@@ -233,8 +246,10 @@ template <class Poly> struct CellSearch {
         const double rhoc = fmax(rho, 0.0), rho2 = rhoc * rhoc, rn = rhoc + p.ph;
         if (rho == POS_INF || cannot_cut(rho2, dw_glob, R2)) {
           phase = 2;  // the block covers every bin / nothing farther than rho can cut
-        } else if (r == RMAX || rn * rn + dw_glob <= 0.0) {
-          // (one more ring could not certify anything if even a tiny polygon fails)
+        } else if (r == RMAX || (r >= 1 && rn * rn + dw_glob <= 0.0)) {
+          // (one more ring could not certify anything if even a tiny polygon fails; ring 1 is always
+          // walked: the true neighbours are the nearby Diracs whatever the weights do, and the rings
+          // are the cheap way to find them)
           phase = 1;  // first tree pass: everything within rho is done
           prev2 = rho2;
           cap = 2.0 * fmax(rhoc, p.ph);
@@ -254,9 +269,10 @@ template <class Poly> struct CellSearch {
           prev2 = cap2;
           cap *= 2.0;
         }
-        if (go && p.abort_on_empty && *(volatile const int *)p.abort_flag) { n = 0; phase = 2; go = false; }
         if (go) {
-          last = !(4.0 * R2 > cap * cap) || !cut_in_pass;
+          // (rc2 = R2 unless the weights displace the cells: then the polygon's own radius is what says
+          // whether it is already small compared with the distances this pass looks at)
+          last = !(4.0 * rc2 > cap * cap) || !cut_in_pass;
           cut_in_pass = false;
           cap2 = last ? POS_INF : cap * cap;
           lo2 = prev2; hi2 = cap2;
@@ -286,6 +302,15 @@ template <class Poly> struct CellSearch {
           if (fx * fx + fy * fy <= prev2) alive = false;  // every site of this node was handled by an earlier pass
         }
         if (alive && d2 > 0.0 && cannot_cut(d2, wi - wm, R2)) alive = false;  // (a)
+        if (alive) {
+          // (a') the same with the disk (m, rc) around the polygon: for every site j of the node
+          //   c_j - m.D_j = |D_j - m|^2/2 - |m|^2/2 + (w_i - w_j)/2 >= dist(m, node)^2/2 - |m|^2/2 + (w_i - wm)/2
+          // and |D_j| <= far corner distance, so no bisector reaches the disk if that bound >= rc * far
+          const double qx = fmax(fmax(ox - mx, mx - (ox + S)), 0.0), qy = fmax(fmax(oy - my, my - (oy + S)), 0.0);
+          const double emin = 0.5 * ((qx * qx + qy * qy) - (mx * mx + my * my) + (wi - wm));
+          const double fx = fmax(fabs(ox), fabs(ox + S)), fy = fmax(fabs(oy), fabs(oy + S));
+          if (emin > 0.0 && emin * emin >= rc2 * (fx * fx + fy * fy) * (1.0 + 1e-9)) alive = false;
+        }
         if (alive) {
           const size_t node = level_offset(l) + code;
           const double Gx = p.nodeG[2 * node], Gy = p.nodeG[2 * node + 1], al = dkey_inv(p.nodeA[node]);
@@ -330,6 +355,21 @@ template <class Poly> struct CellSearch {
       cut_in_pass = true;
       R2 = 0.0;
       for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
+      if (use_m) {  // bounding-box centre, exact radius about it
+        double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+        for (int k = 0; k < n; ++k) {
+          const double vx = P.X(k), vy = P.Y(k);
+          x0 = fmin(x0, vx); x1 = fmax(x1, vx); y0 = fmin(y0, vy); y1 = fmax(y1, vy);
+        }
+        mx = 0.5 * (x0 + x1); my = 0.5 * (y0 + y1);
+        rc2 = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double ax = P.X(k) - mx, ay = P.Y(k) - my;
+          rc2 = fmax(rc2, ax * ax + ay * ay);
+        }
+      } else {
+        rc2 = R2;
+      }
     }
     jc = -1;
   }

@@ -692,35 +692,74 @@ template <int KMAX, int MAXV, int MODE> __global__ void __launch_bounds__(PIECES
 // K4: CSR fill (internal Morton order).  Row i = { (nbr slot s, -hslot) : touched } ∪ { (i, Σ hslot) },
 // columns ascending (what Eigen's setFromTriplets yields per row, kantorovich.hpp:120-121,137-139).
 // ================================================================================================
+// One warp per 32 consecutive rows: the rows' slot tables (hslot, nbr) are read with fully coalesced
+// loads into shared memory (row stride KMAX + 1: conflict-free column access), each lane then sorts
+// its row and the sorted rows are staged in shared memory again so that the warp writes the whole
+// contiguous range [rowptr[first row], rowptr[last row + 1]) with coalesced stores.
+template <int KMAX> constexpr int csr_wpb() { return KMAX <= 16 ? 4 : (KMAX <= 32 ? 2 : 1); }  // warps per block (48 KB of static shared memory)
 template <int KMAX>
-__global__ void k_csr_fill(int N, const int *__restrict__ nbr, const double *__restrict__ hslot,
-                           const unsigned long long *__restrict__ touched, const int *__restrict__ rowptr,
-                           int *__restrict__ col, double *__restrict__ val) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  unsigned long long t = touched[i];
-  if (!t) return;
-  int c[KMAX + 1];
-  double v[KMAX + 1];
-  int n = 0;
-  double diag = 0.0;
-  for (int s = 0; s < KMAX; ++s)
-    if ((t >> s) & 1ull) {
-      double h = hslot[(size_t)i * KMAX + s];
-      int j = nbr[(size_t)i * KMAX + s];
-      diag += h;
-      // insertion into the sorted prefix
-      int q = n++;
-      while (q > 0 && c[q - 1] > j) { c[q] = c[q - 1]; v[q] = v[q - 1]; --q; }
-      c[q] = j; v[q] = -h;
-    }
+__global__ void __launch_bounds__(csr_wpb<KMAX>() * 32) k_csr_fill(int N, const int *__restrict__ nbr, const double *__restrict__ hslot,
+                                                          const unsigned long long *__restrict__ touched,
+                                                          const int *__restrict__ rowptr, int *__restrict__ col,
+                                                          double *__restrict__ val) {
+  constexpr int LD = KMAX + 1, CSR_WPB = csr_wpb<KMAX>();
+  __shared__ double sh_h[CSR_WPB][32 * LD];
+  __shared__ int sh_j[CSR_WPB][32 * LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * CSR_WPB + warp) * 32;
+  if (row0 >= N) return;  // warp-uniform
+  const int nrows = min(32, N - row0);
+  double *H = sh_h[warp];
+  int *J = sh_j[warp];
   {
-    int q = n++;
-    while (q > 0 && c[q - 1] > i) { c[q] = c[q - 1]; v[q] = v[q - 1]; --q; }
-    c[q] = i; v[q] = diag;
+    const size_t base = (size_t)row0 * KMAX;
+    const int cnt = nrows * KMAX;
+    for (int q = lane; q < cnt; q += 32) {
+      const int r = q / KMAX, s = q - r * KMAX;
+      H[r * LD + s] = hslot[base + q];
+      J[r * LD + s] = nbr[base + q];
+    }
   }
-  int o = rowptr[i];
-  for (int q = 0; q < n; ++q) { col[o + q] = c[q]; val[o + q] = v[q]; }
+  __syncwarp();
+  const int i = row0 + lane;
+  const bool live = lane < nrows;
+  const unsigned long long t = live ? touched[i] : 0ull;
+  const int o0 = rowptr[row0], o1 = rowptr[row0 + nrows];
+  // each lane compacts + sorts its row in place (columns ascending, diagonal included)
+  int n = 0;
+  if (t) {
+    double diag = 0.0;
+    for (int s = 0; s < KMAX; ++s)
+      if ((t >> s) & 1ull) {
+        const double h = H[lane * LD + s];
+        const int j = J[lane * LD + s];
+        diag += h;
+        int q = n++;  // insertion into the sorted prefix (q <= s, so unread slots are never overwritten)
+        while (q > 0 && J[lane * LD + q - 1] > j) { J[lane * LD + q] = J[lane * LD + q - 1]; H[lane * LD + q] = H[lane * LD + q - 1]; --q; }
+        J[lane * LD + q] = j; H[lane * LD + q] = -h;
+      }
+    int q = n++;
+    while (q > 0 && J[lane * LD + q - 1] > i) { J[lane * LD + q] = J[lane * LD + q - 1]; H[lane * LD + q] = H[lane * LD + q - 1]; --q; }
+    J[lane * LD + q] = i; H[lane * LD + q] = diag;
+  }
+  __syncwarp();
+  // coalesced write of the warp's contiguous output range: entry e belongs to the LAST row whose
+  // start is <= e (empty rows share their start with the row after them); lanes find it by counting
+  // row starts broadcast with shuffles
+  const int total = o1 - o0;
+  const int my_start = live ? rowptr[i] - o0 : 0x7fffffff;
+  for (int e0 = 0; e0 < total; e0 += 32) {
+    const int e = e0 + lane;
+    int r = -1;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) r += (__shfl_sync(0xffffffffu, my_start, rr) <= e) ? 1 : 0;
+    r = max(r, 0);
+    const int rs = __shfl_sync(0xffffffffu, my_start, r);
+    if (e < total) {
+      col[o0 + e] = J[r * LD + (e - rs)];
+      val[o0 + e] = H[r * LD + (e - rs)];
+    }
+  }
 }
 
 // caller-order views -----------------------------------------------------------------------------

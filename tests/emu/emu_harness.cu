@@ -158,6 +158,9 @@ extern "C" int emu_eval(int mesh_kind,
   p.N = N; p.xs = xs.data(); p.ys = ys.data(); p.ws = ws.data();
   p.cell_lo = 0; p.cell_hi = N;
   p.bin_start = bin_start.data(); p.wmax = wmax.data();
+  double wstat[4] = {0, 0, 1e300, -1e300};
+  for (int k = 0; k < N; ++k) { wstat[0] += ws[k]; wstat[1] += ws[k] * ws[k]; wstat[2] = std::min(wstat[2], ws[k]); wstat[3] = std::max(wstat[3], ws[k]); }
+  p.wstat = wstat;
   // ---- outputs ----
   std::vector<double> cell_bb((size_t)4 * N);
   std::vector<unsigned long long> cnt(CNT_N, 0);

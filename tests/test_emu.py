@@ -105,3 +105,48 @@ def test_capacity_overflow_is_flagged(emu_mod):
     assert r["flags"] != 0
     r = emu_mod.evaluate(dict(kind="mesh", vx=vx, vy=vy, tri=tri, abc=abc), X, np.zeros(len(X)), kmax=64, maxv_piece=70)
     assert r["flags"] == 0 and abs(r["g"].sum() - 1) < 1e-14 and len(r["adjacency"][0]) == 40
+
+
+@pytest.mark.parametrize("name,scale,kind", [("c2", 0.02, "lin"), ("c2", 0.02, "quad"), ("c1", 0.2, "bump")])
+@pytest.mark.parametrize("seg", [False, True])
+def test_weights_with_a_gradient(oracle_mod, emu_mod, name, scale, kind, seg):
+    """Weights with a strong gradient displace every cell far from its Dirac (and hide some Diracs):
+    K2 then leaves the ring walk for the quadtree walk with per-node supporting planes, and prunes with
+    the disk around the polygon instead of the one around y_i."""
+    case = common.make_case(name, scale, "0.2")
+    X = case["X"]
+    if kind == "lin":
+        w = case["w"] + 0.3 * X[:, 0] - 0.1 * X[:, 1]
+    elif kind == "quad":
+        w = case["w"] + 0.25 * (X ** 2).sum(1)
+    else:
+        w = case["w"] + 0.05 * np.exp(-((X - X.mean(0)) ** 2).sum(1) / 0.1)
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(w)
+    assert (g0 == 0).sum() > 50  # hidden Diracs (trap T2)
+    r = emu_mod.evaluate(case["emu_mesh"], X, w, seg=seg)
+    assert r["flags"] == 0
+    assert abs(r["f"] - f0) <= 1e-10 * abs(f0)
+    assert np.abs(r["g"] - g0).max() <= 1e-10 * np.abs(g0).max()
+    assert common.same_pattern(H0, r["H"])
+    # the oracle follows the reference's global-coordinate constructions: good to ~2e-10 of the row diagonal here
+    assert common.hessian_rel_err(H0, r["H"]) <= 5e-10
+
+
+@pytest.mark.parametrize("name,scale,weights", [("c2", 0.004, "0.5"), ("c3", 0.0005, "0.3"), ("c4", 0.004, "0.3")])
+def test_boundary_segment_path_matches_oracle(oracle_mod, emu_mod, name, scale, weights):
+    """ma_seg.cuh (what k_seg runs on grid meshes): kantorovich and both moment orders."""
+    case = common.make_case(name, scale, weights)
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(case["w"])
+    r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], seg=True)
+    assert r["flags"] == 0
+    assert abs(r["f"] - f0) <= 1e-10 * abs(f0)
+    assert np.abs(r["g"] - g0).max() <= 1e-10 * np.abs(g0).max()
+    assert common.same_pattern(H0, r["H"])
+    assert common.hessian_rel_err(H0, r["H"]) <= 1e-10
+    for order in (1, 2):
+        ref = orc.moments(case["w"], order)
+        m = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], seg=True, mode=order)["mom"]
+        k = 3 if order == 1 else 6
+        assert np.abs(m[:, :k] - ref[:, :k]).max() <= 1e-10 * np.abs(ref[:, :k]).max()
