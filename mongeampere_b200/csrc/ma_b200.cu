@@ -52,7 +52,7 @@ struct ma_ctx {
   int mesh_kind = MESH_NONE;
   int nV = 0, nF = 0;
   double bb[4] = {0, 0, 0, 0};
-  Buf vx, vy, tri, abc, tbin_ptr, tbin_face;
+  Buf vx, vy, tri, abc, rho_v, tbin_ptr, tbin_face;
   int tg = 1;
   double tinvx = 1, tinvy = 1;
   int gn = 0, gm = 0;
@@ -262,7 +262,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
-                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat};
+                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
@@ -449,6 +449,7 @@ extern "C" int ma_set_grid(ma_ctx *c, int n, int m, double x0, double y0, double
   c->bb[0] = x0; c->bb[1] = y0;
   c->bb[2] = x0 + (n - 1) * dx; c->bb[3] = y0 + (m - 1) * dy;
   CKR(upload(c, c->abc, abc.data(), abc.size() * 8));
+  CKR(upload(c, c->rho_v, rho_v, (size_t)n * m * 8));
   CK(cudaStreamSynchronize(c->stream));
   invalidate_eval(c);
   return MA_OK;
@@ -550,6 +551,7 @@ int fill_params(ma_ctx *c, Params &p) {
   p.mesh_kind = c->mesh_kind;
   p.nF = c->nF;
   p.abc = c->abc.as<double>();
+  p.rho_v = c->rho_v.as<double>();
   p.gn = c->gn; p.gm = c->gm; p.gx0 = c->gx0; p.gy0 = c->gy0; p.gdx = c->gdx; p.gdy = c->gdy;
   p.vx = c->vx.as<double>(); p.vy = c->vy.as<double>(); p.tri = c->tri.as<int>();
   p.tg = c->tg; p.tinvx = c->tinvx; p.tinvy = c->tinvy;

@@ -44,6 +44,7 @@ struct Params {
   int mesh_kind;
   int nF;
   const double *abc;
+  const double *rho_v;  // grid mesh: density at vertex (i, j) = rho_v[i * gm + j] (L2-resident: 8 B/vertex vs 24 B/face)
   // grid mesh
   int gn, gm;
   double gx0, gy0, gdx, gdy;

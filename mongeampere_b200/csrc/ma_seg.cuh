@@ -103,7 +103,7 @@ MA_DEV unsigned long long cell_integrate_grid(const Params &p, int i, const Poly
   const double xi = p.xs[i], yi = p.ys[i];
   const double inv_dx = 1.0 / p.gdx, inv_dy = 1.0 / p.gdy;
   const double ox = (xi - p.gx0) * inv_dx, oy = (yi - p.gy0) * inv_dy;  // grid coordinate f = u * inv + o
-  const int gn2 = p.gn - 2, gm2 = p.gm - 2, rowf = p.gm - 1;
+  const int gn2 = p.gn - 2, gm2 = p.gm - 2;
   acc.mass = acc.cost = 0.0;
 #pragma unroll
   for (int q = 0; q < 5; ++q) acc.m[q] = 0.0;
@@ -140,9 +140,13 @@ MA_DEV unsigned long long cell_integrate_grid(const Params &p, int i, const Poly
         const double tm = 0.5 * (tc + t1);
         const double fmx = fAx + tm * sx, fmy = fAy + tm * sy;
         const int si = seg_clampi((int)floor(fmx), 0, gn2), sj = seg_clampi((int)floor(fmy), 0, gm2);
-        const int f = 2 * (si * rowf + sj) + (((fmx - (double)si) < (fmy - (double)sj)) ? 1 : 0);
-        const double a = p.abc[3 * (size_t)f], b = p.abc[3 * (size_t)f + 1], c0 = p.abc[3 * (size_t)f + 2];
-        const double r = c0 + a * xi + b * yi;
+        const bool upper = (fmx - (double)si) < (fmy - (double)sj);  // face 1 of the square (above the diagonal)
+        // the face's plane from its three vertex densities: a, b and the value r at y_i
+        const double *rv = p.rho_v + (size_t)si * p.gm + sj;
+        const double r00 = rv[0], r11 = rv[p.gm + 1], rmid = upper ? rv[1] : rv[p.gm];  // r01 or r10
+        const double a = (upper ? (r11 - rmid) : (rmid - r00)) * inv_dx;
+        const double b = (upper ? (rmid - r00) : (r11 - rmid)) * inv_dy;
+        const double r = r00 - a * (((double)si - ox) * p.gdx) - b * (((double)sj - oy) * p.gdy);
         const double dt = t1 - tc;
         seg_item_cell<MODE>(cx, cy, ex, ey, a, b, r, hL * dt, acc);
         if (MODE == MODE_KANTOROVICH) E += dt * (a * (0.5 * (cx + ex)) + b * (0.5 * (cy + ey)) + r);
@@ -224,21 +228,21 @@ MA_DEV unsigned long long cell_integrate_grid(const Params &p, int i, const Poly
         if (!(s1 > s0)) continue;
         double ax, ay, bx, by, kappa, len;
         if (fam == 0) {  // vertical edge (k,mm)-(k,mm+1): left = face 0 of square (k-1,mm), right = face 1 of (k,mm)
-          const int fl = 2 * ((k - 1) * rowf + mm), fr = 2 * (k * rowf + mm) + 1;
-          kappa = p.abc[3 * (size_t)fl] - p.abc[3 * (size_t)fr];
+          const double *rv = p.rho_v + (size_t)k * p.gm + mm;  // a_left - a_right
+          kappa = ((rv[0] - rv[-p.gm]) - (rv[p.gm + 1] - rv[1])) * inv_dx;
           ax = bx = hcoef;
           ay = (s0 - oy) * p.gdy; by = (s1 - oy) * p.gdy;
           len = (s1 - s0) * p.gdy;
         } else if (fam == 1) {  // horizontal edge (mm,k)-(mm+1,k): below = face 1 of square (mm,k-1), above = face 0 of (mm,k)
-          const int fb = 2 * (mm * rowf + k - 1) + 1, ft = 2 * (mm * rowf + k);
-          kappa = p.abc[3 * (size_t)fb + 1] - p.abc[3 * (size_t)ft + 1];
+          const double *rv = p.rho_v + (size_t)mm * p.gm + k;  // b_below - b_above
+          kappa = ((rv[0] - rv[-1]) - (rv[p.gm + 1] - rv[p.gm])) * inv_dy;
           ay = by = hcoef;
           ax = (s0 - ox) * p.gdx; bx = (s1 - ox) * p.gdx;
           len = (s1 - s0) * p.gdx;
         } else {  // diagonal of square (mm, mm-k): n points to face 0 (lower right), so T1 = face 1
-          const int f0 = 2 * (mm * rowf + (mm - k));
-          const double *q0 = p.abc + 3 * (size_t)f0;
-          kappa = ((q0[3] - q0[0]) * inv_dx - (q0[4] - q0[1]) * inv_dy) * ninv;
+          const double *rv = p.rho_v + (size_t)mm * p.gm + (mm - k);
+          // n.(grad rho_1 - grad rho_0) = (r00 + r11 - r01 - r10) (1/dx^2 + 1/dy^2) / |(1/dx, -1/dy)|
+          kappa = ((rv[0] + rv[p.gm + 1]) - (rv[1] + rv[p.gm])) * (inv_dx * inv_dx + inv_dy * inv_dy) * ninv;
           ax = (s0 - ox) * p.gdx; bx = (s1 - ox) * p.gdx;
           ay = ((s0 - (double)k) - oy) * p.gdy; by = ((s1 - (double)k) - oy) * p.gdy;
           len = (s1 - s0) * ddiag;

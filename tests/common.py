@@ -19,7 +19,7 @@ def make_case(name, scale, weights="zero", seed=0):
         cell = ext * ext / N
         w = np.random.default_rng(seed).normal(0.0, float(weights) * cell, N)
     if cfg["kind"] == "grid":
-        emu_mesh = dict(kind="grid", n=cfg["n"], m=cfg["m"], abc=abc)
+        emu_mesh = dict(kind="grid", n=cfg["n"], m=cfg["m"], abc=abc, rho=cfg["rho"])
     else:
         emu_mesh = dict(kind="mesh", vx=cfg["vx"], vy=cfg["vy"], tri=cfg["tri"], abc=abc)
     return dict(cfg=cfg, abc=abc, X=X, w=w, emu_mesh=emu_mesh, N=N)

@@ -57,7 +57,10 @@ def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_t
                  len(vx), vx.ctypes.data_as(C.c_void_p), vy.ctypes.data_as(C.c_void_p), len(tri) // 3,
                  tri.ctypes.data_as(C.c_void_p))
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib().emu_eval(*gargs, p(abc), N, p(x), p(y), p(w), kmax, maxv_piece, mode, C.c_double(filter_tol),
+    rho = np.ascontiguousarray(mesh["rho"], np.float64).reshape(-1) if mesh.get("rho") is not None else None
+    if seg and mesh["kind"] == "grid":
+        assert rho is not None, "the segment path reads the vertex densities"
+    rc = lib().emu_eval(*gargs, p(abc), p(rho) if rho is not None else None, N, p(x), p(y), p(w), kmax, maxv_piece, mode, C.c_double(filter_tol),
                         bin_target, nlanes, int(bool(seg) and mesh["kind"] == "grid"), p(perm), p(mass), p(fcell), p(nbr_cnt), p(nbr), p(hslot), p(touched),
                         p(mom), p(counters), C.byref(flags))
     assert rc == 0

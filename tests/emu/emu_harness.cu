@@ -22,7 +22,7 @@ extern "C" int emu_eval(int mesh_kind,
                         // general mesh
                         int nV, const double *vx, const double *vy, int nF, const int *tri,
                         // densities
-                        const double *abc,
+                        const double *abc, const double *rho_v,
                         // Diracs
                         int N, const double *x, const double *y, const double *w,
                         // knobs
@@ -35,6 +35,7 @@ extern "C" int emu_eval(int mesh_kind,
   // ---- mesh ----
   p.mesh_kind = mesh_kind;
   p.abc = abc;
+  p.rho_v = rho_v;
   std::vector<int> tbin_ptr, tbin_face;
   if (mesh_kind == MESH_GRID) {
     p.gn = gn; p.gm = gm; p.gx0 = gx0; p.gy0 = gy0; p.gdx = gdx; p.gdy = gdy;
