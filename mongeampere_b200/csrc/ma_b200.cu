@@ -80,12 +80,16 @@ struct ma_ctx {
   int pc_np = 0, pc_nv = 0;
 
   // pcg
-  Buf dinv, cgx, cgr, cgz, cgp0, cgp1, cgq, part_pq, part_rz, part_rr, scal, cgflag;
+  Buf dinv, cgx, cgr, cgz, cgp0, cgp1, cgq, cgw1, cgpp, part_pq, part_rz, part_rr, scal, cgflag, cgbar;
+  int cg_single = 0;  // 1: single-reduction CG (one kernel per iteration); measured no faster than the two-kernel PCG (the time is in the kernels, not the launches)
+  int pcg_persist = 0, pcg_blocks_per_sm = 4;  // persistent cooperative PCG: measured slower than the graph of 2-kernel iterations (grid barriers cost more than launches)
   Buf nu_s, x0_s, d_s, g_s;
   size_t last_cg_iters = 0;
 
   // L2 flush
   Buf flush;
+  // pinned host staging for the scalars read back every evaluation (pageable copies are staged and slow)
+  struct HostScalars { int flags, abort_, nnz, pad; double red[8]; } *hs = nullptr;
 
   // timing
   cudaEvent_t ev[MA_T_COUNT + 2] = {};
@@ -118,12 +122,14 @@ int fail(ma_ctx *c, int code, const char *fmt, ...) {
     if (r_ != MA_OK) return r_;       \
   } while (0)
 
-int ensure(ma_ctx *c, Buf &b, size_t bytes) {
+// (re)allocates; `headroom` > 1 over-allocates when growing, for buffers whose size drifts from call to call
+// (cudaFree / cudaMalloc synchronise the device and take milliseconds)
+int ensure(ma_ctx *c, Buf &b, size_t bytes, double headroom = 1.0) {
   if (bytes <= b.cap && b.p) return MA_OK;
   if (b.p) CK(cudaFree(b.p));
   b.p = nullptr;
   b.cap = 0;
-  size_t want = std::max<size_t>(bytes, 256);
+  size_t want = std::max<size_t>((size_t)(bytes * headroom), 256);
   CK(cudaMalloc(&b.p, want));
   b.cap = want;
   return MA_OK;
@@ -244,6 +250,7 @@ extern "C" int ma_create(ma_ctx **out, int device) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  CK(cudaHostAlloc((void **)&c->hs, sizeof(*c->hs), cudaHostAllocDefault));
   for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
   for (auto &ev : c->ev_user) CK(cudaEventCreate(&ev));
   return MA_OK;
@@ -262,13 +269,14 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
-                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v};
+                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->cgbar, &c->cgw1, &c->cgpp};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_user)
       if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
+    if (c->hs) cudaFreeHost(c->hs);
   }
   delete c;
 }
@@ -293,6 +301,9 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   } else if (n == "bin_target") c->bin_target = std::max(1, (int)value);
   else if (n == "cg_rtol") c->cg_rtol = value;
   else if (n == "cg_maxit") c->cg_maxit = (int)value;
+  else if (n == "pcg_persist") c->pcg_persist = (int)value;
+  else if (n == "cg_single") c->cg_single = (int)value;
+  else if (n == "pcg_blocks_per_sm") c->pcg_blocks_per_sm = std::max(1, (int)value);
   else if (n == "filter_tol") c->filter_tol = value;
   else if (n == "persist") c->persist = (int)value;
   else if (n == "clip_a") c->clip_a = std::max(1, (int)value);
@@ -718,10 +729,9 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     if (c->abort_on_empty) {
       // line-search trial: an empty cell means min m = 0 < eps0, the point is rejected whatever the
       // rest of the evaluation says (optimal_transport.hpp:167), so stop here
-      int h_abort = 0;
-      CK(cudaMemcpyAsync(&h_abort, c->flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(&c->hs->abort_, c->flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
-      if (h_abort) {
+      if (c->hs->abort_) {
         c->aborted = true;
         c->mass_min = 0.0;
         invalidate_eval(c);
@@ -737,16 +747,16 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       CKR(reduce4(c, c->fcell.as<double>() + lo, nullptr, nloc, c->red_out.as<double>()));
       CKR(reduce4(c, c->mass.as<double>() + lo, nullptr, nloc, c->red_out.as<double>() + 4));
     }
-    int h_flags = 0;
-    double red[8] = {0};
-    int h_nnz = 0;
-    CK(cudaMemcpyAsync(&h_flags, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->hs->flags = 0; c->hs->nnz = 0;
+    CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
     if (MODE == MODE_KANTOROVICH) {
-      CK(cudaMemcpyAsync(red, c->red_out.p, sizeof red, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(c->hs->red, c->red_out.p, sizeof c->hs->red, cudaMemcpyDeviceToHost, c->stream));
       if (with_hessian)
-        CK(cudaMemcpyAsync(&h_nnz, c->rowptr.as<int>() + c->N, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&c->hs->nnz, c->rowptr.as<int>() + c->N, 4, cudaMemcpyDeviceToHost, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
+    const int h_flags = c->hs->flags, h_nnz = c->hs->nnz;
+    const double *red = c->hs->red;
     if (h_flags & (FLAG_CELL_OVERFLOW | FLAG_PIECE_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
       if (c->trace) fprintf(stderr, "[ma] eval kmax=%d overflow flags=%d\n", c->kmax, h_flags);
       if (c->kmax >= 64) {
@@ -763,8 +773,8 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       c->mass_min = red[6];
       if (with_hessian) {
         c->nnz = h_nnz;
-        CKR(ensure(c, c->col, (size_t)std::max(h_nnz, 1) * 4));
-        CKR(ensure(c, c->val, (size_t)std::max(h_nnz, 1) * 8));
+        CKR(ensure(c, c->col, (size_t)std::max(h_nnz, 1) * 4, 1.3));
+        CKR(ensure(c, c->val, (size_t)std::max(h_nnz, 1) * 8, 1.3));
         if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
         const int N = c->N;
         switch (c->kmax) {
@@ -1028,14 +1038,83 @@ extern "C" int ma_pieces_get(ma_ctx *c, int *cell, int *face, int *ptr, int *tag
 namespace {
 
 // Solve H d = sign * g on the device (internal order), grounded at `ground`.  d_out may alias nothing.
+// single-reduction CG, one kernel per iteration (ma_pcg.cuh)
+int cg1_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double *val, const double *g, double sign,
+              int ground, double *d_out, int *iters_out, double *relres_out) {
+  Cg1State s;
+  const int nblocks = std::min(PCG_MAX_BLOCKS, std::max(1, cdiv(n, PCG_NT)));
+  Buf *vecs[] = {&c->dinv, &c->cgx, &c->cgr, &c->cgz, &c->cgp0, &c->cgp1, &c->cgq, &c->cgw1, &c->cgpp};
+  for (Buf *b : vecs) CKR(ensure(c, *b, (size_t)n * 8));
+  CKR(ensure(c, c->part_pq, (size_t)6 * nblocks * 8)); CKR(ensure(c, c->scal, 64)); CKR(ensure(c, c->cgflag, 16));
+  s.n = n; s.ground = ground; s.nblocks = nblocks; s.rowptr = rowptr; s.col = col; s.val = val;
+  s.dinv = c->dinv.as<double>(); s.x = c->cgx.as<double>(); s.p = c->cgpp.as<double>();
+  s.r[0] = c->cgr.as<double>(); s.r[1] = c->cgz.as<double>();
+  s.s[0] = c->cgp0.as<double>(); s.s[1] = c->cgp1.as<double>();
+  s.w[0] = c->cgq.as<double>(); s.w[1] = c->cgw1.as<double>();
+  s.part = c->part_pq.as<double>(); s.scal = c->scal.as<double>();
+  CK(cudaMemsetAsync(c->cgflag.p, 0, 16, c->stream));
+  CK(cudaMemsetAsync(c->scal.p, 0, 64, c->stream));
+  k_cg1_init<<<nblocks, PCG_NT, 0, c->stream>>>(s, g, sign, c->cgflag.as<int>(), c->dinv.as<double>());
+  k_cg1_init2<<<nblocks, PCG_NT, 0, c->stream>>>(s);
+  k_cg1_rr<<<1, PCG_NT, 0, c->stream>>>(s, 0, 4);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&c->hs->red[0], c->scal.as<double>() + 4, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&c->hs->flags, c->cgflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->hs->flags & 1) {
+    fail(c, MA_SINGULAR_HESSIAN, "Error: hessian of Kantorovich's functional is not invertible (zero diagonal)");
+    return MA_SINGULAR_HESSIAN;
+  }
+  const double gg = c->hs->red[0];
+  int it = 0;
+  double rr = gg;
+  if (gg > 0) {
+    const int batch = 64;  // even, so the buffer parity is the same at every graph launch
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    // k only enters through its parity and through "k > 0"; iteration 0 of the solve needs k = 0, which the
+    // zero-initialised scalars emulate: gamma_prev = 0 => beta = 0, and 0 * gamma / alpha_prev is made finite below
+    for (int b = 0; b < batch; ++b) k_cg1_iter<<<nblocks, PCG_NT, 0, c->stream>>>(s, b + 2);
+    k_cg1_rr<<<1, PCG_NT, 0, c->stream>>>(s, 0, 5);
+    CK(cudaStreamEndCapture(c->stream, &graph));
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    // the very first iteration runs outside the graph with k = 0, then one more to restore even parity
+    k_cg1_iter<<<nblocks, PCG_NT, 0, c->stream>>>(s, 0);
+    k_cg1_iter<<<nblocks, PCG_NT, 0, c->stream>>>(s, 1);
+    c->launches += 2;
+    it = 2;
+    const double tol2 = c->cg_rtol * c->cg_rtol * gg;
+    while (it < c->cg_maxit) {
+      CK(cudaGraphLaunch(exec, c->stream));
+      c->launches += batch + 1;
+      CK(cudaMemcpyAsync(&c->hs->red[1], c->scal.as<double>() + 5, 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      rr = c->hs->red[1];
+      it += batch;
+      if (!(rr > tol2)) break;  // also stops on NaN
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+  }
+  if (d_out) CK(cudaMemcpyAsync(d_out, s.x, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  if (iters_out) *iters_out = it;
+  if (relres_out) *relres_out = gg > 0 ? std::sqrt(rr / gg) : 0.0;
+  c->last_cg_iters = it;
+  if (!(rr == rr)) return fail(c, MA_LINSOLVE_RESIDUAL, "CG produced NaN");
+  return MA_OK;
+}
+
 int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double *val, const double *g, double sign,
               int ground, double *d_out, int *iters_out, double *relres_out) {
+  if (c->cg_single) return cg1_solve(c, n, rowptr, col, val, g, sign, ground, d_out, iters_out, relres_out);
   PcgState s;
   const int nblocks = std::min(PCG_MAX_BLOCKS, std::max(1, cdiv(n, PCG_NT)));
   CKR(ensure(c, c->dinv, (size_t)n * 8)); CKR(ensure(c, c->cgx, (size_t)n * 8)); CKR(ensure(c, c->cgr, (size_t)n * 8));
   CKR(ensure(c, c->cgz, (size_t)n * 8)); CKR(ensure(c, c->cgp0, (size_t)n * 8)); CKR(ensure(c, c->cgp1, (size_t)n * 8));
   CKR(ensure(c, c->cgq, (size_t)n * 8));
-  CKR(ensure(c, c->part_pq, (size_t)nblocks * 8)); CKR(ensure(c, c->part_rz, (size_t)2 * nblocks * 8));
+  CKR(ensure(c, c->part_pq, (size_t)6 * PCG_MAX_BLOCKS * 8)); CKR(ensure(c, c->part_rz, (size_t)2 * nblocks * 8));
   CKR(ensure(c, c->part_rr, (size_t)nblocks * 8)); CKR(ensure(c, c->scal, 64)); CKR(ensure(c, c->cgflag, 16));
   s.n = n; s.ground = ground; s.rowptr = rowptr; s.col = col; s.val = val;
   s.dinv = c->dinv.as<double>(); s.x = c->cgx.as<double>(); s.r = c->cgr.as<double>(); s.z = c->cgz.as<double>();
@@ -1060,7 +1139,32 @@ int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double 
   const double gg = h_scal[2];
   int it = 0;
   double rr = gg;
-  if (gg > 0) {
+  if (gg > 0 && c->pcg_persist) {
+    // one persistent kernel per chunk of iterations, all blocks co-resident (cooperative launch)
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist, PCG_NT, 0));
+    const int pb = std::max(1, std::min(nblocks, std::min(per_sm, c->pcg_blocks_per_sm) * c->sm_count));
+    CKR(ensure(c, c->cgbar, 64));
+    const double tol2 = c->cg_rtol * c->cg_rtol * gg;
+    PcgState sp = s;
+    while (it < c->cg_maxit) {
+      int chunk = std::min(c->cg_maxit - it, 4096);
+      chunk += chunk & 1;  // even: the parity of the p buffers is the same at every launch
+      CK(cudaMemsetAsync(c->cgbar.p, 0, 64, c->stream));
+      unsigned *bar = c->cgbar.as<unsigned>();
+      void *args[] = {&sp, &it, &chunk, (void *)&tol2, &bar};
+      CK(cudaLaunchCooperativeKernel((void *)k_pcg_persist, dim3(pb), dim3(PCG_NT), args, 0, c->stream));
+      c->launches++;
+      double two[2];
+      CK(cudaMemcpyAsync(two, c->scal.as<double>() + 3, 16, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      rr = two[0];
+      const int did = (int)two[1];
+      it += did;
+      if (!(rr > tol2) || did < chunk) break;
+      if (did & 1) break;  // (cannot happen: an odd count means an early stop, handled above)
+    }
+  } else if (gg > 0) {
     const int batch = 32;  // even, so iteration parity is the same in every graph launch
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;

@@ -487,6 +487,13 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
   S.i = -1; S.jc = -1; S.phase = 2; S.n = 0; S.status = 0;  // "done, nothing to emit"
   bool parked = false;  // no more cells for this lane
   for (;;) {
+    // line-search trial: as soon as any cell anywhere is known to be empty the trial point is rejected
+    // (optimal_transport.hpp:167), so the whole warp drops what it is doing (one lane polls the flag)
+    if (p.abort_on_empty) {
+      int f = (lane == 0) ? *(volatile const int *)p.abort_flag : 0;
+      f = __shfl_sync(0xffffffffu, f, 0);
+      if (f) break;
+    }
     // ---- refill: lanes whose cell is finished write it out and take the next cell of the chunk ----
     const bool fin = !parked && S.done();
     const unsigned finmask = __ballot_sync(0xffffffffu, fin);

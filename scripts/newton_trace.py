@@ -11,6 +11,9 @@ maxiter = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 case = common.make_case(name, scale, "zero")
 ctx = capi.Context(0)
 common.load_engine(ctx, case)
+for kv in filter(None, os.environ.get("MA_OPTS", "").split(",")):
+    k, v = kv.split("=")
+    ctx.set_option(k, float(v))
 nu = np.full(case["N"], ctx.total_mass / case["N"])
 t = time.time()
 w, st, rc = ctx.ot_solve(nu, eps_g=1e-7, maxiter=maxiter, verbose=True)
