@@ -39,6 +39,8 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "laguerre_cell_evals_per_s"
+# DRAM bytes of the two roofline kernels per launch at c3 / w = 0, from the ncu capture named in traffic_source
+NCU_TRAFFIC_BYTES = None
 UNIT = "cell-evals/s"
 
 
@@ -54,6 +56,7 @@ def parse_args():
     ap.add_argument("--no-newton", action="store_true", help="skip the metric-2 Newton solve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--newton-workload", default="c2")
+    ap.add_argument("--newton-maxiter", type=int, default=1000)
     ap.add_argument("--cpu-sample", type=float, default=0.1, help="fraction of the cells the CPU legs evaluate")
     return ap.parse_args()
 
@@ -315,10 +318,13 @@ def main_b200(args, rank, world, local_rank):
         common.load_engine(nctx, ncase)
         nu = np.full(ncase["N"], nctx.total_mass / ncase["N"])
         t0 = time.perf_counter()
-        _, st, rc = nctx.ot_solve(nu, eps_g=1e-7, maxiter=100, verbose=False)
+        # the reference's default maxiter = 100 stops this solve at |g| = 9e-4 (the damped Newton of
+        # optimal_transport.hpp crawls from w = 0 on such a density); 1000 lets it reach eps_g = 1e-7
+        _, st, rc = nctx.ot_solve(nu, eps_g=1e-7, maxiter=args.newton_maxiter, verbose=False)
         newton = {"workload": args.newton_workload, "N": ncase["N"], "seconds": time.perf_counter() - t0,
                   "status": capi.STATUS_NAMES[rc], "niter": st["niter"], "neval": st["neval"],
-                  "cg_iters": st["cg_iters"], "final_norm": st["final_norm"], "gpus": 1}
+                  "cg_iters": st["cg_iters"], "final_norm": st["final_norm"], "eps_g": 1e-7,
+                  "maxiter": args.newton_maxiter, "gpus": 1}
         nctx.close()
 
     cpu = None
@@ -344,7 +350,10 @@ def main_b200(args, rank, world, local_rank):
                          "achieved": flops_local / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None,
                          "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": (flops_local / (kern_ms * 1e-3)) / fp64_peak if kern_ms > 0 else None,
-                         "traffic": None,
+                         "traffic": NCU_TRAFFIC_BYTES if (seg and world == 1 and args.workload == "c3" and args.scale == 1.0
+                                                          and args.weights == "zero") else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_cells_persist + k_seg, one "
+                                           "launch each, ncu --set full capture of this workload (profiles/r01m_summary.md)",
                          "peak_source": "DFMA probe in this run (MEASURED_PEAKS.json has no fp64 figure)",
                          "algorithmic_flops_per_launch": flops_local,
                          "flops_per_cell": flops_total / N},

@@ -166,15 +166,15 @@ int reduce4(ma_ctx *c, const double *a, const double *b, int n, double *out_dev)
 }
 
 // prefix sums of the moment terms of SET over the Morton-sorted sites into out[K][n+1]
-template <int SET> int moment_scan(ma_ctx *c, double *out) {
+template <int SET> int moment_scan(ma_ctx *c, double *out, PlaneGate gate = PlaneGate{nullptr, 0.0}) {
   constexpr int K = MomentTerms<SET>::K;
   const int n = c->N, nt = std::max(1, cdiv(n, FS_TILE));
   CKR(ensure(c, c->fs_tiles, (size_t)K * nt * 8));
   const double cx = c->px0 + 0.5 * c->ph * (1 << c->L), cy = c->py0 + 0.5 * c->ph * (1 << c->L);
   k_moment_scan_tiles<SET><<<nt, FS_NT, 0, c->stream>>>(c->xs.as<double>(), c->ys.as<double>(), c->ws.as<double>(), cx, cy,
-                                                        n, out, c->fs_tiles.as<double>());
-  k_moment_scan_sums<<<K, FS_NT, 0, c->stream>>>(c->fs_tiles.as<double>(), nt, n, out);
-  k_moment_scan_add<<<nt, FS_NT, 0, c->stream>>>(out, c->fs_tiles.as<double>(), n, K);
+                                                        n, out, c->fs_tiles.as<double>(), gate);
+  k_moment_scan_sums<<<K, FS_NT, 0, c->stream>>>(c->fs_tiles.as<double>(), nt, n, out, gate);
+  k_moment_scan_add<<<nt, FS_NT, 0, c->stream>>>(out, c->fs_tiles.as<double>(), n, K, gate);
   c->launches += 3;
   CK(cudaGetLastError());
   return MA_OK;
@@ -674,15 +674,16 @@ template <bool POLY = false> int run_cells(ma_ctx *c, Params &p) {
   if (c->L >= 5) k_wmax_top<<<1, 1024, 0, c->stream>>>(c->L, c->wmax.as<double>());
   CKR(reduce4(c, c->ws.as<double>(), nullptr, N, c->wstat.as<double>()));  // weight range (K2's choice of pruning disk)
   c->launches += 2 + (c->L >= 5);
-  CKR(moment_scan<1>(c, c->pre1.as<double>()));
+  const PlaneGate gate{c->wstat.as<double>(), 0.25 * c->ph * c->ph};
+  CKR(moment_scan<1>(c, c->pre1.as<double>(), gate));
   {
     const size_t nnodes = (4 * nb - 1) / 3;
     k_node_fit<<<cdiv((long long)nnodes, 256), 256, 0, c->stream>>>(c->L, c->bin_start.as<int>(), N, c->pre0.as<double>(),
                                                                     c->pre1.as<double>(), c->nodeG.as<double>(),
-                                                                    c->nodeA.as<unsigned long long>());
+                                                                    c->nodeA.as<unsigned long long>(), gate);
     k_node_alpha<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->L, c->xs.as<double>(), c->ys.as<double>(), c->ws.as<double>(),
                                                       c->code_s.as<unsigned>(), c->px0, c->py0, c->ph, c->nodeG.as<double>(),
-                                                      c->nodeA.as<unsigned long long>());
+                                                      c->nodeA.as<unsigned long long>(), gate);
     c->launches += 2;
   }
   CK(cudaGetLastError());

@@ -312,7 +312,7 @@ template <class Poly> struct CellSearch {
           const double fx = fmax(fabs(ox), fabs(ox + S)), fy = fmax(fabs(oy), fabs(oy + S));
           if (emin > 0.0 && emin * emin >= rc2 * (fx * fx + fy * fy) * (1.0 + 1e-9)) alive = false;
         }
-        if (alive) {
+        if (alive && use_m) {  // (the planes are only built when the weights vary, see PlaneGate)
           const size_t node = level_offset(l) + code;
           const double Gx = p.nodeG[2 * node], Gy = p.nodeG[2 * node + 1], al = dkey_inv(p.nodeA[node]);
           const double hs = 0.5 * S, Zx = ox + hs, Zy = oy + hs;

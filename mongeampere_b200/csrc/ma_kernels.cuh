@@ -272,6 +272,15 @@ __global__ void __launch_bounds__(1024) k_wmax_top(int L, double *__restrict__ w
 // ================================================================================================
 constexpr int FS_NT = 256, FS_ITEMS = 4, FS_TILE = FS_NT * FS_ITEMS;
 
+// The per-node planes are only consulted when the weights vary enough to displace cells from their
+// Diracs (CellSearch::use_m, same threshold): the kernels that build them return at once otherwise.
+// gate = {wstat, 0.25 * ph^2}; wstat = {sum, sum of squares, min, max} of the weights (device).
+struct PlaneGate {
+  const double *wstat;
+  double thresh;
+  __device__ __forceinline__ bool off() const { return wstat && !((wstat[3] - wstat[2]) > thresh); }
+};
+
 template <int SET> struct MomentTerms;
 template <> struct MomentTerms<0> { static constexpr int K = 5; };
 template <> struct MomentTerms<1> { static constexpr int K = 3; };
@@ -315,7 +324,9 @@ __device__ __forceinline__ double block_exclusive_scan_f64(double v, double *tot
 template <int SET>
 __global__ void __launch_bounds__(FS_NT) k_moment_scan_tiles(const double *__restrict__ xs, const double *__restrict__ ys,
                                                               const double *__restrict__ ws, double cx, double cy, int n,
-                                                              double *__restrict__ out, double *__restrict__ tile_sums) {
+                                                              double *__restrict__ out, double *__restrict__ tile_sums,
+                                                              PlaneGate gate) {
+  if (SET == 1 && gate.off()) return;
   constexpr int K = MomentTerms<SET>::K;
   __shared__ double sh[FS_NT / 32 + 1];
   const int base = blockIdx.x * FS_TILE + threadIdx.x * FS_ITEMS;
@@ -346,7 +357,8 @@ __global__ void __launch_bounds__(FS_NT) k_moment_scan_tiles(const double *__res
 }
 // one block per component: exclusive scan of that component's tile sums in place; grand total to out[c*(n+1)+n]
 __global__ void __launch_bounds__(FS_NT) k_moment_scan_sums(double *__restrict__ tile_sums, int nt, int n,
-                                                             double *__restrict__ out) {
+                                                             double *__restrict__ out, PlaneGate gate) {
+  if (gate.off()) return;
   __shared__ double sh[FS_NT / 32 + 1];
   double *ts = tile_sums + (size_t)blockIdx.x * nt;
   double carry = 0.0;
@@ -360,7 +372,8 @@ __global__ void __launch_bounds__(FS_NT) k_moment_scan_sums(double *__restrict__
   if (threadIdx.x == 0) out[(size_t)blockIdx.x * (n + 1) + n] = carry;
 }
 __global__ void __launch_bounds__(FS_NT) k_moment_scan_add(double *__restrict__ out, const double *__restrict__ tile_sums,
-                                                            int n, int K) {
+                                                            int n, int K, PlaneGate gate) {
+  if (gate.off()) return;
   const int base = blockIdx.x * FS_TILE + threadIdx.x * FS_ITEMS;
   for (int c = 0; c < K; ++c) {
     double off = tile_sums[(size_t)c * gridDim.x + blockIdx.x];
@@ -388,7 +401,8 @@ __device__ __forceinline__ bool node_fit_one(int L, int l, unsigned code, const 
 }
 __global__ void k_node_fit(int L, const int *__restrict__ bin_start, int n, const double *__restrict__ pre0,
                            const double *__restrict__ pre1, double *__restrict__ nodeG,
-                           unsigned long long *__restrict__ nodeA) {
+                           unsigned long long *__restrict__ nodeA, PlaneGate gate) {
+  if (gate.off()) return;
   const size_t nnodes = level_offset(L + 1);
   size_t node = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= nnodes) return;
@@ -407,7 +421,9 @@ __global__ void k_node_fit(int L, const int *__restrict__ bin_start, int n, cons
 // one thread per site: fold the site into alpha of its node at every level
 __global__ void k_node_alpha(int n, int L, const double *__restrict__ xs, const double *__restrict__ ys,
                              const double *__restrict__ ws, const unsigned *__restrict__ code_s, double px0, double py0,
-                             double ph, const double *__restrict__ nodeG, unsigned long long *__restrict__ nodeA) {
+                             double ph, const double *__restrict__ nodeG, unsigned long long *__restrict__ nodeA,
+                             PlaneGate gate) {
+  if (gate.off()) return;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = j < n;
   const unsigned leaf = live ? code_s[j] : 0u;
