@@ -117,6 +117,18 @@ int ma_ot_solve(ma_ctx *ctx, const double *nu, double *w, int have_initial, doub
 int ma_pieces_build(ma_ctx *ctx, const double *weights, int *npieces, int *nvertices);
 int ma_pieces_get(ma_ctx *ctx, int *cell, int *face, int *ptr, int *tag, double *xy);
 
+/* ---- Laguerre cells as polygons ---------------------------------------------------------------
+ * The power cell of every Dirac clipped to the bounding box of the source mesh, i.e. what
+ * voronoi_polygon_intersection(P, dt, v) (voronoi_polygon_intersection.hpp:153-188) returns for P = that box
+ * (tests/test_voronoi.cpp:41-48, tests/test_power.cpp:43-50 measure these cells); a convex P is then one
+ * host-side clip away (include/MA/voronoi_polygon_intersection.hpp).  Two calls: ma_cells_build runs the
+ * neighbour search (K1 + K2) and returns the total vertex count, ma_cells_get copies out, in the caller's
+ * ordering: cell i has vertices xy[2*ptr[i] .. 2*ptr[i+1]) (CCW, empty for a hidden Dirac) and tag[k] names
+ * the line supporting the edge that STARTS at vertex k: the Laguerre neighbour's index, or -1 / -2 / -3 / -4
+ * for the bottom / right / top / left side of the box. */
+int ma_cells_build(ma_ctx *ctx, const double *weights, int *nvertices);
+int ma_cells_get(ma_ctx *ctx, int *ptr /* N+1 */, double *xy /* 2*nvertices */, int *tag /* nvertices */);
+
 /* ---- device-resident evaluation (what bench.py times as `value`) -----------------------------
  * ma_set_weights uploads w (caller order); ma_evaluate runs K1(per-eval part)+K2+K3+K4 on the
  * device-resident state and leaves masses / Hessian on the device (internal Morton order). */

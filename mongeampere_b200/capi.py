@@ -25,7 +25,8 @@ COUNTER_NAMES = ("pieces", "piece_vertices", "new_vertices", "laguerre_edges", "
 SYMBOLS = (
     "ma_create", "ma_destroy", "ma_last_error", "ma_abi_version", "ma_set_mesh", "ma_set_mesh_pl", "ma_set_grid",
     "ma_set_image", "ma_set_points", "ma_kantorovich", "ma_get_hessian_csr", "ma_moments", "ma_lloyd",
-    "ma_solve_laplacian", "ma_ot_solve", "ma_pieces_build", "ma_pieces_get", "ma_set_weights", "ma_evaluate",
+    "ma_solve_laplacian", "ma_ot_solve", "ma_pieces_build", "ma_pieces_get", "ma_cells_build", "ma_cells_get",
+    "ma_set_weights", "ma_evaluate",
     "ma_get_adjacency", "ma_set_profiling", "ma_get_timings", "ma_set_stats", "ma_get_counters", "ma_flush_l2",
     "ma_measure_fp64_peak", "ma_set_option", "ma_get_info", "ma_set_partition", "ma_timer_start", "ma_timer_stop",
 )
@@ -74,6 +75,8 @@ def load_library(path: str | None = None):
     L.ma_ot_solve.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_size_t, C.c_int, C.POINTER(Statistics)]
     L.ma_pieces_build.argtypes = [vp, vp, ip, ip]
     L.ma_pieces_get.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ma_cells_build.argtypes = [vp, vp, ip]
+    L.ma_cells_get.argtypes = [vp, vp, vp, vp]
     L.ma_set_weights.argtypes = [vp, vp]
     L.ma_evaluate.argtypes = [vp, C.c_int]
     L.ma_get_adjacency.argtypes = [vp, vp, vp, C.c_int]
@@ -258,6 +261,19 @@ class Context:
         xy = np.empty((max(V, 1), 2))
         self._ck(self.L.ma_pieces_get(self.h, _ptr(cell), _ptr(face), _ptr(ptr), _ptr(tag), _ptr(xy)))
         return cell[:P], face[:P], ptr, tag[:V], xy[:V]
+
+    def cells(self, w=None):
+        """Laguerre cells clipped to the mesh bounding box (voronoi_polygon_intersection.hpp:153-188 with
+        P = the box) -> ptr (N+1), xy (nv, 2), tag (nv): neighbour index or -1..-4 for the box sides."""
+        w = np.zeros(self.N) if w is None else _f64(w)
+        nv = C.c_int()
+        self._ck(self.L.ma_cells_build(self.h, _ptr(w), C.byref(nv)))
+        V = nv.value
+        ptr = np.zeros(self.N + 1, np.int32)
+        xy = np.empty((max(V, 1), 2))
+        tag = np.empty(max(V, 1), np.int32)
+        self._ck(self.L.ma_cells_get(self.h, _ptr(ptr), _ptr(xy), _ptr(tag)))
+        return ptr, xy[:V], tag[:V]
 
     # ---- device-resident path / instrumentation ----
     def set_weights(self, w):

@@ -78,6 +78,7 @@ struct ma_ctx {
   // pieces
   Buf pc_count, pc_off, pc_cell, pc_face, pc_ptr, pc_tag, pc_xy;
   int pc_np = 0, pc_nv = 0;
+  int cells_nv = -1;  // ma_cells_build
 
   // pcg
   Buf dinv, cgx, cgr, cgz, cgp0, cgp1, cgq, cgw1, cgpp, part_pq, part_rz, part_rr, scal, cgflag, cgbar;
@@ -217,6 +218,7 @@ int upload(ma_ctx *c, Buf &b, const void *src, size_t bytes) {
 }
 
 void invalidate_eval(ma_ctx *c) {
+  c->cells_nv = -1;
   c->have_eval = false;
   c->have_hessian = false;
 }
@@ -1030,6 +1032,70 @@ extern "C" int ma_pieces_get(ma_ctx *c, int *cell, int *face, int *ptr, int *tag
   }
   if (cell) for (int k = 0; k < np; ++k) cell[k] = perm[hc[k]];
   if (tag) for (int k = 0; k < nv; ++k) tag[k] = ht[k] >= 0 ? perm[ht[k]] : -1;
+  return MA_OK;
+}
+
+// =============================================================================================
+// Laguerre cells (cell ∩ mesh bounding box) as polygons: K1 + K2 only
+// =============================================================================================
+extern "C" int ma_cells_build(ma_ctx *c, const double *w, int *nvertices) {
+  NEED_CTX();
+  if (c->mesh_kind == MESH_NONE || c->N < 1) return fail(c, MA_INVALID, "mesh/points not set");
+  CKR(ma_set_weights(c, w));
+  c->kmax = c->kmax_base;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    CKR(alloc_eval(c));
+    const size_t slots = (size_t)cells_maxv(c->kmax) * c->N;
+    CKR(ensure(c, c->poly_x, slots * 8)); CKR(ensure(c, c->poly_y, slots * 8));
+    CKR(ensure(c, c->poly_t, slots * 4)); CKR(ensure(c, c->poly_n, (size_t)c->N * 4));
+    Params p;
+    fill_params(c, p);
+    p.stats = 0;
+    CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
+    if (c->part_n > 1) CK(cudaMemsetAsync(c->poly_n.p, 0, (size_t)c->N * 4, c->stream));  // other tiles: no polygon here
+    CKR(run_cells<true>(c, p));
+    CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->hs->flags & (FLAG_CELL_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
+      if (c->kmax >= 64) return fail(c, MA_INVALID, "polygon capacity exceeded");
+      c->kmax *= 2;
+      continue;
+    }
+    if (c->hs->flags & FLAG_STACK_OVERFLOW) return fail(c, MA_INVALID, "quadtree stack overflow");
+    const int N = c->N;
+    CKR(ensure(c, c->scratch_i, (size_t)N * 4));
+    CKR(ensure(c, c->cptr, (size_t)(N + 1) * 4));
+    k_cellpoly_count<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->poly_n.as<int>(), c->pos.as<int>(), c->scratch_i.as<int>());
+    CKR(scan_i32(c, c->scratch_i.as<int>(), c->cptr.as<int>(), N));
+    CK(cudaMemcpyAsync(&c->hs->nnz, c->cptr.as<int>() + N, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->cells_nv = c->hs->nnz;
+    if (nvertices) *nvertices = c->cells_nv;
+    c->have_eval = true;
+    c->have_hessian = false;
+    return MA_OK;
+  }
+  return fail(c, MA_INVALID, "cells failed after capacity escalation");
+}
+
+extern "C" int ma_cells_get(ma_ctx *c, int *ptr, double *xy, int *tag) {
+  NEED_CTX();
+  if (c->cells_nv < 0) return fail(c, MA_INVALID, "no cells: call ma_cells_build first");
+  if (!ptr || !xy || !tag) return fail(c, MA_INVALID, "ma_cells_get: null output");
+  const int N = c->N, nv = c->cells_nv;
+  CKR(ensure(c, c->pc_xy, (size_t)std::max(nv, 1) * 16));
+  CKR(ensure(c, c->pc_tag, (size_t)std::max(nv, 1) * 4));
+  k_cellpoly_fill<<<cdiv(N, 128), 128, 0, c->stream>>>(N, c->poly_n.as<int>(), c->poly_x.as<double>(), c->poly_y.as<double>(),
+                                                      c->poly_t.as<int>(), c->xs.as<double>(), c->ys.as<double>(),
+                                                      c->pos.as<int>(), c->perm.as<int>(), c->cptr.as<int>(),
+                                                      c->pc_xy.as<double>(), c->pc_tag.as<int>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ptr, c->cptr.p, (size_t)(N + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (nv) {
+    CK(cudaMemcpyAsync(xy, c->pc_xy.p, (size_t)nv * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(tag, c->pc_tag.p, (size_t)nv * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
   return MA_OK;
 }
 

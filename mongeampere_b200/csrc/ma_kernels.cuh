@@ -826,6 +826,28 @@ __global__ void k_adj_fill(int n, int kmax, const int *__restrict__ nbr, const i
   for (int s = 0; s < c; ++s) idx[o + s] = perm[nbr[(size_t)k * kmax + s]];
 }
 
+// cell polygons in caller order (ma_cells_get)
+__global__ void k_cellpoly_count(int n, const int *__restrict__ poly_n, const int *__restrict__ pos, int *__restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cnt[i] = poly_n[pos[i]];
+}
+__global__ void k_cellpoly_fill(int n, const int *__restrict__ poly_n, const double *__restrict__ px,
+                                const double *__restrict__ py, const int *__restrict__ pt, const double *__restrict__ xs,
+                                const double *__restrict__ ys, const int *__restrict__ pos, const int *__restrict__ perm,
+                                const int *__restrict__ ptr, double *__restrict__ xy, int *__restrict__ tag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = pos[i], m = poly_n[k], o = ptr[i];
+  const double x0 = xs[k], y0 = ys[k];
+  for (int v = 0; v < m; ++v) {
+    const size_t s = (size_t)v * n + k;
+    xy[2 * (size_t)(o + v)] = px[s] + x0;
+    xy[2 * (size_t)(o + v) + 1] = py[s] + y0;
+    const int t = pt[s];
+    tag[o + v] = t >= 0 ? perm[t] : t;  // -1 bottom, -2 right, -3 top, -4 left side of the mesh box
+  }
+}
+
 __global__ void k_fill_bytes(unsigned long long *p, size_t n, unsigned long long v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }

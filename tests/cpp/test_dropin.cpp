@@ -7,6 +7,7 @@
 // build: g++ -std=c++14 -O2 -I include tests/cpp/test_dropin.cpp -L mongeampere_b200 -lma_b200 -Wl,-rpath,...
 #include <MA/lloyd.hpp>
 #include <MA/optimal_transport.hpp>
+#include <MA/voronoi_polygon_intersection.hpp>
 #include <MA/voronoi_triangulation_intersection.hpp>
 
 #include <cstdio>
@@ -104,6 +105,17 @@ int main(int argc, const char **argv) {
       ++pieces;
     });
     printf("area_sum %.17g\npieces %zu\ncell_area0 %.17g\n", area, pieces, cell_area[0]);
+  }
+  // ---- voronoi_polygon_intersection (voronoi_polygon_intersection.hpp:153-188; tests/test_power.cpp:43-50) ----
+  {
+    MA::lite::Weighted_sites dt(X, res);
+    MA::lite::Polygon P;  // a convex pentagon inside the domain, counter-clockwise
+    P.push_back(Point(-0.8, -0.7)); P.push_back(Point(0.6, -0.9)); P.push_back(Point(0.9, 0.1));
+    P.push_back(Point(0.2, 0.85)); P.push_back(Point(-0.7, 0.5));
+    double area = 0;
+    for (MA::lite::Weighted_sites::Finite_vertices_iterator v = dt.finite_vertices_begin(); v != dt.finite_vertices_end(); ++v)
+      area += MA::voronoi_polygon_intersection(P, dt, v).area();
+    printf("pentagon_area %.17g\ncells_area_sum %.17g\n", P.area(), area);
   }
   return 0;
 }

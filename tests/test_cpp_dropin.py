@@ -91,3 +91,5 @@ def test_cpp_dropin_matches_c_abi(gpu_ctx):
     # tests/test_voronoi_tri.cpp:67: the pieces tile the domain; cell 0's pieces have the cell's area
     assert abs(out["area_sum"][0] - 4.0) <= 1e-11
     assert out["pieces"][0] >= N
+    # tests/test_power.cpp:51: the cells clipped to a convex polygon tile it
+    assert abs(out["cells_area_sum"][0] - out["pentagon_area"][0]) <= 1e-12
