@@ -14,7 +14,8 @@ common.load_engine(ctx, case)
 for kv in filter(None, os.environ.get("MA_OPTS", "").split(",")):
     k, v = kv.split("=")
     ctx.set_option(k, float(v))
-nu = np.full(case["N"], ctx.total_mass / case["N"])
+tm = ctx.total_mass if getattr(ctx, "total_mass", None) else float(ctx.kantorovich(np.zeros(case["N"]))[1].sum())
+nu = np.full(case["N"], tm / case["N"])
 t = time.time()
 w, st, rc = ctx.ot_solve(nu, eps_g=1e-7, maxiter=maxiter, verbose=True)
 print("rc", rc, st, "wall", time.time() - t)
