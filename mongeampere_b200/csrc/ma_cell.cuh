@@ -35,6 +35,7 @@ struct Params {
   const double *nodeG;                // 2 per node: least-squares weight gradient (ma_geom.cuh)
   const unsigned long long *nodeA;    // per node: dkey(alpha_B)
   int refill_at;                      // k_cells_persist refills when this many lanes have finished
+  int rmax;                           // K2 walks rings 0..rmax of leaf bins before it turns to the quadtree
   int clip_a, clip_b;                 // K2 clips when n_hold * clip_a >= n_search * clip_b (warp vote policy)
   const int *abort_flag;              // != 0: another cell is already known to be empty, stop (line search)
   int abort_on_empty;
@@ -119,6 +120,13 @@ struct Params {
 // they finish, ma_kernels.cuh).
 // ------------------------------------------------------------------------------------------------
 constexpr int CELL_STACK = 52;
+// host-only work counters (tests/emu): [0] sites looked at, [1] sign loops, [2] clips, [3] tree nodes
+#if !defined(__CUDA_ARCH__) && defined(MA_EMU_COUNTERS)
+#define MA_COUNT(k) (++ma_emu_counters[k])
+extern long long ma_emu_counters[8];
+#else
+#define MA_COUNT(k) ((void)0)
+#endif
 template <class Poly> struct CellSearch {
   int i, n, status, phase;   // phase: 0 rings, 1 tree, 2 finished
   double xi, yi, wi, bx0, by0, bx1, by1, R2;
@@ -191,7 +199,7 @@ template <class Poly> struct CellSearch {
   MA_DEV void search_step(const Params &p, const Poly &P, unsigned *stk) {
     const double NEG_INF = -1.0 / 0.0, POS_INF = 1.0 / 0.0;
     const int G = 1 << p.L;
-    const int RMAX = 3;
+    const int RMAX = p.rmax;
     if (phase == 0 && j >= jend) {
       // ring walk: move on to the next non-empty bin of ring r (a few cheap iterations), so that the
       // step below handles a site in (almost) every call
@@ -212,6 +220,7 @@ template <class Poly> struct CellSearch {
     if (j < jend) {
       // ---- step kind 1: the next site of the current bin
       const int jj = j++;
+      MA_COUNT(0);
       const double Dx = p.xs[jj] - xi, Dy = p.ys[jj] - yi, wj = p.ws[jj];
       const double dd2 = Dx * Dx + Dy * Dy;
       if (jj != i && dd2 > lo2 && dd2 <= hi2) {  // else: itself / an earlier pass's / a later pass's
@@ -226,6 +235,7 @@ template <class Poly> struct CellSearch {
           const double e = c - (mx * Dx + my * Dy);
           if (!(e >= 0.0 && e * e >= rc2 * dd2 * (1.0 + 1e-12))) {
             unsigned long long in = 0ull;
+            MA_COUNT(1);
             for (int k = 0; k < n; ++k)
               if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
             const unsigned long long full = lowmask64(n);
@@ -282,6 +292,7 @@ template <class Poly> struct CellSearch {
         }
       }
       if (phase == 1) {
+        MA_COUNT(3);
         const unsigned e = stk[--sp];
         const int l = (int)(e >> 26);
         const unsigned code = e & 0x3ffffffu;
@@ -325,6 +336,18 @@ template <class Poly> struct CellSearch {
             can = can || !(lb >= (r2 - wi) + 1e-10 * (pp + fabs(al) + slop + r2 + fabs(wi)));
           }
           alive = can;
+        } else if (alive) {
+          // (b') weights (nearly) constant: the planes are not built; every site of the node lies in its
+          // square, so pow_j(p) >= dist(p, square)^2 - wm, tested vertex by vertex (a big boundary cell
+          // defeats the disk of test (a), not this one)
+          bool can = false;
+          for (int k = 0; k < n; ++k) {
+            const double ux = P.X(k), uy = P.Y(k);
+            const double qx = fmax(fmax(ox - ux, ux - (ox + S)), 0.0), qy = fmax(fmax(oy - uy, uy - (oy + S)), 0.0);
+            const double lhs = qx * qx + qy * qy - wm, rhs = ux * ux + uy * uy - wi;
+            can = can || !(lhs >= rhs + 1e-10 * (qx * qx + qy * qy + ux * ux + uy * uy + fabs(wm) + fabs(wi)));
+          }
+          alive = can;
         }
         if (alive) {
           if (l < p.L) {
@@ -346,6 +369,7 @@ template <class Poly> struct CellSearch {
 
   // clip by the held site (requires holding())
   MA_DEV void clip(const Params &p, Poly &P, int maxv) {
+    MA_COUNT(2);
     auto lo = [&](int tag, double &nx, double &ny, double &cl) { lineof(p, tag, nx, ny, cl); };
     int n2;
     if constexpr (Poly::PACK) n2 = clip_packed(P, n, maxv, cin, cDx, cDy, cc, jc, lo);

@@ -10,10 +10,10 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 maxiter = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 case = common.make_case(name, scale, "zero")
 ctx = capi.Context(0)
-common.load_engine(ctx, case)
-for kv in filter(None, os.environ.get("MA_OPTS", "").split(",")):
+for kv in filter(None, os.environ.get("MA_OPTS", "").split(",")):  # before the points are binned (bin_target)
     k, v = kv.split("=")
     ctx.set_option(k, float(v))
+common.load_engine(ctx, case)
 tm = ctx.total_mass if getattr(ctx, "total_mass", None) else float(ctx.kantorovich(np.zeros(case["N"]))[1].sum())
 nu = np.full(case["N"], tm / case["N"])
 t = time.time()

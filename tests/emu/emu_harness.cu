@@ -12,7 +12,13 @@
 #include <limits>
 #include <vector>
 
+#define MA_EMU_COUNTERS
 #include "../../mongeampere_b200/csrc/ma_seg.cuh"
+
+namespace ma { long long ma_emu_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }
+extern "C" void emu_work_counters(long long *out, int reset) {
+  for (int k = 0; k < 8; ++k) { out[k] = ma::ma_emu_counters[k]; if (reset) ma::ma_emu_counters[k] = 0; }
+}
 
 using namespace ma;
 
@@ -155,7 +161,7 @@ extern "C" int emu_eval(int mesh_kind,
       }
   }
   int no_abort = 0;
-  p.nodeG = nodeG.data(); p.nodeA = nodeA.data(); p.abort_flag = &no_abort; p.abort_on_empty = 0; p.clip_a = p.clip_b = 1; p.refill_at = 8;
+  p.nodeG = nodeG.data(); p.nodeA = nodeA.data(); p.abort_flag = &no_abort; p.abort_on_empty = 0; p.clip_a = p.clip_b = 1; p.refill_at = 8; p.rmax = 3;
   p.N = N; p.xs = xs.data(); p.ys = ys.data(); p.ws = ws.data();
   p.cell_lo = 0; p.cell_hi = N;
   p.bin_start = bin_start.data(); p.wmax = wmax.data();
