@@ -782,9 +782,9 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
         if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
         const int N = c->N;
         switch (c->kmax) {
-          case 16: k_csr_fill<16><<<cdiv(N, 32 * csr_wpb<16>()), 32 * csr_wpb<16>(), 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
-          case 32: k_csr_fill<32><<<cdiv(N, 32 * csr_wpb<32>()), 32 * csr_wpb<32>(), 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
-          default: k_csr_fill<64><<<cdiv(N, 32 * csr_wpb<64>()), 32 * csr_wpb<64>(), 0, c->stream>>>(N, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+          case 16: k_csr_fill<16><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, 32 * csr_wpb<16>())), 32 * csr_wpb<16>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+          case 32: k_csr_fill<32><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, 32 * csr_wpb<32>())), 32 * csr_wpb<32>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+          default: k_csr_fill<64><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, 32 * csr_wpb<64>())), 32 * csr_wpb<64>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
         }
         c->launches++;
         CK(cudaGetLastError());

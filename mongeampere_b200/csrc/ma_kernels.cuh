@@ -721,7 +721,7 @@ template <int KMAX, int MAXV, int MODE> __global__ void __launch_bounds__(PIECES
 // contiguous range [rowptr[first row], rowptr[last row + 1]) with coalesced stores.
 template <int KMAX> constexpr int csr_wpb() { return KMAX <= 16 ? 4 : (KMAX <= 32 ? 2 : 1); }  // warps per block (48 KB of static shared memory)
 template <int KMAX>
-__global__ void __launch_bounds__(csr_wpb<KMAX>() * 32) k_csr_fill(int N, const int *__restrict__ nbr, const double *__restrict__ hslot,
+__global__ void __launch_bounds__(csr_wpb<KMAX>() * 32) k_csr_fill(int row_lo, int N, const int *__restrict__ nbr, const double *__restrict__ hslot,
                                                           const unsigned long long *__restrict__ touched,
                                                           const int *__restrict__ rowptr, int *__restrict__ col,
                                                           double *__restrict__ val) {
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(csr_wpb<KMAX>() * 32) k_csr_fill(int N, const 
   __shared__ double sh_h[CSR_WPB][32 * LD];
   __shared__ int sh_j[CSR_WPB][32 * LD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * CSR_WPB + warp) * 32;
+  const int row0 = row_lo + (blockIdx.x * CSR_WPB + warp) * 32;  // rows [row_lo, N): this context's Morton tile
   if (row0 >= N) return;  // warp-uniform
   const int nrows = min(32, N - row0);
   double *H = sh_h[warp];
