@@ -127,6 +127,10 @@ int ma_pieces_get(ma_ctx *ctx, int *cell, int *face, int *ptr, int *tag, double 
  * the line supporting the edge that STARTS at vertex k: the Laguerre neighbour's index, or -1 / -2 / -3 / -4
  * for the bottom / right / top / left side of the box. */
 int ma_cells_build(ma_ctx *ctx, const double *weights, int *nvertices);
+/* With ma_set_option(ctx, "abort_on_empty", 1) ma_cells_build stops as soon as a cell of this context's tile is found
+ * empty and ma_get_info(ctx, "aborted") returns 1 (no polygons then): the cheap "does this trial point hide a Dirac?"
+ * test of the line search (optimal_transport.hpp:167), used by the multi-GPU Newton loop before it pays for a full
+ * evaluation. */
 int ma_cells_get(ma_ctx *ctx, int *ptr /* N+1 */, double *xy /* 2*nvertices */, int *tag /* nvertices */);
 
 /* ---- device-resident evaluation (what bench.py times as `value`) -----------------------------

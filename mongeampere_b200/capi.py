@@ -275,6 +275,18 @@ class Context:
         self._ck(self.L.ma_cells_get(self.h, _ptr(ptr), _ptr(xy), _ptr(tag)))
         return ptr, xy[:V], tag[:V]
 
+    def has_empty_cell(self, w):
+        """True iff some Dirac of this context's tile has an empty Laguerre cell at weights w (K1 + K2 only, stops at
+        the first one): the line search rejects such a trial point (optimal_transport.hpp:167)."""
+        w = _f64(w)
+        nv = C.c_int()
+        self.set_option("abort_on_empty", 1)
+        try:
+            self._ck(self.L.ma_cells_build(self.h, _ptr(w), C.byref(nv)))
+            return bool(self.info("aborted"))
+        finally:
+            self.set_option("abort_on_empty", 0)
+
     # ---- device-resident path / instrumentation ----
     def set_weights(self, w):
         w = _f64(w)

@@ -63,6 +63,7 @@ struct ma_ctx {
   Buf x, y, xs, ys, perm, pos, code, bin_count, bin_start, wmax;
   Buf code_s, pre0, pre1, fs_tiles, nodeG, nodeA, wstat;  // per-node supporting planes (ma_geom.cuh)
   bool abort_on_empty = false, aborted = false;
+  bool probe_empty = false;  // option "abort_on_empty": ma_cells_build stops at the first empty cell and reports it
   int L = 0;
   double px0 = 0, py0 = 0, ph = 1;
 
@@ -308,6 +309,7 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "pcg_blocks_per_sm") c->pcg_blocks_per_sm = std::max(1, (int)value);
   else if (n == "filter_tol") c->filter_tol = value;
   else if (n == "persist") c->persist = (int)value;
+  else if (n == "abort_on_empty") c->probe_empty = value != 0;
   else if (n == "rmax") c->rmax = std::min(8, std::max(1, (int)value));
   else if (n == "clip_a") c->clip_a = std::max(1, (int)value);
   else if (n == "clip_b") c->clip_b = std::max(1, (int)value);
@@ -339,6 +341,7 @@ extern "C" double ma_get_info(ma_ctx *c, const char *name) {
   if (n == "mesh_kind") return c->mesh_kind;
   if (n == "launches") return (double)c->launches;
   if (n == "strategy") return c->strategy;
+  if (n == "aborted") return c->aborted ? 1 : 0;
   if (n == "fval") return c->fval;
   if (n == "cell_lo") return (double)((long long)c->N * c->part_rank / c->part_n);
   if (n == "cell_hi") return (double)((long long)c->N * (c->part_rank + 1) / c->part_n);
@@ -1050,13 +1053,22 @@ extern "C" int ma_cells_build(ma_ctx *c, const double *w, int *nvertices) {
     CKR(ensure(c, c->poly_x, slots * 8)); CKR(ensure(c, c->poly_y, slots * 8));
     CKR(ensure(c, c->poly_t, slots * 4)); CKR(ensure(c, c->poly_n, (size_t)c->N * 4));
     Params p;
+    c->abort_on_empty = c->probe_empty;
     fill_params(c, p);
+    c->abort_on_empty = false;
     p.stats = 0;
     CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
     if (c->part_n > 1) CK(cudaMemsetAsync(c->poly_n.p, 0, (size_t)c->N * 4, c->stream));  // other tiles: no polygon here
     CKR(run_cells<true>(c, p));
     CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->hs->abort_, c->flags.as<int>() + 1, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->aborted = c->probe_empty && c->hs->abort_ != 0;
+    if (c->aborted) {  // a cell of this tile is empty (the caller only wanted to know): no polygons
+      invalidate_eval(c);
+      if (nvertices) *nvertices = 0;
+      return MA_OK;
+    }
     if (c->hs->flags & (FLAG_CELL_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
       if (c->kmax >= 64) return fail(c, MA_INVALID, "polygon capacity exceeded");
       c->kmax *= 2;

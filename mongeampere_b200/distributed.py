@@ -13,7 +13,8 @@ exchanged, through torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU 
     all ranks hold bit-identical weights.
 
 `TileEvaluator` is anything with `.N`, `.kantorovich(w) -> (f_part, g_part, H_part)` (g_part zero and
-H_part empty outside the tile) and `.solve_laplacian_matrix(H, g) -> d`; `mongeampere_b200.capi.Context`
+H_part empty outside the tile), `.has_empty_cell(w) -> bool` (cheap: neighbour search only) and
+`.solve_laplacian_matrix(H, g) -> d`; `mongeampere_b200.capi.Context`
 after `set_partition` is one.  The Newton loop restates optimal_transport.hpp:89-193 (same conditions,
 same `niter++ <= maxiter` quirk) around the distributed evaluation.
 """
@@ -127,7 +128,14 @@ class DistributedKantorovich:
             alpha, x0, n0 = 1.0, x.copy(), np.linalg.norm(g)
             while True:  # :163-176
                 x = x0 + alpha * d
-                fx, m, g, h = f(x)
+                # a trial point that hides a Dirac anywhere has min m = 0 < eps0 and is rejected whatever the
+                # rest of the evaluation says (:167): find that out from the neighbour search alone, on every
+                # tile, before paying for the integrals of a wildly distorted diagram
+                if self._allreduce_sum(np.array([1.0 if self.tile.has_empty_cell(x) else 0.0]))[0] > 0:
+                    stats["neval"] += 1  # the reference evaluates it (App. B T5)
+                    m, g = np.zeros(N), np.full(N, np.inf)
+                else:
+                    fx, m, g, h = f(x)
                 if m.min() >= eps0 and np.linalg.norm(g) <= (1 - alpha / 2) * n0:
                     break
                 alpha *= 0.5
@@ -154,6 +162,9 @@ class ContextTile:
 
     def kantorovich(self, w):
         return self.ctx.kantorovich(w)
+
+    def has_empty_cell(self, w):
+        return self.ctx.has_empty_cell(w)
 
     def solve_laplacian_matrix(self, H, g):
         d, _ = self.ctx.solve_laplacian_matrix(H, g)

@@ -26,6 +26,10 @@ class OracleTile:
         D = sp.diags(mask.astype(np.float64))
         return f_part, np.where(mask, g, 0.0), sp.csr_matrix(D @ H)
 
+    def has_empty_cell(self, w):
+        g = self.orc.kantorovich(w)[1]
+        return bool((g[self.lo:self.hi] <= 0).any())
+
     def solve_laplacian_matrix(self, H, g):
         return self.O.solve_laplacian_matrix(H, g)
 
