@@ -40,7 +40,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "laguerre_cell_evals_per_s"
 # DRAM bytes of the two roofline kernels per launch at c3 / w = 0, from the ncu capture named in traffic_source
-NCU_TRAFFIC_BYTES = 152.0e6 + 300.3e6 + 259.6e6 + 75.2e6  # k_cells_persist (read + write) + k_seg (read + write)
+NCU_TRAFFIC_BYTES = 153.2e6 + 295.5e6 + 259.0e6 + 75.1e6  # k_cells_persist (read + write) + k_seg (read + write)
 UNIT = "cell-evals/s"
 
 
@@ -353,13 +353,13 @@ def main_b200(args, rank, world, local_rank):
                          "traffic": NCU_TRAFFIC_BYTES if (seg and world == 1 and args.workload == "c3" and args.scale == 1.0
                                                           and args.weights == "zero") else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_cells_persist + k_seg, one "
-                                           "launch each, ncu --set full capture of this workload (profiles/r01m_summary.md)",
+                                           "launch each, ncu --set full capture of this workload (profiles/r01n_summary.md)",
                          "peak_source": "DFMA probe in this run (MEASURED_PEAKS.json has no fp64 figure)",
                          "algorithmic_flops_per_launch": flops_local,
                          "flops_per_cell": flops_total / N},
             "roofline_hbm": {"bound": "hbm", "kernel": "k_csr_fill (K4)", "achieved": k4_bytes / (k4_ms * 1e-3) / 1e9
                              if k4_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
-                             "traffic": 204.0e6 + 55.5e6 if (world == 1 and args.workload == "c3" and args.scale == 1.0) else None,
+                             "traffic": 204.0e6 + 54.5e6 if (world == 1 and args.workload == "c3" and args.scale == 1.0) else None,
                              "frac": k4_bytes / (k4_ms * 1e-3) / 1e9 / hbm_peak if k4_ms > 0 else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
             "e2e": {"value": N / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "h2d_bytes_per_step": h2d,
