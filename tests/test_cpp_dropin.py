@@ -93,3 +93,13 @@ def test_cpp_dropin_matches_c_abi(gpu_ctx):
     assert out["pieces"][0] >= N
     # tests/test_power.cpp:51: the cells clipped to a convex polygon tile it
     assert abs(out["cells_area_sum"][0] - out["pentagon_area"][0]) <= 1e-12
+
+
+def test_header_layer_host_parts():
+    """include/MA/functions.hpp + lite.hpp without any GPU call (tests/cpp/test_lite_host.cpp)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_lite_host")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_lite_host.cpp"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr

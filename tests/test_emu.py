@@ -150,3 +150,17 @@ def test_boundary_segment_path_matches_oracle(oracle_mod, emu_mod, name, scale, 
         m = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], seg=True, mode=order)["mom"]
         k = 3 if order == 1 else 6
         assert np.abs(m[:, :k] - ref[:, :k]).max() <= 1e-10 * np.abs(ref[:, :k]).max()
+
+
+@pytest.mark.parametrize("kmax", [32, 64])
+def test_array_polygon_classes(oracle_mod, emu_mod, kmax):
+    """kmax = 32 / 64 are the capacity classes a cell with more than 16 vertices escalates to: polygons as
+    shifted arrays (clip_rebuild) instead of the packed-order fast path (clip_packed)."""
+    case = common.make_case("c3", 0.0005, "0.3")
+    orc = common.oracle_for(oracle_mod, case)
+    ref = orc.kantorovich(case["w"])
+    check(emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], kmax=kmax, maxv_piece=20 if kmax == 32 else 40), ref,
+          orc.counters())
+    r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], kmax=kmax, seg=True)
+    assert r["flags"] == 0 and common.same_pattern(ref[2], r["H"])
+    assert np.abs(r["g"] - ref[1]).max() <= 1e-10 * np.abs(ref[1]).max()

@@ -252,3 +252,44 @@ def test_full_size_c3_properties_and_two_kernels_agree(gpu_ctx):
     assert np.abs(g1 - g2).max() <= 1e-12 * np.abs(g2).max()
     assert common.same_pattern(H1, H2)
     assert abs(H1 - H2).max() <= 1e-11 * d
+
+
+@pytest.mark.parametrize("kmax", [32, 64])
+def test_larger_capacity_classes(gpu_ctx, oracle_mod, kmax):
+    """The array-polygon kernels a cell with more than 16 vertices escalates to (forced here)."""
+    case = common.make_case("c2", 0.02, "0.5")
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(case["w"])
+    common.load_engine(gpu_ctx, case)
+    gpu_ctx.set_option("kmax", kmax)
+    try:
+        for stats in (False, True):
+            gpu_ctx.set_stats(stats)
+            f1, g1, H1 = gpu_ctx.kantorovich(case["w"])
+            assert abs(f1 - f0) <= 1e-10 * abs(f0)
+            assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
+            assert common.same_pattern(H0, H1)
+            assert abs(H0 - H1).max() <= 1e-10 * np.abs(H0.diagonal()).max()
+    finally:
+        gpu_ctx.set_stats(False)
+        gpu_ctx.set_option("kmax", 16)
+
+
+def test_escalation_on_a_many_sided_cell(gpu_ctx, oracle_mod):
+    """One Dirac surrounded by a ring of 40: its cell has 40 sides, more than the 16-vertex fast class holds."""
+    t = np.linspace(0, 2 * np.pi, 40, endpoint=False)
+    X = np.vstack([[0.5, 0.5], np.c_[0.5 + 0.3 * np.cos(t), 0.5 + 0.3 * np.sin(t)],
+                   np.random.default_rng(3).uniform(0.02, 0.98, (200, 2))])
+    X = X[np.r_[True, np.ones(40, bool), (np.hypot(X[41:, 0] - 0.5, X[41:, 1] - 0.5) > 0.33)]]
+    case = common.make_case("c1", 0.01, "zero")
+    cfg = case["cfg"]
+    orc = oracle_mod.Oracle(cfg["vx"], cfg["vy"], cfg["tri"], case["abc"])
+    orc.set_points(X)
+    w = np.zeros(len(X))
+    f0, g0, H0 = orc.kantorovich(w)
+    gpu_ctx.set_mesh(cfg["vx"], cfg["vy"], cfg["tri"], case["abc"])
+    gpu_ctx.set_points(X)
+    f1, g1, H1 = gpu_ctx.kantorovich(w)
+    assert gpu_ctx.info("kmax") >= 32 and (H0[0] != 0).sum() == 41
+    assert abs(f1 - f0) <= 1e-10 * abs(f0) and np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
+    assert common.same_pattern(H0, H1)
