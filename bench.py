@@ -342,8 +342,9 @@ def main_b200(args, rank, world, local_rank):
             "config": {"workload": workload_name(args), "N": N, "faces": int(case["cfg"]["tri"].shape[0]),
                        "weights": args.weights, "hessian": True, "nnz": nnz_total,
                        "partition": f"{world} Morton tile(s) of Diracs, points/weights/mesh replicated",
-                       "l2": "no flush: one evaluation streams ~0.6 GB (201 MB of face coefficients + 0.4 GB of "
-                             "per-cell tables), larger than the 126 MB L2"},
+                       "l2": "no flush: one evaluation moves ~1 GB through DRAM (ncu: K2 0.45 GB, K3 0.33 GB, K4 0.26 GB of "
+                             "per-cell polygons / slot tables / CSR), several times the 126 MB L2; only the 33.5 MB of vertex "
+                             "densities can stay L2-resident from step to step"},
             "stages_ms": {"prep_K1": stage["prep"] / args.steps, "cells_K2": k2_ms, "pieces_K3": k3_ms,
                           "reduce_scan": stage["reduce"] / args.steps, "csr_K4": k4_ms},
             "roofline": {"bound": "fp64", "kernel": kern_name,
