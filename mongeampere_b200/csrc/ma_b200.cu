@@ -310,7 +310,7 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "filter_tol") c->filter_tol = value;
   else if (n == "persist") c->persist = (int)value;
   else if (n == "abort_on_empty") c->probe_empty = value != 0;
-  else if (n == "rmax") c->rmax = std::min(8, std::max(1, (int)value));
+  else if (n == "rmax") c->rmax = std::min(MA_RING_TABLE_RMAX, std::max(1, (int)value));
   else if (n == "clip_a") c->clip_a = std::max(1, (int)value);
   else if (n == "clip_b") c->clip_b = std::max(1, (int)value);
   else if (n == "refill_at") c->refill_at = std::min(32, std::max(1, (int)value));
@@ -783,7 +783,6 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
         CKR(ensure(c, c->col, (size_t)std::max(h_nnz, 1) * 4, 1.3));
         CKR(ensure(c, c->val, (size_t)std::max(h_nnz, 1) * 8, 1.3));
         if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
-        const int N = c->N;
         switch (c->kmax) {
           case 16: k_csr_fill<16><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, 32 * csr_wpb<16>())), 32 * csr_wpb<16>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
           case 32: k_csr_fill<32><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, 32 * csr_wpb<32>())), 32 * csr_wpb<32>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;

@@ -204,11 +204,8 @@ template <class Poly> struct CellSearch {
       // ring walk: move on to the next non-empty bin of ring r (a few cheap iterations), so that the
       // step below handles a site in (almost) every call
       while (q < nq && j >= jend) {
-        int ox, oy;  // position q of ring r: top row, bottom row, then the two columns
-        const int side = 2 * r + 1;
-        if (q < side) { ox = q - r; oy = -r; }
-        else if (q < 2 * side) { ox = q - side - r; oy = r; }
-        else { const int t = q - 2 * side; ox = (t & 1) ? r : -r; oy = (t >> 1) - r + 1; }
+        int ox, oy;  // position q of ring r, nearest bins first (table)
+        ring_offset(r, q, ox, oy);
         ++q;
         const int cx = bx + ox, cy = by + oy;
         if (cx >= 0 && cx < G && cy >= 0 && cy < G) {

@@ -287,6 +287,43 @@ MA_DEV uint32_t morton_part1(uint32_t v) {
 }
 MA_DEV uint32_t morton2(uint32_t x, uint32_t y) { return morton_part1(x) | (morton_part1(y) << 1); }
 
+// Offsets (ox, oy) of the bins of ring r = 0..8 around a bin, ring after ring, nearest first inside a ring
+// (the ring walk of K2 then meets the true neighbours early and wastes fewer clips).  Ring r starts at entry
+// (2r-1)^2 for r >= 1 (entry 0 for r = 0) and has 8r entries.
+#define MA_RING_TABLE_VALUES \
+    0, 0, 0, -1, -1, 0, 1, 0, 0, 1, -1, -1, 1, -1, -1, 1, 1, 1, 0, -2, -2, 0, 2, 0, 0, 2, -1, -2, 1, -2, -2, -1, \
+    2, -1, -2, 1, 2, 1, -1, 2, 1, 2, -2, -2, 2, -2, -2, 2, 2, 2, 0, -3, -3, 0, 3, 0, 0, 3, -1, -3, 1, -3, -3, -1, \
+    3, -1, -3, 1, 3, 1, -1, 3, 1, 3, -2, -3, 2, -3, -3, -2, 3, -2, -3, 2, 3, 2, -2, 3, 2, 3, -3, -3, 3, -3, -3, 3, \
+    3, 3, 0, -4, -4, 0, 4, 0, 0, 4, -1, -4, 1, -4, -4, -1, 4, -1, -4, 1, 4, 1, -1, 4, 1, 4, -2, -4, 2, -4, -4, -2, \
+    4, -2, -4, 2, 4, 2, -2, 4, 2, 4, -3, -4, 3, -4, -4, -3, 4, -3, -4, 3, 4, 3, -3, 4, 3, 4, -4, -4, 4, -4, -4, 4, \
+    4, 4, 0, -5, -5, 0, 5, 0, 0, 5, -1, -5, 1, -5, -5, -1, 5, -1, -5, 1, 5, 1, -1, 5, 1, 5, -2, -5, 2, -5, -5, -2, \
+    5, -2, -5, 2, 5, 2, -2, 5, 2, 5, -3, -5, 3, -5, -5, -3, 5, -3, -5, 3, 5, 3, -3, 5, 3, 5, -4, -5, 4, -5, -5, \
+    -4, 5, -4, -5, 4, 5, 4, -4, 5, 4, 5, -5, -5, 5, -5, -5, 5, 5, 5, 0, -6, -6, 0, 6, 0, 0, 6, -1, -6, 1, -6, -6, \
+    -1, 6, -1, -6, 1, 6, 1, -1, 6, 1, 6, -2, -6, 2, -6, -6, -2, 6, -2, -6, 2, 6, 2, -2, 6, 2, 6, -3, -6, 3, -6, \
+    -6, -3, 6, -3, -6, 3, 6, 3, -3, 6, 3, 6, -4, -6, 4, -6, -6, -4, 6, -4, -6, 4, 6, 4, -4, 6, 4, 6, -5, -6, 5, \
+    -6, -6, -5, 6, -5, -6, 5, 6, 5, -5, 6, 5, 6, -6, -6, 6, -6, -6, 6, 6, 6, 0, -7, -7, 0, 7, 0, 0, 7, -1, -7, 1, \
+    -7, -7, -1, 7, -1, -7, 1, 7, 1, -1, 7, 1, 7, -2, -7, 2, -7, -7, -2, 7, -2, -7, 2, 7, 2, -2, 7, 2, 7, -3, -7, \
+    3, -7, -7, -3, 7, -3, -7, 3, 7, 3, -3, 7, 3, 7, -4, -7, 4, -7, -7, -4, 7, -4, -7, 4, 7, 4, -4, 7, 4, 7, -5, \
+    -7, 5, -7, -7, -5, 7, -5, -7, 5, 7, 5, -5, 7, 5, 7, -6, -7, 6, -7, -7, -6, 7, -6, -7, 6, 7, 6, -6, 7, 6, 7, \
+    -7, -7, 7, -7, -7, 7, 7, 7, 0, -8, -8, 0, 8, 0, 0, 8, -1, -8, 1, -8, -8, -1, 8, -1, -8, 1, 8, 1, -1, 8, 1, 8, \
+    -2, -8, 2, -8, -8, -2, 8, -2, -8, 2, 8, 2, -2, 8, 2, 8, -3, -8, 3, -8, -8, -3, 8, -3, -8, 3, 8, 3, -3, 8, 3, \
+    8, -4, -8, 4, -8, -8, -4, 8, -4, -8, 4, 8, 4, -4, 8, 4, 8, -5, -8, 5, -8, -8, -5, 8, -5, -8, 5, 8, 5, -5, 8, \
+    5, 8, -6, -8, 6, -8, -8, -6, 8, -6, -8, 6, 8, 6, -6, 8, 6, 8, -7, -8, 7, -8, -8, -7, 8, -7, -8, 7, 8, 7, -7, \
+    8, 7, 8, -8, -8, 8, -8, -8, 8, 8, 8
+constexpr int MA_RING_TABLE_RMAX = 8;
+static const signed char ring_table_host[] = {MA_RING_TABLE_VALUES};
+#ifdef __CUDACC__
+__device__ const signed char ring_table_dev[] = {MA_RING_TABLE_VALUES};
+#endif
+MA_DEV void ring_offset(int r, int q, int &ox, int &oy) {
+  const int e = 2 * ((r == 0 ? 0 : (2 * r - 1) * (2 * r - 1)) + q);
+#ifdef __CUDA_ARCH__
+  ox = ring_table_dev[e]; oy = ring_table_dev[e + 1];
+#else
+  ox = ring_table_host[e]; oy = ring_table_host[e + 1];
+#endif
+}
+
 // Can a half-plane of a site at squared distance >= d2 whose weight satisfies w_i - w_j >= dw cut a
 // polygon contained in the disk of squared radius R2 around y_i?  The bisector's signed distance
 // from y_i is t = (d^2 + w_i - w_j) / (2 d); it cannot cut iff t >= R.
