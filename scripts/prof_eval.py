@@ -27,6 +27,9 @@ if wfile is not None:
     else:
         case["w"] = np.load(wfile)
 ctx.set_weights(case["w"])
+if os.environ.get("MA_PART"):  # e.g. MA_PART=0,8: evaluate only Morton tile 0 of 8 (what one rank of an 8-GPU run does)
+    r, n = map(int, os.environ["MA_PART"].split(","))
+    ctx.set_partition(r, n)
 for _ in range(nev):
     ctx.evaluate(True)
 print("nnz", ctx.info("nnz"), "mass_sum", ctx.info("mass_sum"))
