@@ -173,7 +173,20 @@ int ma_get_counters(ma_ctx *ctx, int64_t *c /* 8 */);
 int ma_flush_l2(ma_ctx *ctx, size_t bytes);
 /* DFMA throughput micro-benchmark (FLOP/s), the fp64 roofline denominator "of measured". */
 int ma_measure_fp64_peak(ma_ctx *ctx, double *flops_per_s);
-/* Option knobs: "kmax", "strategy" (0 auto, 1 fused thread-per-cell, 2 warp-per-cell), "cg_rtol", ... */
+/* Option knobs (ma_set_option; defaults in parentheses):
+ *   "kmax" (16)            capacity class every evaluation starts from: 16 (packed-order polygons), 32, 64; escalated
+ *                          automatically when a cell has more vertices
+ *   "strategy" (0)         0: grid meshes use the boundary-segment kernel k_seg, general meshes k_pieces; 2: k_pieces always
+ *   "bin_target" (1)       average Diracs per leaf bin (upper bound), takes effect at the next ma_set_points
+ *   "rmax" (6)             rings of leaf bins K2 walks before it turns to the quadtree
+ *   "persist" (1)          K2 with persistent lanes (k_cells_persist) or one cell per lane (0)
+ *   "persist_waves", "persist_min_chunk", "clip_a", "clip_b", "refill_at"   scheduling of k_cells_persist
+ *   "cg_rtol" (1e-12), "cg_maxit" (200000)   PCG stopping rule, relative to |g|
+ *   "cg_single" (0), "pcg_persist" (0), "pcg_blocks_per_sm"   alternative CG kernels (measured no faster)
+ *   "filter_tol" (1e-11)   relative threshold below which k_pieces re-decides a sign in double-double
+ *   "abort_on_empty" (0)   see ma_cells_build
+ * Read-outs (ma_get_info): "N", "nF", "nnz", "kmax", "levels", "mesh_kind", "strategy", "sm_count", "fval", "mass_sum",
+ *   "mass_min", "cg_iters", "launches", "cell_lo", "cell_hi", "aborted". */
 int ma_set_option(ma_ctx *ctx, const char *name, double value);
 double ma_get_info(ma_ctx *ctx, const char *name);
 
