@@ -60,7 +60,7 @@ struct ma_ctx {
 
   // points
   int N = 0;
-  Buf x, y, xs, ys, perm, pos, code, bin_count, bin_start, wmax;
+  Buf x, y, xs, ys, perm, pos, code, bin_count, bin_start, bin_rm, wmax;
   Buf code_s, pre0, pre1, fs_tiles, nodeG, nodeA, wstat;  // per-node supporting planes (ma_geom.cuh)
   bool abort_on_empty = false, aborted = false;
   bool probe_empty = false;  // option "abort_on_empty": ma_cells_build stops at the first empty cell and reports it
@@ -272,7 +272,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
-                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->cgbar, &c->cgw1, &c->cgpp};
+                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->cgbar, &c->cgw1, &c->cgpp, &c->bin_rm};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
@@ -526,6 +526,8 @@ extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y)
   k_bin_scatter<<<cdiv(N, 256), 256, 0, c->stream>>>(c->code.as<unsigned>(), N, c->bin_start.as<int>(),
                                                      c->bin_count.as<int>(), c->perm.as<int>());
   k_bin_sort<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(c->bin_start.as<int>(), (int)nb, c->perm.as<int>());
+  CKR(ensure(c, c->bin_rm, nb * 8));
+  k_bin_rowmajor<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(G, c->bin_start.as<int>(), c->bin_rm.as<int>());
   k_gather_points<<<cdiv(N, 256), 256, 0, c->stream>>>(c->x.as<double>(), c->y.as<double>(), c->perm.as<int>(), N,
                                                        c->xs.as<double>(), c->ys.as<double>(), c->pos.as<int>());
   CK(cudaMemsetAsync(c->w.p, 0, (size_t)N * 8, c->stream));
@@ -557,6 +559,7 @@ int fill_params(ma_ctx *c, Params &p) {
   p.xs = c->xs.as<double>(); p.ys = c->ys.as<double>(); p.ws = c->ws.as<double>();
   p.L = c->L; p.px0 = c->px0; p.py0 = c->py0; p.ph = c->ph;
   p.bin_start = c->bin_start.as<int>();
+  p.bin_rm = c->bin_rm.as<int>();
   p.wmax = c->wmax.as<double>();
   p.wstat = c->wstat.as<double>();
   p.nodeG = c->nodeG.as<double>();

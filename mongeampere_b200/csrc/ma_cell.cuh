@@ -30,6 +30,7 @@ struct Params {
   int L;
   double px0, py0, ph;
   const int *bin_start;
+  const int *bin_rm;  // row-major copy for the ring walk: bin (cx, cy) holds the sites [bin_rm[2q], bin_rm[2q+1]), q = cy * 2^L + cx
   const double *wmax;
   const double *wstat;                // {sum, sum of squares, min, max} of the weights of this evaluation
   const double *nodeG;                // 2 per node: least-squares weight gradient (ma_geom.cuh)
@@ -201,16 +202,41 @@ template <class Poly> struct CellSearch {
     const int G = 1 << p.L;
     const int RMAX = p.rmax;
     if (phase == 0 && j >= jend) {
-      // ring walk: move on to the next non-empty bin of ring r (a few cheap iterations), so that the
-      // step below handles a site in (almost) every call
-      while (q < nq && j >= jend) {
-        int ox, oy;  // position q of ring r, nearest bins first (table)
-        ring_offset(r, q, ox, oy);
-        ++q;
-        const int cx = bx + ox, cy = by + oy;
-        if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
-          const unsigned code = morton2((unsigned)cx, (unsigned)cy);
-          j = p.bin_start[code]; jend = p.bin_start[code + 1];
+      // ring walk: move on to the next non-empty bin (a few cheap iterations), closing a ring when its last
+      // bin is behind us, so that the step below handles a site in (almost) every call
+      while (phase == 0 && j >= jend) {
+        if (q == nq) {  // ring r is complete: every site inside the (2r+1)^2 block has been seen
+          rdone = r;
+          // all bins covered?  (tiny grids)
+          const bool all = bx - r <= 0 && bx + r >= G - 1 && by - r <= 0 && by + r >= G - 1;
+          // distance from y_i to the block boundary (exact for interior bins, a lower bound at the grid's edge)
+          const double ex = xi - (p.px0 + (double)bx * p.ph), ey = yi - (p.py0 + (double)by * p.ph);
+          const double emin = fmin(fmax(fmin(fmin(ex, p.ph - ex), fmin(ey, p.ph - ey)), 0.0), p.ph);  // to the nearest side of the own bin
+          const double rho = (double)r * p.ph + emin, rho2 = rho * rho, rn = rho + p.ph;
+          if (all || cannot_cut(rho2, dw_glob, R2)) {
+            phase = 2;  // nothing farther than rho can cut
+          } else if (r == RMAX || (r >= 1 && rn * rn + dw_glob <= 0.0)) {
+            // (one more ring could not certify anything if even a tiny polygon fails; ring 1 is always
+            // walked: the true neighbours are the nearby Diracs whatever the weights do, and the rings
+            // are the cheap way to find them)
+            phase = 1;  // first tree pass: everything within rho is done
+            prev2 = rho2;
+            cap = 2.0 * fmax(rho, p.ph);
+            cut_in_pass = true;
+            pass = 0;
+            sp = -1;  // "begin a pass"
+          } else {
+            ++r; q = 0; nq = 8 * r;
+          }
+        } else {
+          int ox, oy;  // position q of ring r, nearest bins first (table)
+          ring_offset(r, q, ox, oy);
+          ++q;
+          const int cx = bx + ox, cy = by + oy;
+          if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
+            const int2 se = reinterpret_cast<const int2 *>(p.bin_rm)[(size_t)cy * G + cx];  // no Morton encoding, one load
+            j = se.x; jend = se.y;
+          }
         }
       }
     }
@@ -241,34 +267,7 @@ template <class Poly> struct CellSearch {
           }
         }
       }
-    } else if (phase == 0) {
-      // ---- step kind 2: the next bin of the ring walk
-      if (q == nq) {  // ring r is complete
-        rdone = r;
-        // distance from y_i to the part of the block boundary that has bins behind it
-        double rho = POS_INF;
-        if (bx - r > 0) rho = fmin(rho, xi - (p.px0 + (double)(bx - r) * p.ph));
-        if (bx + r < G - 1) rho = fmin(rho, (p.px0 + (double)(bx + r + 1) * p.ph) - xi);
-        if (by - r > 0) rho = fmin(rho, yi - (p.py0 + (double)(by - r) * p.ph));
-        if (by + r < G - 1) rho = fmin(rho, (p.py0 + (double)(by + r + 1) * p.ph) - yi);
-        const double rhoc = fmax(rho, 0.0), rho2 = rhoc * rhoc, rn = rhoc + p.ph;
-        if (rho == POS_INF || cannot_cut(rho2, dw_glob, R2)) {
-          phase = 2;  // the block covers every bin / nothing farther than rho can cut
-        } else if (r == RMAX || (r >= 1 && rn * rn + dw_glob <= 0.0)) {
-          // (one more ring could not certify anything if even a tiny polygon fails; ring 1 is always
-          // walked: the true neighbours are the nearby Diracs whatever the weights do, and the rings
-          // are the cheap way to find them)
-          phase = 1;  // first tree pass: everything within rho is done
-          prev2 = rho2;
-          cap = 2.0 * fmax(rhoc, p.ph);
-          cut_in_pass = true;
-          pass = 0;
-          sp = -1;  // "begin a pass"
-        } else {
-          ++r; q = 0; nq = 8 * r;
-        }
-      }
-    } else {
+    } else if (phase == 1) {
       // ---- step kind 3: the next node of the tree walk
       if (sp <= 0) {
         bool go = true;

@@ -195,6 +195,14 @@ __global__ void k_bin_sort(const int *__restrict__ bin_start, int nbins, int *__
     perm[j + 1] = v;
   }
 }
+// row-major (start, end) table of the leaf bins for K2's ring walk
+__global__ void k_bin_rowmajor(int G, const int *__restrict__ bin_start, int *__restrict__ bin_rm) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)G * G) return;
+  const unsigned cx = (unsigned)(q % G), cy = (unsigned)(q / G);
+  const unsigned code = morton2(cx, cy);
+  reinterpret_cast<int2 *>(bin_rm)[q] = make_int2(bin_start[code], bin_start[code + 1]);
+}
 __global__ void k_gather_points(const double *__restrict__ x, const double *__restrict__ y,
                                 const int *__restrict__ perm, int n, double *__restrict__ xs, double *__restrict__ ys,
                                 int *__restrict__ pos) {

@@ -164,6 +164,14 @@ extern "C" int emu_eval(int mesh_kind,
   p.nodeG = nodeG.data(); p.nodeA = nodeA.data(); p.abort_flag = &no_abort; p.abort_on_empty = 0; p.clip_a = p.clip_b = 1; p.refill_at = 8; p.rmax = 3;
   p.N = N; p.xs = xs.data(); p.ys = ys.data(); p.ws = ws.data();
   p.cell_lo = 0; p.cell_hi = N;
+  std::vector<int> bin_rm(2 * nb);
+  for (int cy = 0; cy < G; ++cy)
+    for (int cx = 0; cx < G; ++cx) {
+      unsigned code = morton2(cx, cy);
+      bin_rm[2 * ((size_t)cy * G + cx)] = bin_start[code];
+      bin_rm[2 * ((size_t)cy * G + cx) + 1] = bin_start[code + 1];
+    }
+  p.bin_rm = bin_rm.data();
   p.bin_start = bin_start.data(); p.wmax = wmax.data();
   double wstat[4] = {0, 0, 1e300, -1e300};
   for (int k = 0; k < N; ++k) { wstat[0] += ws[k]; wstat[1] += ws[k] * ws[k]; wstat[2] = std::min(wstat[2], ws[k]); wstat[3] = std::max(wstat[3], ws[k]); }
