@@ -293,3 +293,27 @@ def test_escalation_on_a_many_sided_cell(gpu_ctx, oracle_mod):
     assert gpu_ctx.info("kmax") >= 32 and (H0[0] != 0).sum() == 41
     assert abs(f1 - f0) <= 1e-10 * abs(f0) and np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
     assert common.same_pattern(H0, H1)
+
+
+def test_closed_forms_one_and_two_diracs(gpu_ctx):
+    """N = 1: the cell is the whole domain; N = 2 on the unit square with uniform density: masses split by the
+    bisector, H_01 = -len(bisector ∩ square) / (2 |y_0 - y_1|) (kantorovich.hpp:117-121)."""
+    vx = np.array([0.0, 1.0, 1.0, 0.0]); vy = np.array([0.0, 0.0, 1.0, 1.0])
+    tri = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    abc = np.array([[0, 0, 1.0], [0, 0, 1.0]])
+    gpu_ctx.set_mesh(vx, vy, tri, abc)
+    gpu_ctx.set_points(np.array([[0.3, 0.6]]))
+    f, g, H = gpu_ctx.kantorovich(np.array([0.25]))
+    assert abs(g[0] - 1.0) <= 1e-14 and H.nnz == 0
+    # ∫ |x - y|^2 over the square = 1/3 - y.(1,1) + |y|^2  => f = w m - cost
+    cost = 2.0 / 3.0 - (0.3 + 0.6) + (0.09 + 0.36)
+    assert abs(f - (0.25 - cost)) <= 1e-14
+    gpu_ctx.set_points(np.array([[0.25, 0.5], [0.75, 0.5]]))
+    f, g, H = gpu_ctx.kantorovich(np.array([0.0, 0.1]))  # bisector x = 0.5 - 0.1 / (2 * 0.5) = 0.4
+    assert np.allclose(g, [0.4, 0.6], rtol=0, atol=1e-14)
+    Hd = H.toarray()
+    assert np.allclose(Hd, [[1.0, -1.0], [-1.0, 1.0]], rtol=0, atol=1e-14)  # length 1 / (2 * 0.5)
+    # coincident Diracs: the heavier one keeps the cell, the other is hidden (trap T2: empty row)
+    gpu_ctx.set_points(np.array([[0.5, 0.5], [0.5, 0.5], [0.2, 0.2]]))
+    f, g, H = gpu_ctx.kantorovich(np.array([0.0, 0.05, 0.0]))
+    assert g[0] == 0.0 and abs(g.sum() - 1.0) <= 1e-14 and H[0].nnz == 0
