@@ -99,9 +99,21 @@ __global__ void __launch_bounds__(PCG_NT) k_pcg_A(PcgState s, int it) {
     double pi = 0.0, qi = 0.0;
     if (i != s.ground) {
       pi = z[i] + beta * pold[i];
-      for (int k = s.rowptr[i]; k < s.rowptr[i + 1]; ++k) {
-        int j = s.col[k];
-        qi += s.val[k] * (z[j] + beta * pold[j]);  // z, p_old are 0 at the grounded index
+      // 4 entries per trip, their loads issued together: a row is ~7 entries and the latency of this kernel is the
+      // chain rowptr -> (col, val) -> (z, p_old) gathers, not bandwidth
+      const int k1 = s.rowptr[i + 1];
+      for (int k = s.rowptr[i]; k < k1; k += 4) {
+        int j[4];
+        double v[4], a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool in = k + u < k1;
+          j[u] = in ? s.col[k + u] : i;
+          v[u] = in ? s.val[k + u] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = z[j[u]] + beta * pold[j[u]];  // z, p_old are 0 at the grounded index
+        qi += (v[0] * a[0] + v[1] * a[1]) + (v[2] * a[2] + v[3] * a[3]);
       }
     }
     pnew[i] = pi;
