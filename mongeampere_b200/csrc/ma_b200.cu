@@ -30,6 +30,8 @@ struct Buf {
 struct ma_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // copy stream of ma_get_hessian_csr
+  cudaEvent_t ev_chunk[8] = {};
   std::string err;
   int sm_count = 148;
 
@@ -250,6 +252,8 @@ extern "C" int ma_create(ma_ctx **out, int device) {
   *out = c;
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  for (auto &ev : c->ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -278,6 +282,9 @@ extern "C" void ma_destroy(ma_ctx *c) {
       if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_user)
       if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_chunk)
+      if (ev) cudaEventDestroy(ev);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     if (c->hs) cudaFreeHost(c->hs);
   }
@@ -891,16 +898,30 @@ extern "C" int ma_get_hessian_csr(ma_ctx *c, int *rowptr, int *col, double *val)
   k_rowcnt_to_caller<<<cdiv(N, 256), 256, 0, c->stream>>>(c->rowptr.as<int>(), c->pos.as<int>(), N,
                                                           c->scratch_i.as<int>());
   CKR(scan_i32(c, c->scratch_i.as<int>(), c->cptr.as<int>(), N));
-  k_csr_to_caller<<<cdiv(N, 128), 128, 0, c->stream>>>(N, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(),
-                                                       c->pos.as<int>(), c->perm.as<int>(), c->cptr.as<int>(),
-                                                       c->ccol.as<int>(), c->cval.as<double>());
-  c->launches += 2;
-  CK(cudaGetLastError());
+  c->launches += 1;
+  // the row pointers first: the host needs them to know which byte ranges of col / val belong to which rows
   CK(cudaMemcpyAsync(rowptr, c->cptr.p, (size_t)(N + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (c->nnz) {
-    CK(cudaMemcpyAsync(col, c->ccol.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(val, c->cval.p, (size_t)c->nnz * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  // then chunk by chunk: rows of chunk q are put in caller order on the main stream while the copy engine
+  // ships chunk q-1 on the second stream (the transfer is PCIe-bound, the conversion hides behind it)
+  const int Q = (c->nnz > (1 << 20)) ? 8 : 1;
+  for (int q = 0; q < Q; ++q) {
+    const int r0 = (int)((long long)N * q / Q), r1 = (int)((long long)N * (q + 1) / Q);
+    if (r1 <= r0) continue;
+    k_csr_to_caller<<<cdiv(r1 - r0, 128), 128, 0, c->stream>>>(r0, r1, c->rowptr.as<int>(), c->col.as<int>(),
+                                                             c->val.as<double>(), c->pos.as<int>(), c->perm.as<int>(),
+                                                             c->cptr.as<int>(), c->ccol.as<int>(), c->cval.as<double>());
+    c->launches += 1;
+    CK(cudaEventRecord(c->ev_chunk[q], c->stream));
+    CK(cudaStreamWaitEvent(c->stream2, c->ev_chunk[q], 0));
+    const size_t e0 = (size_t)rowptr[r0], e1 = (size_t)rowptr[r1];
+    if (e1 > e0) {
+      CK(cudaMemcpyAsync(col + e0, c->ccol.as<int>() + e0, (e1 - e0) * 4, cudaMemcpyDeviceToHost, c->stream2));
+      CK(cudaMemcpyAsync(val + e0, c->cval.as<double>() + e0, (e1 - e0) * 8, cudaMemcpyDeviceToHost, c->stream2));
+    }
   }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream2));
   CK(cudaStreamSynchronize(c->stream));
   return MA_OK;
 }

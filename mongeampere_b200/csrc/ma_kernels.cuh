@@ -804,11 +804,12 @@ __global__ void k_rowcnt_to_caller(const int *__restrict__ rowptr_sorted, const 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { int k = pos[i]; cnt_caller[i] = rowptr_sorted[k + 1] - rowptr_sorted[k]; }
 }
-__global__ void k_csr_to_caller(int n, const int *__restrict__ rowptr_s, const int *__restrict__ col_s,
+// caller rows [r0, n)
+__global__ void k_csr_to_caller(int r0, int n, const int *__restrict__ rowptr_s, const int *__restrict__ col_s,
                                 const double *__restrict__ val_s, const int *__restrict__ pos,
                                 const int *__restrict__ perm, const int *__restrict__ rowptr_c, int *__restrict__ col_c,
                                 double *__restrict__ val_c) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int k = pos[i];
   int s = rowptr_s[k], e = rowptr_s[k + 1], o = rowptr_c[i];
