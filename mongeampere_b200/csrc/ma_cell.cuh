@@ -1,14 +1,16 @@
-// ma_cell.cuh — per-thread / per-lane work of the two evaluation kernels, written as
-// __host__ __device__ functions so that tests/emu can run the very same code serially on the CPU.
+// ma_cell.cuh — per-thread / per-lane work of the evaluation kernels, written as __host__ __device__
+// functions so that tests/emu can run the very same code serially on the CPU.
 //
-//   cell_build   (K2)  replaces CGAL Regular_triangulation_2's neighbour circulator
-//                      (kantorovich.hpp:65-72, vti.hpp:265): builds the power cell of Dirac i inside
-//                      the mesh bounding box by clipping against candidate sites found by a
-//                      nearest-first walk over a quadtree of Morton-ordered bins, pruned with the
-//                      per-node maximum weight ("security radius").
-//   lane_pieces  (K3)  replaces the overlay traversal + callbacks (vti.hpp:250-305,
+//   CellSearch / cell_build   (K2)  replaces CGAL Regular_triangulation_2's neighbour circulator
+//                      (kantorovich.hpp:65-72, vti.hpp:265): builds the power cell of Dirac i inside the
+//                      mesh bounding box by clipping against candidate sites found by a ring walk over
+//                      the leaf bins (security-radius certificate) and, when the weights
+//                      have a gradient, a quadtree walk pruned by per-node supporting planes.  A
+//                      resumable per-lane state machine (search_step / clip) driven by warp votes.
+//   lane_pieces  (K3, general meshes)  replaces the overlay traversal + callbacks (vti.hpp:250-305,
 //                      kantorovich.hpp:87-136, lloyd.hpp:48-68,91-122): one lane clips candidate
 //                      triangles against the cell's half-plane table and integrates the pieces.
+//                      (Grid meshes: ma_seg.cuh.)
 #pragma once
 #include "ma_geom.cuh"
 
