@@ -1213,7 +1213,10 @@ int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double 
               int ground, double *d_out, int *iters_out, double *relres_out) {
   if (c->cg_single) return cg1_solve(c, n, rowptr, col, val, g, sign, ground, d_out, iters_out, relres_out);
   PcgState s;
-  const int nblocks = std::min(PCG_MAX_BLOCKS, std::max(1, cdiv(n, PCG_NT)));
+  // one resident wave at most (the kernels are grid-stride loops): a second, partial wave only adds a tail
+  int per_sm = 8;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_A, PCG_NT, 0));
+  const int nblocks = std::min(std::min(PCG_MAX_BLOCKS, std::max(1, per_sm) * c->sm_count), std::max(1, cdiv(n, PCG_NT)));
   CKR(ensure(c, c->dinv, (size_t)n * 8)); CKR(ensure(c, c->cgx, (size_t)n * 8)); CKR(ensure(c, c->cgr, (size_t)n * 8));
   CKR(ensure(c, c->cgz, (size_t)n * 8)); CKR(ensure(c, c->cgp0, (size_t)n * 8)); CKR(ensure(c, c->cgp1, (size_t)n * 8));
   CKR(ensure(c, c->cgq, (size_t)n * 8));
