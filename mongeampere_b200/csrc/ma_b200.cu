@@ -85,6 +85,7 @@ struct ma_ctx {
 
   // pcg
   Buf dinv, cgx, cgr, cgz, cgp0, cgp1, cgq, cgw1, cgpp, part_pq, part_rz, part_rr, scal, cgflag, cgbar;
+  int cg_warm = 1;    // Newton: start each PCG from (1 - tau) times the previous direction
   int cg_single = 0;  // 1: single-reduction CG (one kernel per iteration); measured no faster than the two-kernel PCG (the time is in the kernels, not the launches)
   int pcg_persist = 0, pcg_blocks_per_sm = 4;  // persistent cooperative PCG: measured slower than the graph of 2-kernel iterations (grid barriers cost more than launches)
   Buf nu_s, x0_s, d_s, g_s;
@@ -313,6 +314,7 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "cg_maxit") c->cg_maxit = (int)value;
   else if (n == "pcg_persist") c->pcg_persist = (int)value;
   else if (n == "cg_single") c->cg_single = (int)value;
+  else if (n == "cg_warm") c->cg_warm = (int)value;
   else if (n == "pcg_blocks_per_sm") c->pcg_blocks_per_sm = std::max(1, (int)value);
   else if (n == "filter_tol") c->filter_tol = value;
   else if (n == "persist") c->persist = (int)value;
@@ -1210,7 +1212,8 @@ int cg1_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double 
 }
 
 int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double *val, const double *g, double sign,
-              int ground, double *d_out, int *iters_out, double *relres_out) {
+              int ground, double *d_out, int *iters_out, double *relres_out, const double *x0 = nullptr,
+              double x0_scale = 1.0) {
   if (c->cg_single) return cg1_solve(c, n, rowptr, col, val, g, sign, ground, d_out, iters_out, relres_out);
   PcgState s;
   // one resident wave at most (the kernels are grid-stride loops): a second, partial wave only adds a tail
@@ -1229,7 +1232,8 @@ int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double 
   s.scal = c->scal.as<double>(); s.nblocks = nblocks; s.flag = c->cgflag.as<int>();
   CK(cudaMemsetAsync(c->cgflag.p, 0, 16, c->stream));
   CK(cudaMemsetAsync(c->part_rz.p, 0, (size_t)2 * nblocks * 8, c->stream));
-  k_pcg_init<<<nblocks, PCG_NT, 0, c->stream>>>(s, g, sign);
+  k_pcg_init<<<nblocks, PCG_NT, 0, c->stream>>>(s, g, sign, x0, x0_scale);
+  if (x0) { k_pcg_resid<<<nblocks, PCG_NT, 0, c->stream>>>(s); c->launches++; }
   k_pcg_init2<<<1, PCG_NT, 0, c->stream>>>(s);
   c->launches += 2;
   CK(cudaGetLastError());
@@ -1433,13 +1437,21 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
     return g;
   }();
   int rc_final = MA_OK;
+  bool have_dir = false;
+  double last_alpha = 0.0;
   while (gnorm >= eps_g && niter++ <= maxiter) {  // :150-151 (including the maxiter+1 quirk, T6)
     int it = 0;
     double relres = 0;
     // d = -solve_laplacian_matrix(h, g)   :153   (internal order)
     auto t0p = now();
+    // warm start: after a damped step tau the gradient is ~(1 - tau) g and the Hessian has hardly moved, so the new
+    // direction is close to (1 - tau) times the last one (still in d_s)
+    const bool warm = c->cg_warm && have_dir;
+    if (warm) CK(cudaMemcpyAsync(c->scratch_d.p, c->d_s.p, (size_t)N * 8, cudaMemcpyDeviceToDevice, c->stream));
     int rc = pcg_solve(c, N, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(), c->g_s.as<double>(), -1.0,
-                       ground, c->d_s.as<double>(), &it, &relres);
+                       ground, c->d_s.as<double>(), &it, &relres, warm ? c->scratch_d.as<double>() : nullptr,
+                       1.0 - last_alpha);
+    have_dir = true;
     t_pcg += secs(t0p, now());
     cg_total += it;
     if (rc != MA_OK) return finish(rc);
@@ -1465,6 +1477,7 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
         break;
       }
     }
+    last_alpha = alpha;
     if (verbose)
       fprintf(stderr, "it %zu: f=%.15g |df|=%g min(m)=%g tau = %g eval = %zu cg = %d\n", niter, fx, gnorm, nu_min,
               alpha, neval, it);

@@ -54,7 +54,10 @@ __device__ __forceinline__ double sum_partials(const double *part, int nb, doubl
 }
 
 // dinv, r = g (0 at ground), z = r*dinv, p0 = z, x = 0, partial rz (parity 0), partial gg
-__global__ void __launch_bounds__(PCG_NT) k_pcg_init(PcgState s, const double *__restrict__ g, double sign) {
+// x0 != nullptr: start from x = scale * x0 (the Newton loop passes the previous direction: with a damped step tau
+// the next direction is close to (1 - tau) times the last one); k_pcg_resid then turns r into b - A x.
+__global__ void __launch_bounds__(PCG_NT) k_pcg_init(PcgState s, const double *__restrict__ g, double sign,
+                                                      const double *__restrict__ x0, double scale) {
   __shared__ double sh[PCG_NT / 32];
   double rz = 0.0, gg = 0.0;
   for (int i = blockIdx.x * PCG_NT + threadIdx.x; i < s.n; i += gridDim.x * PCG_NT) {
@@ -68,11 +71,29 @@ __global__ void __launch_bounds__(PCG_NT) k_pcg_init(PcgState s, const double *_
       else di = 1.0 / d;
     }
     double zi = ri * di;
-    s.dinv[i] = di; s.x[i] = 0.0; s.r[i] = ri; s.z[i] = zi; s.p[0][i] = 0.0; s.p[1][i] = 0.0;
+    s.dinv[i] = di; s.x[i] = (x0 && i != s.ground) ? scale * x0[i] : 0.0; s.r[i] = ri; s.z[i] = zi; s.p[0][i] = 0.0; s.p[1][i] = 0.0;
     rz += ri * zi; gg += ri * ri;
   }
   double a = block_sum(rz, sh), b = block_sum(gg, sh);
   if (threadIdx.x == 0) { s.part_rz[blockIdx.x] = a; s.part_rr[blockIdx.x] = b; }
+}
+// r = b - A x for a non-zero starting point (same grid as k_pcg_init: it overwrites that kernel's r.z partials)
+__global__ void __launch_bounds__(PCG_NT) k_pcg_resid(PcgState s) {
+  __shared__ double sh[PCG_NT / 32];
+  const double *__restrict__ x = s.x;
+  double rz = 0.0;
+  for (int i = blockIdx.x * PCG_NT + threadIdx.x; i < s.n; i += gridDim.x * PCG_NT) {
+    double ri = 0.0;
+    if (i != s.ground) {
+      ri = s.r[i];
+      for (int k = s.rowptr[i]; k < s.rowptr[i + 1]; ++k) ri -= s.val[k] * x[s.col[k]];  // x is 0 at the grounded index
+    }
+    const double zi = ri * s.dinv[i];
+    s.r[i] = ri; s.z[i] = zi;
+    rz += ri * zi;
+  }
+  double a = block_sum(rz, sh);
+  if (threadIdx.x == 0) s.part_rz[blockIdx.x] = a;
 }
 __global__ void __launch_bounds__(PCG_NT) k_pcg_init2(PcgState s) {
   __shared__ double sh[PCG_NT / 32];
