@@ -179,6 +179,7 @@ int ma_measure_fp64_peak(ma_ctx *ctx, double *flops_per_s);
  *   "strategy" (0)         0: grid meshes use the boundary-segment kernel k_seg, general meshes k_pieces; 2: k_pieces always
  *   "bin_target" (1)       average Diracs per leaf bin (upper bound), takes effect at the next ma_set_points
  *   "rmax" (6)             rings of leaf bins K2 walks before it turns to the quadtree
+ *   "rtree" (4)            rings it walks in any case, even when the ring certificate cannot succeed (weights with a gradient)
  *   "persist" (1)          K2 with persistent lanes (k_cells_persist) or one cell per lane (0)
  *   "persist_waves", "persist_min_chunk", "clip_a", "clip_b", "refill_at"   scheduling of k_cells_persist
  *   "cg_rtol" (1e-12), "cg_maxit" (200000)   PCG stopping rule, relative to |g|

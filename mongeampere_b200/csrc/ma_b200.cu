@@ -44,7 +44,7 @@ struct ma_ctx {
   int cg_maxit = 200000;
   double filter_tol = 1e-11;
   int profiling = 0, stats = 0, trace = 0;
-  int clip_a = 2, clip_b = 1, refill_at = 8, rmax = 6;
+  int clip_a = 2, clip_b = 1, refill_at = 8, rmax = 6, rtree = 4;
   int persist = 1, persist_waves = 3, persist_min_chunk = 32;  // K2 with persistent lanes (k_cells_persist)
   int strategy = 0;  // 0 auto (grid mesh: fused segment kernel, general mesh: pieces), 2: pieces always
   int part_rank = 0, part_n = 1;  // Morton tile of the Diracs this context evaluates
@@ -320,6 +320,7 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "persist") c->persist = (int)value;
   else if (n == "abort_on_empty") c->probe_empty = value != 0;
   else if (n == "rmax") c->rmax = std::min(MA_RING_TABLE_RMAX, std::max(1, (int)value));
+  else if (n == "rtree") c->rtree = std::min(MA_RING_TABLE_RMAX, std::max(0, (int)value));
   else if (n == "clip_a") c->clip_a = std::max(1, (int)value);
   else if (n == "clip_b") c->clip_b = std::max(1, (int)value);
   else if (n == "refill_at") c->refill_at = std::min(32, std::max(1, (int)value));
@@ -575,7 +576,7 @@ int fill_params(ma_ctx *c, Params &p) {
   p.nodeA = c->nodeA.as<unsigned long long>();
   p.abort_flag = c->flags.as<int>() + 1;
   p.abort_on_empty = c->abort_on_empty ? 1 : 0;
-  p.clip_a = c->clip_a; p.clip_b = c->clip_b; p.refill_at = c->refill_at; p.rmax = c->rmax;
+  p.clip_a = c->clip_a; p.clip_b = c->clip_b; p.refill_at = c->refill_at; p.rmax = c->rmax; p.rtree = std::min(c->rtree, c->rmax);
   for (int k = 0; k < 4; ++k) p.bb[k] = c->bb[k];
   p.mesh_kind = c->mesh_kind;
   p.nF = c->nF;

@@ -39,6 +39,7 @@ struct Params {
   const unsigned long long *nodeA;    // per node: dkey(alpha_B)
   int refill_at;                      // k_cells_persist refills when this many lanes have finished
   int rmax;                           // K2 walks rings 0..rmax of leaf bins before it turns to the quadtree
+  int rtree;                          // ... and at least rings 0..rtree even when the ring certificate cannot work
   int clip_a, clip_b;                 // K2 clips when n_hold * clip_a >= n_search * clip_b (warp vote policy)
   const int *abort_flag;              // != 0: another cell is already known to be empty, stop (line search)
   int abort_on_empty;
@@ -217,10 +218,10 @@ template <class Poly> struct CellSearch {
           const double rho = (double)r * p.ph + emin, rho2 = rho * rho, rn = rho + p.ph;
           if (all || cannot_cut(rho2, dw_glob, R2)) {
             phase = 2;  // nothing farther than rho can cut
-          } else if (r == RMAX || (r >= 1 && rn * rn + dw_glob <= 0.0)) {
-            // (one more ring could not certify anything if even a tiny polygon fails; ring 1 is always
+          } else if (r == RMAX || (r >= p.rtree && rn * rn + dw_glob <= 0.0)) {
+            // (one more ring could not certify anything if even a tiny polygon fails; rings 0..rtree are always
             // walked: the true neighbours are the nearby Diracs whatever the weights do, and the rings
-            // are the cheap way to find them)
+            // are the cheap way to find them — the quadtree walk prunes badly while the polygon is still big)
             phase = 1;  // first tree pass: everything within rho is done
             prev2 = rho2;
             cap = 2.0 * fmax(rho, p.ph);

@@ -161,7 +161,7 @@ extern "C" int emu_eval(int mesh_kind,
       }
   }
   int no_abort = 0;
-  p.nodeG = nodeG.data(); p.nodeA = nodeA.data(); p.abort_flag = &no_abort; p.abort_on_empty = 0; p.clip_a = p.clip_b = 1; p.refill_at = 8; p.rmax = 3;
+  p.nodeG = nodeG.data(); p.nodeA = nodeA.data(); p.abort_flag = &no_abort; p.abort_on_empty = 0; p.clip_a = p.clip_b = 1; p.refill_at = 8; p.rmax = 3; p.rtree = 1;
   p.N = N; p.xs = xs.data(); p.ys = ys.data(); p.ws = ws.data();
   p.cell_lo = 0; p.cell_hi = N;
   std::vector<int> bin_rm(2 * nb);
