@@ -164,6 +164,24 @@ template <class Poly> struct CellSearch {
     else { nx = 1; ny = 0; cl = bx0; }
   }
 
+  // the same line with double-double coefficients from the ORIGINAL inputs (exact stage of the sign filter)
+  MA_DEV ddline ddlineof(const Params &p, int tag) const {
+    if (tag >= 0) return dd_bisector(xi, yi, wi, p.xs[tag], p.ys[tag], p.ws[tag]);
+    ddline l;
+    const bool horiz = (tag == -1 || tag == -3);
+    l.nx = dd_from(horiz ? 0.0 : 1.0);
+    l.ny = dd_from(horiz ? 1.0 : 0.0);
+    l.cl = tag == -1 ? dd_sub_dd(p.bb[1], yi) : (tag == -2 ? dd_sub_dd(p.bb[2], xi) : (tag == -3 ? dd_sub_dd(p.bb[3], yi) : dd_sub_dd(p.bb[0], xi)));
+    return l;
+  }
+  // Exact stage (the role of CGAL::Filtered_predicate's second stage, predicates.hpp:159-167): is vertex k of the
+  // polygon — the intersection of the lines supporting edges k-1 and k — strictly on i's side of the bisector
+  // with site jj?  Side2 of predicates.hpp:101-115 (Side1 for a corner of the box); ties are outside (:86, T3).
+  MA_DEV bool exact_inside(const Params &p, const Poly &P, int k, int jj) const {
+    const int ta = P.T(k == 0 ? n - 1 : k - 1), tb = P.T(k);
+    return dd_side(ddlineof(p, ta), ddlineof(p, tb), dd_bisector(xi, yi, wi, p.xs[jj], p.ys[jj], p.ws[jj])) > 0;
+  }
+
   MA_DEV void init(const Params &p, int cell, Poly &P) {
     i = cell;
     xi = p.xs[i]; yi = p.ys[i]; wi = p.ws[i];
@@ -257,13 +275,34 @@ template <class Poly> struct CellSearch {
           // (Measured from the polygon, not from y_i: once the weights have a gradient the cell lies far
           // from its Dirac and a disk around y_i would reject nothing.)
           // (use_m = false: m = 0 and rc2 = R2, the disk around y_i)
-          const double c = 0.5 * (dd2 + (wi - wj));
+          const double dw = wi - wj;
+          const double c = 0.5 * (dd2 + dw);
           const double e = c - (mx * Dx + my * Dy);
-          if (!(e >= 0.0 && e * e >= rc2 * dd2 * (1.0 + 1e-12))) {
-            unsigned long long in = 0ull;
+          // (margin 1e-9: anything closer to tangency than that goes through the filtered sign test below)
+          if (!(e >= 0.0 && e * e >= rc2 * dd2 * (1.0 + 1e-9))) {
+            unsigned long long in = 0ull, unc = 0ull;
             MA_COUNT(1);
-            for (int k = 0; k < n; ++k)
-              if (c - (P.X(k) * Dx + P.Y(k) * Dy) > 0.0) in |= 1ull << k;
+            // sign of pow_j - pow_i at every vertex with a forward-error filter; what the filter cannot decide is
+            // re-evaluated in double-double from the original (y, w) (predicates.hpp:101-115,139-168)
+            const double cmag = 0.5 * (dd2 + fabs(dw));
+            for (int k = 0; k < n; ++k) {
+              const double tx = P.X(k) * Dx, ty = P.Y(k) * Dy;
+              const double val = c - (tx + ty);
+              if (val > 0.0) in |= 1ull << k;
+              if (fabs(val) <= p.filter_tol * (cmag + fabs(tx) + fabs(ty))) unc |= 1ull << k;
+            }
+            if (unc) {
+              for (int k = 0; k < n; ++k)
+                if ((unc >> k) & 1ull) {
+                  if (exact_inside(p, P, k, jj)) in |= 1ull << k;
+                  else in &= ~(1ull << k);
+                }
+#ifdef __CUDA_ARCH__
+              atomicAdd(p.flags + 2, 1);
+#else
+              p.flags[2] += 1;
+#endif
+            }
             const unsigned long long full = lowmask64(n);
             if (in == 0ull) { n = 0; phase = 2; }
             else if (in != full) { jc = jj; cDx = Dx; cDy = Dy; cc = c; cin = in; }

@@ -474,7 +474,9 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT) k_c
   MA_WARP_SYNC();
   if (!valid) return;
   if (fl) atomicOr(p.flags, fl);
-  if (n == 0 && p.abort_on_empty) p.flags[1] = 1;  // an empty cell: the line search rejects this trial point
+  // a genuinely empty cell (not a capacity / stack overflow, which the host answers by escalating):
+  // the line search rejects this trial point
+  if (n == 0 && p.abort_on_empty) p.flags[1] = 1;
   if (n < 0) n = 0;
   cell_emit(p, i, P, n);
   if (POLY) {
@@ -528,8 +530,10 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
         if (S.i >= 0) {
           const int i = S.i;
           int n = S.n;
+          // a genuinely empty cell rejects the line-search trial; an overflowed one must NOT (the host
+          // escalates the capacity class and evaluates the trial point again)
           if (S.status) { atomicOr(p.flags, S.status); n = 0; }
-          if (n == 0 && p.abort_on_empty) p.flags[1] = 1;  // an empty cell: the line search rejects this trial point
+          else if (n == 0 && p.abort_on_empty) p.flags[1] = 1;
           cell_emit(p, i, P, n);
           if (POLY) {
             p.poly_n[i] = n;

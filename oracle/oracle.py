@@ -31,15 +31,39 @@ MODE_PER_CELL = 2   # per-cell OpenMP enumeration instead of the reference's glo
 MODE_RECORD = 4     # keep the pieces
 
 
+def _cpu_key() -> str:
+    """Identifies the host CPU's instruction set: the library is built -march=native, so a copy
+    built on another machine (it travels to the GPU box with the snapshot) is rebuilt there."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    return hashlib.sha1(line.encode()).hexdigest()[:16]
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False) -> str:
-    """Compile the oracle with g++ (no external dependencies)."""
+    """Compile the oracle with g++ -O3 -march=native (no external dependencies)."""
     src = os.path.join(_HERE, "ma_oracle.cpp")
-    if (not force and os.path.exists(_LIB_PATH)
+    stamp = _LIB_PATH + ".cpu"
+    key = _cpu_key()
+    try:
+        same_cpu = open(stamp).read().strip() == key
+    except OSError:
+        same_cpu = False
+    if (not force and same_cpu and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
         return _LIB_PATH
     os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
-    cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-shared", "-fPIC", src, "-o", _LIB_PATH, "-lquadmath"]
+    tmp = _LIB_PATH + f".{os.getpid()}.tmp"
+    cmd = ["g++", "-O3", "-march=native", "-std=c++17", "-fopenmp", "-shared", "-fPIC", src, "-o", tmp, "-lquadmath"]
     subprocess.check_call(cmd)
+    os.replace(tmp, _LIB_PATH)  # atomic: concurrent ranks / xdist workers may build at the same time
+    with open(stamp, "w") as fh:
+        fh.write(key)
     return _LIB_PATH
 
 
@@ -47,14 +71,14 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        build()
+    build()  # no-op when the library is current for this source and this CPU
     L = C.CDLL(_LIB_PATH)
     L.mao_create.restype = C.c_void_p
     L.mao_destroy.argtypes = [C.c_void_p]
     L.mao_linear_functions.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int, _ip, _dp]
     L.mao_set_mesh.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _ip, _dp]
     L.mao_set_points.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    L.mao_set_cell_range.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.mao_kantorovich.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int]
     L.mao_moments.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, _dp]
     L.mao_fval.argtypes = [C.c_void_p]
@@ -121,6 +145,10 @@ class Oracle:
         self.y = np.ascontiguousarray(X[:, 1])
         self.N = len(self.x)
         self.L.mao_set_points(self.h, self.N, self.x, self.y)
+
+    def set_cell_range(self, lo=0, hi=-1):
+        """bench.py's CPU legs: evaluate only the cells [lo, hi) of this problem (per-cell mode); hi < 0 = all."""
+        self.L.mao_set_cell_range(self.h, int(lo), int(hi))
 
     def default_mode(self):
         return MODE_BRUTE if self.N <= 2000 else 0

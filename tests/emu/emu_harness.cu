@@ -179,10 +179,11 @@ extern "C" int emu_eval(int mesh_kind,
   // ---- outputs ----
   std::vector<double> cell_bb((size_t)4 * N);
   std::vector<unsigned long long> cnt(CNT_N, 0);
-  int flags = 0;
+  int flags4[4] = {0, 0, 0, 0};  // mirrors the device flags[4]: status bits, abort, K2 exact-stage count, spare
+  int &flags = flags4[0];
   p.kmax = kmax; p.nbr = nbr; p.nbr_cnt = nbr_cnt; p.cell_bb = cell_bb.data();
   p.mass = mass; p.fcell = fcell; p.hslot = hslot; p.touched = touched; p.mom = mom;
-  p.counters = cnt.data(); p.stats = 1; p.flags = &flags; p.filter_tol = filter_tol;
+  p.counters = cnt.data(); p.stats = 1; p.flags = flags4; p.filter_tol = filter_tol;
   // ---- K2 ----
   const int maxv_cell = kmax + 4;
   {

@@ -1,0 +1,246 @@
+"""GPU parity at the sizes BASELINE.json names, on converged (graded) weights and on degenerate inputs.
+
+Everything here compares the CUDA engine (through the C-ABI) with the CPU oracle — never with itself.
+Tolerances are the north star's: f, g 1e-10 relative, H 1e-10 of the diagonal scale with an identical
+pattern, converged weights / cost 1e-8, Newton niter / neval identical."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from mongeampere_b200 import inputs
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+NT = os.cpu_count() or 1
+
+
+def compare_eval(orc, O, ctx, w, tag=""):
+    f0, g0, H0 = orc.kantorovich(w, mode=O.MODE_PER_CELL)
+    f1, g1, H1 = ctx.kantorovich(w)
+    assert abs(f1 - f0) <= 1e-10 * max(abs(f0), 1e-300), (tag, f0, f1)
+    assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max(), tag
+    assert common.same_pattern(H0, H1), (tag, H0.nnz, H1.nnz)
+    assert abs(H0 - H1).max() <= 1e-10 * np.abs(H0.diagonal()).max(), tag
+    return f1, g1, H1
+
+
+@pytest.mark.parametrize("name,scale", [("c2", 1.0), ("c3", 0.1), ("c1", 1.0)])
+def test_baseline_sizes_w0_and_converged(gpu_ctx, oracle_mod, name, scale):
+    """c1 and c2 at the size BASELINE.json states (10 k / 100 k Diracs), c3 at a tenth (100 k Diracs on a 648^2
+    image grid): evaluation at w = 0 AND at the converged weights of the damped-Newton solve (the graded regime:
+    cells displaced from their Diracs, the quadtree walk with supporting planes decides the adjacency)."""
+    case = common.make_case(name, scale, "zero")
+    orc = common.oracle_for(oracle_mod, case, nthreads=NT)
+    common.load_engine(gpu_ctx, case)
+    N = case["N"]
+    compare_eval(orc, oracle_mod, gpu_ctx, np.zeros(N), "w=0")
+    nu = np.full(N, gpu_ctx.total_mass / N)
+    w, st, rc = gpu_ctx.ot_solve(nu, eps_g=1e-7, maxiter=2000)
+    assert rc == 0 and st["final_norm"] < 1e-7, (rc, st)
+    f1, g1, H1 = compare_eval(orc, oracle_mod, gpu_ctx, w, "converged")
+    # ... and the converged point is a solution for the ORACLE too (optimal_transport.hpp:150)
+    assert np.linalg.norm(g1 - nu) < 1e-7
+    # half-way weights: a graded field that is not a fixed point (masses far from uniform)
+    compare_eval(orc, oracle_mod, gpu_ctx, 0.5 * w, "half")
+
+
+@pytest.mark.parametrize("name,scale", [("c3", 0.01), ("c2", 0.05)])
+def test_newton_trajectory_matches_oracle(gpu_ctx, oracle_mod, name, scale):
+    """Full damped Newton from w = 0 to |m - nu| < 1e-7 on 10 k / 5 k Diracs: identical iteration and
+    evaluation counts, weights (gauge: last weight) and cost within 1e-8."""
+    case = common.make_case(name, scale, "zero")
+    orc = common.oracle_for(oracle_mod, case, nthreads=NT)
+    common.load_engine(gpu_ctx, case)
+    N = case["N"]
+    nu = np.full(N, gpu_ctx.total_mass / N)
+    x0, st0, _ = oracle_mod.ot_solve(orc, nu, eps_g=1e-7, maxiter=1000, mode=oracle_mod.MODE_PER_CELL)
+    x1, st1, rc = gpu_ctx.ot_solve(nu, eps_g=1e-7, maxiter=1000)
+    assert rc == 0 and st0["status"] == "ok"
+    assert st1["niter"] == st0["niter"] and st1["neval"] == st0["neval"], (st0, st1)
+    assert np.abs((x1 - x1[-1]) - (x0 - x0[-1])).max() <= 1e-8
+    f0 = orc.kantorovich(x0, mode=oracle_mod.MODE_PER_CELL)[0] - nu.dot(x0)
+    assert abs(st1["fval"] - f0) <= 1e-8 * abs(f0)
+
+
+def test_c4_moments_at_a_tenth(gpu_ctx, oracle_mod):
+    """Config 4 (Lloyd, lloyd.hpp:126-144) at a tenth of its size: 25 k points on a 324^2 grid."""
+    case = common.make_case("c4", 0.1, "zero")
+    orc = common.oracle_for(oracle_mod, case, nthreads=NT)
+    common.load_engine(gpu_ctx, case)
+    ref = orc.moments(case["w"], 2, mode=oracle_mod.MODE_PER_CELL)
+    m, m1, m2 = gpu_ctx.moments(case["w"], 2)
+    got = np.c_[m, m1, m2]
+    assert (np.abs(got - ref).max(axis=0) <= 1e-10 * np.abs(ref).max(axis=0)).all()
+    # five Lloyd iterations X <- centroids (tests/test_lloyd.cpp:52-56) stay together
+    X0 = case["X"].copy()
+    X1 = case["X"].copy()
+    for _ in range(5):
+        orc.set_points(X0)
+        X0 = orc.lloyd(np.zeros(case["N"]), mode=oracle_mod.MODE_PER_CELL)[1]
+        gpu_ctx.set_points(X1)
+        X1 = gpu_ctx.lloyd()[1]
+    assert np.abs(X1 - X0).max() <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# degenerate inputs
+# ---------------------------------------------------------------------------------------------------------------
+def drop_zeros(H, tol):
+    H = sp.csr_matrix(H).copy()
+    H.data[np.abs(H.data) <= tol] = 0.0
+    H.eliminate_zeros()
+    H.sort_indices()
+    return H
+
+
+def unit_square(ctx, O, rho=None):
+    vx, vy, tri = inputs.unit_square_mesh()
+    rho = np.ones(4) if rho is None else rho
+    abc = inputs.pl_coefficients(vx, vy, rho, tri)
+    ctx.set_mesh(vx, vy, tri, abc)
+    return O.Oracle(vx, vy, tri, abc)
+
+
+def test_lattice_is_five_point_laplacian(gpu_ctx, oracle_mod):
+    """Every interior Voronoi vertex is a co-circular quadruple (mirror of tests/test_oracle.py): the masses are
+    equal, H is the scaled 5-point Laplacian, the degenerate diagonal neighbours carry (at most) zeros."""
+    for n in (6, 32):
+        unit_square(gpu_ctx, oracle_mod)
+        c = (np.arange(n) + 0.5) / n
+        X = np.stack(np.meshgrid(c, c, indexing="ij"), -1).reshape(-1, 2)
+        gpu_ctx.set_points(X)
+        f, g, H = gpu_ctx.kantorovich(np.zeros(n * n))
+        assert np.allclose(g, 1.0 / n ** 2, rtol=0, atol=1e-15)
+        i, j = np.divmod(np.arange(n * n), n)
+        A = sp.lil_matrix((n * n, n * n))
+        for di, dj in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            ok = (i + di >= 0) & (i + di < n) & (j + dj >= 0) & (j + dj < n)
+            A[np.arange(n * n)[ok], ((i + di) * n + j + dj)[ok]] = -0.5
+        A = sp.csr_matrix(A)
+        A = A - sp.diags(np.asarray(A.sum(axis=1)).ravel())
+        assert abs(H - A).max() <= 1e-13
+        assert abs(H - H.T).max() <= 1e-13  # structurally symmetric up to explicit zeros
+        Hz = drop_zeros(H, 1e-13)
+        assert common.same_pattern(drop_zeros(A, 0.0), Hz)
+
+
+def test_jittered_grids_like_bench_opttransport(gpu_ctx, oracle_mod):
+    """tests/bench_opttransport.cpp:45-60: n x n grid jittered by 1/(2n) — near-degenerate quadruples everywhere.
+    Neighbour sets bit-identical to the oracle and to Qhull's lifted hull (edges inside the domain), H symmetric
+    in structure."""
+    from scipy.spatial import ConvexHull
+    n = 100
+    X = inputs.jittered_grid_points(n, 11)
+    case = common.make_case("c1r", 0.001, "zero")  # 2 x 2 image mesh on [-1,1]^2, rho = 1.001
+    cfg = case["cfg"]
+    X = np.clip(X, -1 + 1e-9, 1 - 1e-9)
+    orc = oracle_mod.Oracle(cfg["vx"], cfg["vy"], cfg["tri"], case["abc"], nthreads=NT)
+    orc.set_points(X)
+    gpu_ctx.set_grid(2, 2, cfg["rho"])
+    gpu_ctx.set_points(X)
+    w = np.zeros(len(X))
+    f1, g1, H1 = compare_eval(orc, oracle_mod, gpu_ctx, w, "jittered")
+    S = sp.csr_matrix((np.ones(H1.nnz), H1.indices, H1.indptr), shape=H1.shape)
+    assert (S != S.T).nnz == 0
+    # Qhull: lower hull of the lifted points = Delaunay; every Hessian edge is a Delaunay edge
+    lift = np.c_[X, (X ** 2).sum(1) - w]
+    hull = ConvexHull(lift)
+    low = hull.simplices[hull.equations[:, 2] < 0]
+    E = set()
+    for a, b, c in low:
+        E |= {(min(a, b), max(a, b)), (min(b, c), max(b, c)), (min(a, c), max(a, c))}
+    Hc = sp.triu(S, 1).tocoo()
+    P = set(zip(Hc.row.tolist(), Hc.col.tolist()))
+    assert P <= E
+    inner = {(a, b) for a, b in E - P}
+    # Delaunay edges missing from H are dual to Voronoi edges outside the domain: both ends near the boundary
+    for a, b in inner:
+        assert min(1 - abs(X[a]).max(), 1 - abs(X[b]).max()) < 3.0 / n, (a, b)
+
+
+def test_cocircular_and_on_mesh_points(gpu_ctx, oracle_mod):
+    """Exact co-circular quadruples inside a random cloud, and Diracs exactly on mesh vertices / mesh edges of a
+    coarse image grid: same results as the oracle (values; the pattern up to zero-length edges)."""
+    rng = np.random.default_rng(5)
+    n = 17
+    vx, vy = inputs.grid_vertices(n, n)
+    rho = inputs.gaussian_mixture_density(vx, vy)
+    tri = inputs.grid_triangles(n, n)
+    abc = inputs.pl_coefficients(vx, vy, rho, tri)
+    X = rng.uniform(-0.95, 0.95, (600, 2))
+    # 20 squares of 4 co-circular sites each (axis-aligned and rotated by 45 degrees)
+    quads = []
+    for k in range(20):
+        c = rng.uniform(-0.8, 0.8, 2)
+        r = 0.02
+        d = np.array([[1, 0], [0, 1], [-1, 0], [0, -1]]) * r if k % 2 else np.array([[1, 1], [-1, 1], [-1, -1], [1, -1]]) * r
+        quads.append(c + d)
+    # Diracs on mesh vertices and on mesh edges (midpoints of horizontal, vertical and diagonal edges)
+    vv = np.c_[vx, vy][rng.choice(n * n, 30, replace=False)]
+    h = 2.0 / (n - 1)
+    on_edges = np.r_[vv[:10] + [h / 2, 0], vv[10:20] + [0, h / 2], vv[20:] + [h / 2, h / 2]]
+    X = np.r_[X, np.concatenate(quads), vv, on_edges]
+    X = X[(np.abs(X) < 0.999).all(1)]
+    orc = oracle_mod.Oracle(vx, vy, tri, abc, nthreads=NT)
+    orc.set_points(X)
+    gpu_ctx.set_grid(n, n, rho)
+    gpu_ctx.set_points(X)
+    for w in (np.zeros(len(X)), rng.normal(0, 2e-4, len(X))):
+        f0, g0, H0 = orc.kantorovich(w)
+        f1, g1, H1 = gpu_ctx.kantorovich(w)
+        d = np.abs(H0.diagonal()).max()
+        assert abs(f1 - f0) <= 1e-10 * abs(f0)
+        assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
+        assert abs(H0 - H1).max() <= 1e-10 * d
+        assert common.same_pattern(drop_zeros(H0, 1e-12 * d), drop_zeros(H1, 1e-12 * d))
+        S = sp.csr_matrix((np.ones(H1.nnz), H1.indices, H1.indptr), shape=H1.shape)
+        Hz = drop_zeros(H1, 1e-12 * d)
+        assert abs(Hz - Hz.T).max() <= 1e-9 * d
+
+
+def test_forced_fallback_on_gpu(gpu_ctx, oracle_mod):
+    """filter_tol = 1e300 sends EVERY sign decision of k_pieces (and of the neighbour search) to the exact
+    stage on the device: identical results, and the fallback counter proves the path ran."""
+    case = common.make_case("c2", 0.01, "0.4")
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(case["w"])
+    common.load_engine(gpu_ctx, case)
+    gpu_ctx.set_option("filter_tol", 1e300)
+    try:
+        for stats in (True, False):
+            gpu_ctx.set_stats(stats)
+            f1, g1, H1 = gpu_ctx.kantorovich(case["w"])
+            assert abs(f1 - f0) <= 1e-10 * abs(f0)
+            assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
+            assert common.same_pattern(H0, H1)
+            assert abs(H0 - H1).max() <= 1e-10 * np.abs(H0.diagonal()).max()
+            if stats:
+                assert gpu_ctx.counters()["fallbacks"] > 0
+        assert gpu_ctx.info("cell_fallbacks") > 0  # the neighbour search (K2) took its exact stage too
+    finally:
+        gpu_ctx.set_stats(False)
+        gpu_ctx.set_option("filter_tol", 1e-11)
+
+
+def test_ot_solve_with_capacity_escalation(gpu_ctx, oracle_mod):
+    """A Dirac ringed by 40 others (its cell has 40 sides: the 16-vertex class overflows at every evaluation): the
+    line search must escalate, not reject the trial: same niter / neval / weights as the oracle."""
+    t = np.linspace(0, 2 * np.pi, 40, endpoint=False)
+    X = np.vstack([[0.5, 0.5], np.c_[0.5 + 0.3 * np.cos(t), 0.5 + 0.3 * np.sin(t)],
+                   np.random.default_rng(3).uniform(0.02, 0.98, (200, 2))])
+    X = X[np.r_[True, np.ones(40, bool), (np.hypot(X[41:, 0] - 0.5, X[41:, 1] - 0.5) > 0.33)]]
+    orc = unit_square(gpu_ctx, oracle_mod)
+    orc.set_points(X)
+    gpu_ctx.set_points(X)
+    N = len(X)
+    nu = np.full(N, 1.0 / N)
+    x0, st0, _ = oracle_mod.ot_solve(orc, nu, eps_g=1e-9)
+    x1, st1, rc = gpu_ctx.ot_solve(nu, eps_g=1e-9)
+    assert rc == 0 and st0["status"] == "ok"
+    assert st1["niter"] == st0["niter"] and st1["neval"] == st0["neval"], (st0, st1)
+    assert np.abs((x1 - x1[-1]) - (x0 - x0[-1])).max() <= 1e-8
+    # the trial-point probe used by the multi-GPU line search must not mistake the overflow for an empty cell
+    assert not gpu_ctx.has_empty_cell(np.zeros(N))
