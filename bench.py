@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--newton-workload", default="c2")
     ap.add_argument("--newton-maxiter", type=int, default=1000)
     ap.add_argument("--cpu-sample", type=float, default=0.1, help="fraction of the cells the CPU legs evaluate")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (ma_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -238,6 +239,9 @@ def main_b200(args, rank, world, local_rank):
     N = case["N"]
     ctx = capi.Context(local_rank)  # raises without the CUDA library / a device: no fallback
     from tests import common
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, float(v))
     common.load_engine(ctx, case)
     ctx.set_partition(rank, world)
     ctx.set_weights(case["w"])

@@ -66,6 +66,11 @@ struct ma_ctx {
   int N = 0;
   Buf x, y, xs, ys, perm, pos, code, bin_count, bin_start, bin_rm, wmax;
   Buf code_s, pre0, pre1, fs_tiles, nodeG, nodeA, wstat;  // per-node supporting planes (ma_geom.cuh)
+  Buf xr, yr, wr, rm2s, s2rm, rm_start, blk_cnt;          // the sites in row-major bin order (ma_block.cuh)
+  int bG = 1;
+  double bph = 1, binv = 1, block_target = 1.0;           // block grid: bG x bG bins of side bph, ~block_target Diracs each
+  Buf hard1, hard2, hard_n;                               // cells the block kernels pass on (lists + 2 counters)
+  int lean = 1;                                           // K2: block kernels first (0: CellSearch for every cell)
   bool abort_on_empty = false, aborted = false;
   bool probe_empty = false;  // option "abort_on_empty": ma_cells_build stops at the first empty cell and reports it
   int L = 0;
@@ -279,7 +284,8 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
-                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->cgbar, &c->cgw1, &c->cgpp, &c->bin_rm};
+                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->cgbar, &c->cgw1, &c->cgpp, &c->bin_rm,
+                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->hard1, &c->hard2, &c->hard_n};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
@@ -320,6 +326,8 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "pcg_blocks_per_sm") c->pcg_blocks_per_sm = std::max(1, (int)value);
   else if (n == "filter_tol") c->filter_tol = value;
   else if (n == "persist") c->persist = (int)value;
+  else if (n == "lean") c->lean = (int)value;
+  else if (n == "block_target") c->block_target = std::max(0.05, value);
   else if (n == "abort_on_empty") c->probe_empty = value != 0;
   else if (n == "rmax") c->rmax = std::min(MA_RING_TABLE_RMAX, std::max(1, (int)value));
   else if (n == "rtree") c->rtree = std::min(MA_RING_TABLE_RMAX, std::max(0, (int)value));
@@ -543,6 +551,29 @@ extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y)
   k_bin_rowmajor<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(G, c->bin_start.as<int>(), c->bin_rm.as<int>());
   k_gather_points<<<cdiv(N, 256), 256, 0, c->stream>>>(c->x.as<double>(), c->y.as<double>(), c->perm.as<int>(), N,
                                                        c->xs.as<double>(), c->ys.as<double>(), c->pos.as<int>());
+  {  // the sites once more, filed under the row-major bins of the block grid (about block_target Diracs per bin)
+    int bG = (int)std::ceil(std::sqrt((double)N / c->block_target));
+    bG = std::max(1, std::min(bG, 8192));
+    c->bG = bG;
+    c->bph = ext / bG;
+    c->binv = bG / ext;
+    const size_t nbb = (size_t)bG * bG;
+    CKR(ensure(c, c->xr, (size_t)N * 8)); CKR(ensure(c, c->yr, (size_t)N * 8)); CKR(ensure(c, c->wr, (size_t)N * 8));
+    CKR(ensure(c, c->rm2s, (size_t)N * 4)); CKR(ensure(c, c->s2rm, (size_t)N * 4));
+    CKR(ensure(c, c->rm_start, (nbb + 1) * 4)); CKR(ensure(c, c->blk_cnt, nbb * 4)); CKR(ensure(c, c->scratch_i, (size_t)N * 4));
+    CKR(ensure(c, c->hard1, (size_t)N * 4)); CKR(ensure(c, c->hard2, (size_t)N * 4)); CKR(ensure(c, c->hard_n, 16));
+    CK(cudaMemsetAsync(c->blk_cnt.p, 0, nbb * 4, c->stream));
+    k_blk_count<<<cdiv(N, 256), 256, 0, c->stream>>>(c->xs.as<double>(), c->ys.as<double>(), N, c->px0, c->py0, c->binv, bG,
+                                                     c->scratch_i.as<int>(), c->blk_cnt.as<int>());
+    CKR(scan_i32(c, c->blk_cnt.as<int>(), c->rm_start.as<int>(), (int)nbb));
+    CK(cudaMemsetAsync(c->blk_cnt.p, 0, nbb * 4, c->stream));
+    k_blk_scatter<<<cdiv(N, 256), 256, 0, c->stream>>>(c->scratch_i.as<int>(), N, c->rm_start.as<int>(), c->blk_cnt.as<int>(),
+                                                       c->rm2s.as<int>());
+    k_blk_fill<<<cdiv((long long)nbb, 256), 256, 0, c->stream>>>((int)nbb, c->rm_start.as<int>(), c->rm2s.as<int>(),
+                                                                c->xs.as<double>(), c->ys.as<double>(), c->xr.as<double>(),
+                                                                c->yr.as<double>(), c->s2rm.as<int>());
+    CK(cudaMemsetAsync(c->wr.p, 0, (size_t)N * 8, c->stream));
+  }
   CK(cudaMemsetAsync(c->w.p, 0, (size_t)N * 8, c->stream));
   CK(cudaGetLastError());
   // per-node planes: sorted leaf codes + the geometric half of the moment prefix sums
@@ -574,6 +605,9 @@ int fill_params(ma_ctx *c, Params &p) {
   p.bin_start = c->bin_start.as<int>();
   p.bin_rm = c->bin_rm.as<int>();
   p.wmax = c->wmax.as<double>();
+  p.xr = c->xr.as<double>(); p.yr = c->yr.as<double>(); p.wr = c->wr.as<double>();
+  p.rm2s = c->rm2s.as<int>(); p.rm_start = c->rm_start.as<int>();
+  p.bG = c->bG; p.bph = c->bph; p.binv = c->binv;
   p.wstat = c->wstat.as<double>();
   p.nodeG = c->nodeG.as<double>();
   p.nodeA = c->nodeA.as<unsigned long long>();
@@ -605,9 +639,37 @@ int fill_params(ma_ctx *c, Params &p) {
 
 constexpr int cells_maxv(int kmax) { return kmax == 16 ? 16 : (kmax == 32 ? 36 : 64); }
 
+// K2 fast path: block kernels of radius 2, then 3, then CellSearch on what is left (lists stay on the device)
+template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
+  constexpr int MAXV = 16;
+  const size_t sm = cells_smem_bytes<MAXV, NT>();
+  const int ncells = p.cell_hi - p.cell_lo;
+  int *cnt = c->hard_n.as<int>();
+  CK(cudaMemsetAsync(cnt, 0, 16, c->stream));
+  CK(cudaFuncSetAttribute(k_cells_block<2, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(cudaFuncSetAttribute(k_cells_block<3, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const int nblk = std::max(1, cdiv(ncells, NT));
+  k_cells_block<2, MAXV, NT, POLY><<<nblk, NT, sm, c->stream>>>(p, nullptr, nullptr, c->hard1.as<int>(), cnt);
+  // the later stages see a fraction of the cells (or, with graded weights, all of them: k_cells_persist then ignores the list)
+  const int nblk2 = std::max(1, std::min(nblk, c->sm_count * 8));
+  k_cells_block<3, MAXV, NT, POLY><<<nblk2, NT, sm, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cells_persist<MAXV, NT, POLY>, NT, sm));
+  const long long warps_target = (long long)c->sm_count * std::max(per_sm, 1) * (NT / 32) * c->persist_waves;
+  const int nwarps = (int)std::max<long long>(1, std::min<long long>(warps_target, cdiv(ncells, c->persist_min_chunk)));
+  k_cells_persist<MAXV, NT, POLY><<<cdiv(nwarps, NT / 32), NT, sm, c->stream>>>(p, c->persist_min_chunk, c->hard2.as<int>(), cnt + 1);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+
 template <int MAXV, int NT, bool POLY> int launch_cells(ma_ctx *c, const Params &p) {
   size_t sm = cells_smem_bytes<MAXV, NT>();
   const int ncells = p.cell_hi - p.cell_lo;
+  if constexpr (MAXV == 16) {
+    if (c->lean && c->persist) return launch_cells_lean<NT, POLY>(c, p);
+  }
   if (c->persist) {
     // persistent lanes: each warp owns `chunk` consecutive cells; about 3 waves of resident blocks
     CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -616,7 +678,7 @@ template <int MAXV, int NT, bool POLY> int launch_cells(ma_ctx *c, const Params 
     const long long warps_target = (long long)c->sm_count * std::max(per_sm, 1) * (NT / 32) * c->persist_waves;
     int chunk = (int)std::max<long long>(c->persist_min_chunk, (ncells + warps_target - 1) / warps_target);
     const int nwarps = std::max(1, cdiv(ncells, chunk));
-    k_cells_persist<MAXV, NT, POLY><<<cdiv(nwarps, NT / 32), NT, sm, c->stream>>>(p, chunk);
+    k_cells_persist<MAXV, NT, POLY><<<cdiv(nwarps, NT / 32), NT, sm, c->stream>>>(p, chunk, nullptr, nullptr);
   } else {
     CK(cudaFuncSetAttribute(k_cells<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_cells<MAXV, NT, POLY><<<std::max(1, cdiv(ncells, NT)), NT, sm, c->stream>>>(p);
@@ -689,7 +751,8 @@ int alloc_eval(ma_ctx *c) {
 // K1 per-eval part + K2 on the current device weights (c->w, caller order)
 template <bool POLY = false> int run_cells(ma_ctx *c, Params &p) {
   const int N = c->N;
-  k_gather<<<cdiv(N, 256), 256, 0, c->stream>>>(c->w.as<double>(), c->perm.as<int>(), N, c->ws.as<double>());
+  k_gather_w<<<cdiv(N, 256), 256, 0, c->stream>>>(c->w.as<double>(), c->perm.as<int>(), c->s2rm.as<int>(), N,
+                                                  c->ws.as<double>(), c->wr.as<double>());
   const size_t nb = (size_t)1 << (2 * c->L);
   k_wmax_leaf<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(c->ws.as<double>(), c->bin_start.as<int>(), c->L,
                                                                c->wmax.as<double>());

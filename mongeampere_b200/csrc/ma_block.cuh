@@ -1,0 +1,142 @@
+// ma_block.cuh — K2, fast path: the power cell of a Dirac from the sites of the (2R+1)^2 block of leaf bins
+// around its own bin, with a per-vertex security certificate.
+//
+// Replaces CGAL Regular_triangulation_2's neighbour circulator (kantorovich.hpp:65-72, vti.hpp:265) for the
+// cells whose neighbours all live in that block — 85 % of the cells of a uniform point set at ~1 Dirac per
+// bin with R = 2, 99.6 % with R = 3 (measured).  The remaining cells go to CellSearch (ma_cell.cuh: ring
+// walk + quadtree) through a compacted list.
+//
+// Why a second kernel for the same job: CellSearch is a resumable state machine that handles one site per
+// step with a dozen data-dependent branches around it (16.7 k thread-instructions per cell, 9 of 32 lanes
+// active, profiles/r01n_summary.md).  Here the candidate list is known up front — the sites are kept a
+// second time in ROW-MAJOR bin order, so the bins [bx-R, bx+R] of one bin row are one contiguous run and a
+// block is 2R+1 runs — and every lane of a warp walks its own list in lock step: one candidate per
+// iteration, the same straight-line code for all lanes, warp votes to skip the sign loop / the clip when
+// no lane needs them.
+//
+// Certificate.  After the block every site inside the block's rectangle B has been tested.  A site j outside
+// B takes vertex p from i iff |p - y_j|^2 - w_j < |p - y_i|^2 - w_i; with w_j <= wmax this needs
+// dist(p, outside of B)^2 < |p - y_i|^2 - w_i + wmax.  If that fails for every vertex the polygon is the
+// cell (the per-vertex form certifies more cells than "security radius >= 2 R", which measures the worst
+// vertex against the nearest side of B).  Sides of B on the rim of the bin grid are unbounded: there are no
+// sites beyond it.
+#pragma once
+#include "ma_cell.cuh"
+
+namespace ma {
+
+// the block kernels run while max w - min w <= MA_LEAN_RANGE bin areas of the block grid
+#ifndef MA_LEAN_RANGE
+#define MA_LEAN_RANGE 4.0
+#endif
+
+#ifdef __CUDA_ARCH__
+#define MA_WARP_MAX_INT(v) ((int)__reduce_max_sync(0xffffffffu, (int)(v)))
+#else
+#define MA_WARP_MAX_INT(v) (v)
+#endif
+
+// Builds the cell of S.i (S.init() already done) from the block of radius R.  `active` = false lanes only
+// keep the warp's votes company.  On return S.phase == 0: polygon of S.n vertices in P, certified says whether
+// it is final; S.phase == 2: S.n == 0 and S.status tells an empty cell (0) from a capacity overflow.
+template <int R, class Poly>
+MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv, bool active, bool &certified) {
+  constexpr int NR = 2 * R + 1;
+  const int G = p.bG;
+  // the Dirac's bin of the block grid (same expression as k_blk_count, so a site is in the bin it was filed under)
+  const int cbx = min(max((int)((S.xi - p.px0) * p.binv), 0), G - 1);
+  const int cby = min(max((int)((S.yi - p.py0) * p.binv), 0), G - 1);
+  const int x0 = max(cbx - R, 0), x1 = min(cbx + R, G - 1);
+  int cum[NR + 1], off[NR];
+  cum[0] = 0;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int dy = (r == 0) ? 0 : ((r & 1) ? -((r + 1) >> 1) : (r >> 1));  // own row first, then -1, +1, -2, +2 ...
+    const int row = cby + dy;
+    int s = 0, len = 0;
+    if (active && row >= 0 && row < G) {
+      s = p.rm_start[(size_t)row * G + x0];
+      len = p.rm_start[(size_t)row * G + x1 + 1] - s;
+    }
+    off[r] = s - cum[r];
+    cum[r + 1] = cum[r] + len;
+  }
+  const int T = cum[NR];
+  const int Tmax = MA_WARP_MAX_INT(T);
+  for (int t = 0; t < Tmax; ++t) {
+    const bool act = active && S.phase == 0 && t < T;
+    int o = off[0];
+#pragma unroll
+    for (int r = 1; r < NR; ++r) o = (t >= cum[r]) ? off[r] : o;
+    const int pos = act ? t + o : 0;
+    const double Dx = p.xr[pos] - S.xi, Dy = p.yr[pos] - S.yi, wj = p.wr[pos];
+    const double dd2 = Dx * Dx + Dy * Dy;
+    const double dw = S.wi - wj;
+    const double c = 0.5 * (dd2 + dw);
+    MA_COUNT(0);
+    if (act && dd2 == 0.0) {  // itself, or a coincident site: the heavier (then the earlier) one keeps the cell
+      const int jj = p.rm2s[pos];
+      if (jj != S.i && (wj > S.wi || (wj == S.wi && jj < S.i))) { S.n = 0; S.phase = 2; }
+    }
+    // the bisector misses the disk of radius sqrt(R2) around y_i that contains the polygon => it cannot cut
+    const bool test = act && S.phase == 0 && dd2 > 0.0 && !(c >= 0.0 && c * c >= S.R2 * dd2 * (1.0 + 1e-9));
+    bool cut = false;
+    if (MA_WARP_ANY(test)) {
+      if (test) {
+        MA_COUNT(1);
+        unsigned long long in = 0ull, unc = 0ull;
+        const double cmag = 0.5 * (dd2 + fabs(dw));
+        const int n = S.n;
+        for (int k = 0; k < n; ++k) {
+          const double tx = P.X(k) * Dx, ty = P.Y(k) * Dy;
+          const double val = c - (tx + ty);
+          if (val > 0.0) in |= 1ull << k;
+          if (fabs(val) <= p.filter_tol * (cmag + fabs(tx) + fabs(ty))) unc |= 1ull << k;
+        }
+        const int jj = p.rm2s[pos];
+        if (unc) {  // exact stage (CellSearch::exact_inside), rare
+          for (int k = 0; k < n; ++k)
+            if ((unc >> k) & 1ull) {
+              if (S.exact_inside(p, P, k, jj)) in |= 1ull << k;
+              else in &= ~(1ull << k);
+            }
+#ifdef __CUDA_ARCH__
+          atomicAdd(p.flags + 2, 1);
+#else
+          p.flags[2] += 1;
+#endif
+        }
+        if (in == 0ull) { S.n = 0; S.phase = 2; }
+        else if (in != lowmask64(n)) { S.jc = jj; S.cDx = Dx; S.cDy = Dy; S.cc = c; S.cin = in; cut = true; }
+      }
+      MA_WARP_SYNC();
+      if (MA_WARP_ANY(cut)) {
+        if (cut) S.clip(p, P, maxv);  // overflow: status = FLAG_CELL_OVERFLOW, n = 0, phase = 2
+        MA_WARP_SYNC();
+      }
+    }
+  }
+  // ---- certificate ----
+  certified = false;
+  if (S.phase == 0) {
+    const double INF = 1.0 / 0.0;
+    const double bl = (cbx - R > 0) ? p.px0 + (double)(cbx - R) * p.bph - S.xi : -INF;
+    const double br = (cbx + R < G - 1) ? p.px0 + (double)(cbx + R + 1) * p.bph - S.xi : INF;
+    const double bb = (cby - R > 0) ? p.py0 + (double)(cby - R) * p.bph - S.yi : -INF;
+    const double bt = (cby + R < G - 1) ? p.py0 + (double)(cby + R + 1) * p.bph - S.yi : INF;
+    const double dwg = p.wmax[0] - S.wi;  // >= 0
+    const double slack = 1e-9 * p.bph;    // a site sits in its bin up to the rounding of the bin index
+    bool ok = true;
+    for (int k = 0; k < S.n; ++k) {
+      const double X = P.X(k), Y = P.Y(k);
+      const double rp = X * X + Y * Y + dwg;
+      const double d = fmin(fmin(X - bl, br - X), fmin(Y - bb, bt - Y)) - slack;
+      ok = ok && (rp <= 0.0 || (d > 0.0 && d * d >= rp * (1.0 + 1e-9)));
+    }
+    certified = ok;
+  } else {
+    certified = S.status == 0;  // hidden Dirac: one site covers a superset of the cell, nothing to certify
+  }
+}
+
+}  // namespace ma

@@ -34,6 +34,15 @@ struct Params {
   const int *bin_start;
   const int *bin_rm;  // row-major copy for the ring walk: bin (cx, cy) holds the sites [bin_rm[2q], bin_rm[2q+1]), q = cy * 2^L + cx
   const double *wmax;
+  // the sites a second time in ROW-MAJOR bin order (ma_block.cuh): the bins [a, b] of one bin row are the
+  // contiguous run [rm_start[row * bG + a], rm_start[row * bG + b + 1]) of (xr, yr, wr); rm2s maps a position
+  // of that order to the index in the Morton order (the index cells and tags use)
+  // (that "block grid" has its own resolution bG x bG over the same square as the quadtree's leaf bins, about one
+  // Dirac per bin whatever N is; bins of side bph = 1 / binv)
+  const double *xr, *yr, *wr;
+  const int *rm2s, *rm_start;
+  int bG;
+  double bph, binv;
   const double *wstat;                // {sum, sum of squares, min, max} of the weights of this evaluation
   const double *nodeG;                // 2 per node: least-squares weight gradient (ma_geom.cuh)
   const unsigned long long *nodeA;    // per node: dkey(alpha_B)

@@ -203,6 +203,48 @@ __global__ void k_bin_rowmajor(int G, const int *__restrict__ bin_start, int *__
   const unsigned code = morton2(cx, cy);
   reinterpret_cast<int2 *>(bin_rm)[q] = make_int2(bin_start[code], bin_start[code + 1]);
 }
+// The block grid of ma_block.cuh: the (Morton-sorted) sites filed a second time under row-major bins of a bG x bG
+// grid (count, scan, scatter, sort inside the bin by site index so that the order is reproducible).
+__global__ void k_blk_count(const double *__restrict__ xs, const double *__restrict__ ys, int n, double px0, double py0,
+                            double binv, int G, int *__restrict__ bin, int *__restrict__ count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int bx = min(max((int)((xs[k] - px0) * binv), 0), G - 1);
+  const int by = min(max((int)((ys[k] - py0) * binv), 0), G - 1);
+  const int q = by * G + bx;
+  bin[k] = q;
+  atomicAdd(&count[q], 1);
+}
+__global__ void k_blk_scatter(const int *__restrict__ bin, int n, const int *__restrict__ start, int *__restrict__ fill,
+                              int *__restrict__ rm2s) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int q = bin[k];
+  rm2s[start[q] + atomicAdd(&fill[q], 1)] = k;
+}
+__global__ void k_blk_fill(int nb, const int *__restrict__ start, int *__restrict__ rm2s, const double *__restrict__ xs,
+                           const double *__restrict__ ys, double *__restrict__ xr, double *__restrict__ yr,
+                           int *__restrict__ s2rm) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nb) return;
+  const int s = start[q], e = start[q + 1];
+  for (int a = s + 1; a < e; ++a) {
+    const int v = rm2s[a];
+    int b = a - 1;
+    while (b >= s && rm2s[b] > v) { rm2s[b + 1] = rm2s[b]; --b; }
+    rm2s[b + 1] = v;
+  }
+  for (int a = s; a < e; ++a) {
+    const int k = rm2s[a];
+    xr[a] = xs[k]; yr[a] = ys[k]; s2rm[k] = a;
+  }
+}
+// per evaluation: ws[k] = w[perm[k]] and its row-major twin
+__global__ void k_gather_w(const double *__restrict__ w, const int *__restrict__ perm, const int *__restrict__ s2rm, int n,
+                           double *__restrict__ ws, double *__restrict__ wr) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) { const double v = w[perm[k]]; ws[k] = v; wr[s2rm[k]] = v; }
+}
 __global__ void k_gather_points(const double *__restrict__ x, const double *__restrict__ y,
                                 const int *__restrict__ perm, int n, double *__restrict__ xs, double *__restrict__ ys,
                                 int *__restrict__ pos) {
@@ -456,6 +498,10 @@ __global__ void k_node_alpha(int n, int L, const double *__restrict__ xs, const 
   }
 }
 
+// The weights vary so much that the block certificate (which only knows the global maximum weight) would certify
+// few cells: the block kernels then leave everything to CellSearch (quadtree walk with supporting planes).
+__device__ __forceinline__ bool weights_graded(const Params &p) { return (p.wstat[3] - p.wstat[2]) > MA_LEAN_RANGE * p.bph * p.bph; }
+
 // ================================================================================================
 // K2: one thread per cell.  POLY: also store the cell polygon for k_seg (grid meshes).
 // ================================================================================================
@@ -496,7 +542,10 @@ template <int MAXV, int NT> constexpr size_t cells_smem_bytes() { return (size_t
 #ifndef MA_K2_MINBLOCKS
 #define MA_K2_MINBLOCKS 5  // 5 blocks of 128 threads per SM: <= 102 registers, 41 KB of polygons each
 #endif
-template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K2_MINBLOCKS : 1)) k_cells_persist(Params p, int chunk) {
+// `list` != null: the kernel handles the cells list[0 .. *list_n) left over by the block kernels (k_cells_block)
+// — unless the weights are graded (then the block kernels did nothing and it takes the whole tile) — and sizes
+// its chunks itself from the device-side count (the host never reads it).
+template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K2_MINBLOCKS : 1)) k_cells_persist(Params p, int chunk, const int *__restrict__ list, const int *__restrict__ list_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
   double *sy = sx + MAXV * NT;
@@ -505,9 +554,16 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
   Poly P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
   const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
   const long long warp_global = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
-  long long first = (long long)p.cell_lo + warp_global * chunk;
-  int next = (int)(first < p.cell_hi ? first : p.cell_hi);                       // warp-uniform
-  const int end = (int)(first + chunk < p.cell_hi ? first + chunk : p.cell_hi);  // warp-uniform
+  int lo = p.cell_lo, hi = p.cell_hi;
+  if (list) {
+    if (weights_graded(p)) list = nullptr;
+    else { lo = 0; hi = *list_n; }
+    const long long nwarps = (long long)gridDim.x * (NT / 32);
+    chunk = (int)max((long long)chunk, ((long long)(hi - lo) + nwarps - 1) / nwarps);
+  }
+  long long first = (long long)lo + warp_global * chunk;
+  int next = (int)(first < hi ? first : hi);                       // warp-uniform
+  const int end = (int)(first + chunk < hi ? first + chunk : hi);  // warp-uniform
   CellSearch<Poly> S;
   unsigned stk[CELL_STACK];
   S.i = -1; S.jc = -1; S.phase = 2; S.n = 0; S.status = 0;  // "done, nothing to emit"
@@ -544,7 +600,7 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
           }
         }
         const int idx = next + __popc(finmask & lt_mask);
-        if (idx < end) S.init(p, idx, P);
+        if (idx < end) S.init(p, list ? list[idx] : idx, P);
         else { parked = true; S.i = -1; }
       }
       next += n_fin;
@@ -567,6 +623,61 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
       if (ho) S.clip(p, P, MAXV);
       __syncwarp();
     }
+  }
+}
+
+// ================================================================================================
+// K2, fast path (ma_block.cuh): one thread per cell, all lanes of a warp walk their candidate lists in lock
+// step.  Cells the block of radius R cannot certify (or whose polygon outgrows the 16-vertex class) are
+// appended to out_list for the next stage; with graded weights the kernel does nothing at all (CellSearch's
+// quadtree walk with supporting planes is the path for that regime).
+// ================================================================================================
+#ifndef MA_K2B_MINBLOCKS
+#define MA_K2B_MINBLOCKS 5
+#endif
+template <int R, int MAXV, int NT, bool POLY>
+__global__ void __launch_bounds__(NT, MA_K2B_MINBLOCKS) k_cells_block(Params p, const int *__restrict__ in_list, const int *__restrict__ in_n,
+                                                                      int *__restrict__ out_list, int *__restrict__ out_n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (weights_graded(p)) return;
+  double *sx = reinterpret_cast<double *>(smem_raw);
+  double *sy = sx + MAXV * NT;
+  int *st = reinterpret_cast<int *>(sy + MAXV * NT);
+  typedef PolyRef<NT, true> Poly;
+  const unsigned lane = threadIdx.x & 31u;
+  const int n_in = in_list ? *in_n : p.cell_hi - p.cell_lo;
+  for (int base = blockIdx.x * NT; base < n_in; base += gridDim.x * NT) {
+    const int idx = base + threadIdx.x;
+    if ((idx & ~31) >= n_in) continue;  // warp-uniform (NT is a multiple of 32)
+    const bool valid = idx < n_in;
+    const int i = valid ? (in_list ? in_list[idx] : p.cell_lo + idx) : (in_list ? in_list[n_in - 1] : p.cell_hi - 1);
+    Poly P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+    CellSearch<Poly> S;
+    S.init(p, i, P);
+    bool cert = false;
+    block_search<R>(p, S, P, MAXV, valid, cert);
+    __syncwarp();
+    if (valid && cert) {
+      const int n = S.n;
+      if (n == 0 && p.abort_on_empty) p.flags[1] = 1;  // a hidden Dirac: the line search rejects this trial point
+      cell_emit(p, i, P, n);
+      if (POLY) {
+        p.poly_n[i] = n;
+        for (int k = 0; k < n; ++k) {
+          const size_t o = (size_t)k * p.N + i;
+          p.poly_x[o] = P.X(k); p.poly_y[o] = P.Y(k); p.poly_t[o] = P.T(k);
+        }
+      }
+    }
+    const bool hard = valid && !cert;
+    const unsigned hm = __ballot_sync(0xffffffffu, hard);
+    if (hm) {
+      int b = 0;
+      if (lane == (unsigned)(__ffs(hm) - 1)) b = atomicAdd(out_n, __popc(hm));
+      b = __shfl_sync(0xffffffffu, b, __ffs(hm) - 1);
+      if (hard) out_list[b + __popc(hm & ((1u << lane) - 1u))] = i;
+    }
+    __syncwarp();
   }
 }
 

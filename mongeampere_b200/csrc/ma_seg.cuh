@@ -30,7 +30,7 @@
 // there is nothing to make robust.  One THREAD handles one cell (the polygon stays in shared memory
 // where K2 built it).  SURVEY.md §7.2 "two regimes", DESIGN.md §3.
 #pragma once
-#include "ma_cell.cuh"
+#include "ma_block.cuh"
 
 namespace ma {
 

@@ -16,11 +16,11 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_HERE, "emu_harness.cu")
-    deps = [src] + [os.path.join(_ROOT, "mongeampere_b200", "csrc", f) for f in ("ma_cell.cuh", "ma_geom.cuh", "ma_seg.cuh")]
+    deps = [src] + [os.path.join(_ROOT, "mongeampere_b200", "csrc", f) for f in ("ma_cell.cuh", "ma_geom.cuh", "ma_seg.cuh", "ma_block.cuh")]
     if not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(d) for d in deps):
         return _LIB
     os.makedirs(os.path.dirname(_LIB), exist_ok=True)
-    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "--expt-extended-lambda", "--expt-relaxed-constexpr",
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--expt-extended-lambda", "--expt-relaxed-constexpr",
                            "-Xcompiler", "-fPIC", "-shared", src, "-o", _LIB])
     return _LIB
 
@@ -31,6 +31,18 @@ def lib():
         build()
         _lib = C.CDLL(_LIB)
     return _lib
+
+
+def set_lean(on: bool):
+    """K2 through the block kernels' lane code (ma_block.cuh) first, CellSearch for what they cannot certify."""
+    lib().emu_set_lean(int(on))
+
+
+def lean_counts():
+    """Cells finished by the radius-2 block, the radius-3 block and CellSearch in the last evaluation."""
+    out = (C.c_int * 4)()
+    lib().emu_get_lean(out)
+    return tuple(out[1:4])
 
 
 def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_target=2, nlanes=32, seg=False):

@@ -22,6 +22,12 @@ extern "C" void emu_work_counters(long long *out, int reset) {
 
 using namespace ma;
 
+// K2 through the block kernels' lane code first (ma_block.cuh), as launch_cells_lean does on the GPU:
+// [0] on/off, [1..3] cells finished by radius 2 / radius 3 / CellSearch in the last evaluation
+static int emu_lean[4] = {0, 0, 0, 0};
+extern "C" void emu_set_lean(int on) { emu_lean[0] = on; }
+extern "C" void emu_get_lean(int *out) { for (int k = 0; k < 4; ++k) out[k] = emu_lean[k]; }
+
 extern "C" int emu_eval(int mesh_kind,
                         // grid mesh
                         int gn, int gm, double gx0, double gy0, double gdx, double gdy,
@@ -184,6 +190,29 @@ extern "C" int emu_eval(int mesh_kind,
   p.kmax = kmax; p.nbr = nbr; p.nbr_cnt = nbr_cnt; p.cell_bb = cell_bb.data();
   p.mass = mass; p.fcell = fcell; p.hslot = hslot; p.touched = touched; p.mom = mom;
   p.counters = cnt.data(); p.stats = 1; p.flags = flags4; p.filter_tol = filter_tol;
+  // the block grid (k_blk_count / k_blk_scatter / k_blk_fill / k_gather_w): ~1 Dirac per row-major bin
+  const int bG = std::max(1, (int)std::ceil(std::sqrt((double)N)));
+  const size_t nbb = (size_t)bG * bG;
+  p.bG = bG; p.bph = ext / bG; p.binv = bG / ext;
+  std::vector<int> rm_start(nbb + 1, 0), rm2s(N), blk(N);
+  std::vector<double> xr(N), yr(N), wr(N);
+  for (int k = 0; k < N; ++k) {
+    const int bx = std::min(std::max((int)((xs[k] - p.px0) * p.binv), 0), bG - 1);
+    const int by = std::min(std::max((int)((ys[k] - p.py0) * p.binv), 0), bG - 1);
+    blk[k] = by * bG + bx;
+    rm_start[blk[k] + 1]++;
+  }
+  for (size_t q = 0; q < nbb; ++q) rm_start[q + 1] += rm_start[q];
+  {
+    std::vector<int> fill(rm_start.begin(), rm_start.end() - 1);
+    for (int k = 0; k < N; ++k) {  // ascending k inside a bin, as k_blk_fill sorts
+      const int pos = fill[blk[k]]++;
+      xr[pos] = xs[k]; yr[pos] = ys[k]; wr[pos] = ws[k]; rm2s[pos] = k;
+    }
+  }
+  p.xr = xr.data(); p.yr = yr.data(); p.wr = wr.data(); p.rm2s = rm2s.data(); p.rm_start = rm_start.data();
+  const bool graded = (wstat[3] - wstat[2]) > MA_LEAN_RANGE * p.bph * p.bph;
+  emu_lean[1] = emu_lean[2] = emu_lean[3] = 0;
   // ---- K2 ----
   const int maxv_cell = kmax + 4;
   {
@@ -194,7 +223,21 @@ extern "C" int emu_eval(int mesh_kind,
       // kmax = 16 is the packed-polygon class of the GPU (capacity 16), the larger ones shift arrays
       PolyRef<1, true> PP{px.data(), py.data(), pt.data()};
       PolyRef<1, false> PA{px.data(), py.data(), pt.data()};
-      int n = (kmax == 16) ? cell_build(p, i, PP, 16, &fl) : cell_build(p, i, PA, maxv_cell, &fl);
+      int n = -2;
+      if (kmax == 16 && emu_lean[0] && !graded) {
+        for (int pass = 0; pass < 2 && n == -2; ++pass) {
+          CellSearch<PolyRef<1, true>> S;
+          S.init(p, i, PP);
+          bool cert = false;
+          if (pass == 0) block_search<2>(p, S, PP, 16, true, cert);
+          else block_search<3>(p, S, PP, 16, true, cert);
+          if (cert) { n = S.n; emu_lean[1 + pass]++; }
+        }
+      }
+      if (n == -2) {
+        emu_lean[3]++;
+        n = (kmax == 16) ? cell_build(p, i, PP, 16, &fl) : cell_build(p, i, PA, maxv_cell, &fl);
+      }
       flags |= fl;
       if (n < 0) n = 0;
       auto finish = [&](auto &P) {

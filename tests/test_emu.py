@@ -164,3 +164,56 @@ def test_array_polygon_classes(oracle_mod, emu_mod, kmax):
     r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], kmax=kmax, seg=True)
     assert r["flags"] == 0 and common.same_pattern(ref[2], r["H"])
     assert np.abs(r["g"] - ref[1]).max() <= 1e-10 * np.abs(ref[1]).max()
+
+
+@pytest.mark.parametrize("name,scale,weights", [("c1", 0.2, "zero"), ("c1", 0.2, "0.3"), ("c2", 0.02, "0.5"),
+                                                ("c3", 0.003, "0.3"), ("c5", 0.0005, "zero"), ("c1r", 0.1, "zero")])
+def test_block_kernel_lane_code(oracle_mod, emu_mod, name, scale, weights):
+    """K2's fast path (ma_block.cuh, what k_cells_block runs): block of radius 2, then 3, then CellSearch for the
+    cells neither certifies — same neighbours, masses and Hessian as the oracle, and most cells certified."""
+    case = common.make_case(name, scale, weights)
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(case["w"])
+    emu_mod.set_lean(True)
+    try:
+        r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], seg=case["emu_mesh"]["kind"] == "grid")
+        c2, c3, rest = emu_mod.lean_counts()
+    finally:
+        emu_mod.set_lean(False)
+    assert r["flags"] == 0
+    assert c2 + c3 + rest == case["N"] and c2 + c3 >= 0.9 * case["N"]
+    assert abs(r["f"] - f0) <= 1e-10 * abs(f0)
+    assert np.abs(r["g"] - g0).max() <= 1e-10 * np.abs(g0).max()
+    assert common.same_pattern(H0, r["H"])
+    assert abs(H0 - r["H"]).max() <= 1e-10 * np.abs(H0.diagonal()).max()
+
+
+def test_block_kernel_degenerate_and_forced_exact(oracle_mod, emu_mod):
+    """Lattice (every Voronoi vertex a co-circular quadruple), a jittered grid as in tests/bench_opttransport.cpp:45-60,
+    and every sign forced through the double-double stage."""
+    emu_mod.set_lean(True)
+    try:
+        n = 12
+        vx, vy, tri = inputs.unit_square_mesh()
+        abc = inputs.pl_coefficients(vx, vy, np.ones(4), tri)
+        mesh = dict(kind="mesh", vx=vx, vy=vy, tri=tri, abc=abc)
+        c = (np.arange(n) + 0.5) / n
+        X = np.stack(np.meshgrid(c, c, indexing="ij"), -1).reshape(-1, 2)
+        r = emu_mod.evaluate(mesh, X, np.zeros(n * n))
+        assert np.allclose(r["g"], 1.0 / n ** 2, atol=1e-14) and np.abs(r["H"].sum(1)).max() < 1e-12
+        Hd = r["H"].toarray()
+        assert np.allclose(np.diag(Hd)[[n + 1, 2 * n + 2]], 2.0, atol=1e-12)
+        # jittered grid on the 2 x 2 image mesh
+        case = common.make_case("c1r", 0.001, "zero")
+        X = np.clip(inputs.jittered_grid_points(30, 11), -1 + 1e-9, 1 - 1e-9)
+        cfg = case["cfg"]
+        orc = oracle_mod.Oracle(cfg["vx"], cfg["vy"], cfg["tri"], case["abc"])
+        orc.set_points(X)
+        f0, g0, H0 = orc.kantorovich(np.zeros(len(X)))
+        for tol in (1e-11, 1e300):
+            r = emu_mod.evaluate(case["emu_mesh"], X, np.zeros(len(X)), seg=True, filter_tol=tol)
+            assert sum(emu_mod.lean_counts()[:2]) > 0.9 * len(X)
+            assert abs(r["f"] - f0) <= 1e-10 * abs(f0) and np.abs(r["g"] - g0).max() <= 1e-10 * g0.max()
+            assert common.same_pattern(H0, r["H"])
+    finally:
+        emu_mod.set_lean(False)
