@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libma_b200.so")
 SOURCES = ["ma_b200.cu"]
-HEADERS = ["ma_geom.cuh", "ma_cell.cuh", "ma_seg.cuh", "ma_kernels.cuh", "ma_pcg.cuh"]
+HEADERS = ["ma_geom.cuh", "ma_cell.cuh", "ma_block.cuh", "ma_seg.cuh", "ma_kernels.cuh", "ma_pcg.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -28,9 +28,11 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
+    tmp = LIB_PATH + f".{os.getpid()}.tmp"
     cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB_PATH)  # atomic: a snapshot / another process never sees a half-written library
     return LIB_PATH
 
 

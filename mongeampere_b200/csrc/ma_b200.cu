@@ -56,7 +56,7 @@ struct ma_ctx {
   int mesh_kind = MESH_NONE;
   int nV = 0, nF = 0;
   double bb[4] = {0, 0, 0, 0};
-  Buf vx, vy, tri, abc, rho_v, tbin_ptr, tbin_face;
+  Buf vx, vy, tri, abc, rho_v, rho_p, tbin_ptr, tbin_face;
   int tg = 1;
   double tinvx = 1, tinvy = 1;
   int gn = 0, gm = 0;
@@ -284,7 +284,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
-                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->cgbar, &c->cgw1, &c->cgpp, &c->bin_rm,
+                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->rho_p, &c->cgbar, &c->cgw1, &c->cgpp, &c->bin_rm,
                   &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->hard1, &c->hard2, &c->hard_n};
     for (Buf *b : all) release(*b);
     for (auto &ev : c->ev)
@@ -488,6 +488,18 @@ extern "C" int ma_set_grid(ma_ctx *c, int n, int m, double x0, double y0, double
   c->bb[2] = x0 + (n - 1) * dx; c->bb[3] = y0 + (m - 1) * dy;
   CKR(upload(c, c->abc, abc.data(), abc.size() * 8));
   CKR(upload(c, c->rho_v, rho_v, (size_t)n * m * 8));
+  {  // one replicated layer around the grid for the line-major K3 (ma_seg.cuh: seg_rv)
+    std::vector<double> pad((size_t)(n + 2) * (m + 2));
+    for (int a = -1; a <= n; ++a) {
+      const double *src = rho_v + (size_t)std::min(std::max(a, 0), n - 1) * m;
+      double *dst = pad.data() + (size_t)(a + 1) * (m + 2);
+      dst[0] = src[0];
+      memcpy(dst + 1, src, (size_t)m * 8);
+      dst[m + 1] = src[m - 1];
+    }
+    CKR(upload(c, c->rho_p, pad.data(), pad.size() * 8));
+    CK(cudaStreamSynchronize(c->stream));  // pad is freed at the end of this scope
+  }
   CK(cudaStreamSynchronize(c->stream));
   invalidate_eval(c);
   return MA_OK;
@@ -619,6 +631,7 @@ int fill_params(ma_ctx *c, Params &p) {
   p.nF = c->nF;
   p.abc = c->abc.as<double>();
   p.rho_v = c->rho_v.as<double>();
+  p.rho_p = c->rho_p.as<double>();
   p.gn = c->gn; p.gm = c->gm; p.gx0 = c->gx0; p.gy0 = c->gy0; p.gdx = c->gdx; p.gdy = c->gdy;
   p.vx = c->vx.as<double>(); p.vy = c->vy.as<double>(); p.tri = c->tri.as<int>();
   p.tg = c->tg; p.tinvx = c->tinvx; p.tinvy = c->tinvy;
@@ -710,7 +723,7 @@ template <bool POLY> int launch_cells_kmax(ma_ctx *c, const Params &p) {
   }
 }
 template <int MAXV, int NT, int MODE> int launch_seg(ma_ctx *c, const Params &p) {
-  size_t sm = cells_smem_bytes<MAXV, NT>();
+  size_t sm = seg_smem_bytes<MAXV, NT, MODE>();
   CK(cudaFuncSetAttribute(k_seg<MAXV, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   k_seg<MAXV, NT, MODE><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
   c->launches++;

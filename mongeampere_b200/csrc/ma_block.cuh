@@ -84,28 +84,9 @@ MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv
     if (MA_WARP_ANY(test)) {
       if (test) {
         MA_COUNT(1);
-        unsigned long long in = 0ull, unc = 0ull;
-        const double cmag = 0.5 * (dd2 + fabs(dw));
         const int n = S.n;
-        for (int k = 0; k < n; ++k) {
-          const double tx = P.X(k) * Dx, ty = P.Y(k) * Dy;
-          const double val = c - (tx + ty);
-          if (val > 0.0) in |= 1ull << k;
-          if (fabs(val) <= p.filter_tol * (cmag + fabs(tx) + fabs(ty))) unc |= 1ull << k;
-        }
         const int jj = p.rm2s[pos];
-        if (unc) {  // exact stage (CellSearch::exact_inside), rare
-          for (int k = 0; k < n; ++k)
-            if ((unc >> k) & 1ull) {
-              if (S.exact_inside(p, P, k, jj)) in |= 1ull << k;
-              else in &= ~(1ull << k);
-            }
-#ifdef __CUDA_ARCH__
-          atomicAdd(p.flags + 2, 1);
-#else
-          p.flags[2] += 1;
-#endif
-        }
+        const unsigned long long in = S.sign_mask(p, P, jj, Dx, Dy, c, dd2, dw);
         if (in == 0ull) { S.n = 0; S.phase = 2; }
         else if (in != lowmask64(n)) { S.jc = jj; S.cDx = Dx; S.cDy = Dy; S.cc = c; S.cin = in; cut = true; }
       }

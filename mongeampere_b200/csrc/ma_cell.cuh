@@ -59,6 +59,7 @@ struct Params {
   int nF;
   const double *abc;
   const double *rho_v;  // grid mesh: density at vertex (i, j) = rho_v[i * gm + j] (L2-resident: 8 B/vertex vs 24 B/face)
+  const double *rho_p;  // the same padded by one replicated layer: vertex (i, j), -1 <= i <= gn, at [(i+1)*(gm+2) + j+1]
   // grid mesh
   int gn, gm;
   double gx0, gy0, gdx, gdy;
@@ -191,6 +192,43 @@ template <class Poly> struct CellSearch {
     return dd_side(ddlineof(p, ta), ddlineof(p, tb), dd_bisector(xi, yi, wi, p.xs[jj], p.ys[jj], p.ws[jj])) > 0;
   }
 
+  // Bit k set <=> vertex k is strictly on i's side of the bisector { u.D = c } with site jj (pow_i < pow_j there).
+  // The sign of c - u.D is taken in fp64 behind a forward-error filter; what the filter cannot decide is
+  // re-evaluated in double-double from the original (y, w) (predicates.hpp:101-115,139-168).  The filter costs one
+  // |.|-min per vertex: it compares the smallest |value| with a bound on the rounding error that holds for every
+  // vertex, |u.D| <= sqrt(R2 dd2), and only then looks at the vertices one by one.
+  MA_DEV unsigned long long sign_mask(const Params &p, const Poly &P, int jj, double Dx, double Dy, double c, double dd2,
+                                      double dw) const {
+    unsigned long long in = 0ull;
+    double amin = 1.0 / 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double val = c - (P.X(k) * Dx + P.Y(k) * Dy);
+      if (val > 0.0) in |= 1ull << k;
+      amin = fmin(amin, fabs(val));
+    }
+    const double cmag = 0.5 * (dd2 + fabs(dw));
+    // (|c| + |ux Dx| + |uy Dy|)^2 <= 2 cmag^2 + 4 R2 dd2
+    if (amin * amin <= (p.filter_tol * p.filter_tol) * (2.0 * cmag * cmag + 4.0 * R2 * dd2)) {
+      bool any = false;
+      for (int k = 0; k < n; ++k) {
+        const double tx = P.X(k) * Dx, ty = P.Y(k) * Dy;
+        if (fabs(c - (tx + ty)) <= p.filter_tol * (cmag + fabs(tx) + fabs(ty))) {
+          any = true;
+          if (exact_inside(p, P, k, jj)) in |= 1ull << k;
+          else in &= ~(1ull << k);
+        }
+      }
+      if (any) {
+#ifdef __CUDA_ARCH__
+        atomicAdd(p.flags + 2, 1);
+#else
+        p.flags[2] += 1;
+#endif
+      }
+    }
+    return in;
+  }
+
   MA_DEV void init(const Params &p, int cell, Poly &P) {
     i = cell;
     xi = p.xs[i]; yi = p.ys[i]; wi = p.ws[i];
@@ -289,29 +327,8 @@ template <class Poly> struct CellSearch {
           const double e = c - (mx * Dx + my * Dy);
           // (margin 1e-9: anything closer to tangency than that goes through the filtered sign test below)
           if (!(e >= 0.0 && e * e >= rc2 * dd2 * (1.0 + 1e-9))) {
-            unsigned long long in = 0ull, unc = 0ull;
             MA_COUNT(1);
-            // sign of pow_j - pow_i at every vertex with a forward-error filter; what the filter cannot decide is
-            // re-evaluated in double-double from the original (y, w) (predicates.hpp:101-115,139-168)
-            const double cmag = 0.5 * (dd2 + fabs(dw));
-            for (int k = 0; k < n; ++k) {
-              const double tx = P.X(k) * Dx, ty = P.Y(k) * Dy;
-              const double val = c - (tx + ty);
-              if (val > 0.0) in |= 1ull << k;
-              if (fabs(val) <= p.filter_tol * (cmag + fabs(tx) + fabs(ty))) unc |= 1ull << k;
-            }
-            if (unc) {
-              for (int k = 0; k < n; ++k)
-                if ((unc >> k) & 1ull) {
-                  if (exact_inside(p, P, k, jj)) in |= 1ull << k;
-                  else in &= ~(1ull << k);
-                }
-#ifdef __CUDA_ARCH__
-              atomicAdd(p.flags + 2, 1);
-#else
-              p.flags[2] += 1;
-#endif
-            }
+            const unsigned long long in = sign_mask(p, P, jj, Dx, Dy, c, dd2, dw);
             const unsigned long long full = lowmask64(n);
             if (in == 0ull) { n = 0; phase = 2; }
             else if (in != full) { jc = jj; cDx = Dx; cDy = Dy; cc = c; cin = in; }

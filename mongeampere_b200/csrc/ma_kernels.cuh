@@ -693,17 +693,18 @@ template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT, (MAX
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
   double *sy = sx + MAXV * NT;
-  int *st = reinterpret_cast<int *>(sy + MAXV * NT);
+  double *se = sy + MAXV * NT;  // per-edge accumulators of the Hessian's edge integrals (kantorovich mode)
   const int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
   if (i >= p.cell_hi) return;
-  PolyRef<NT, false> P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+  PolyRef<NT, false> P{sx + threadIdx.x, sy + threadIdx.x, nullptr};  // the tags stay in global memory
   const int n = p.poly_n[i];
   for (int k = 0; k < n; ++k) {
     const size_t o = (size_t)k * p.N + i;
-    P.X(k) = p.poly_x[o]; P.Y(k) = p.poly_y[o]; P.T(k) = p.poly_t[o];
+    P.X(k) = p.poly_x[o]; P.Y(k) = p.poly_y[o];
   }
   SegAcc acc;
-  unsigned long long touched = cell_integrate_grid<MODE>(p, i, P, n, acc, p.hslot + (size_t)i * p.kmax);
+  unsigned long long touched = cell_integrate_lines<MODE, NT>(p, i, P, n, acc, p.hslot + (size_t)i * p.kmax, se + threadIdx.x,
+                                                              [&](int k) { return p.poly_t[(size_t)k * p.N + i]; });
   if (MODE == MODE_KANTOROVICH) {
     p.mass[i] = acc.mass;
     p.fcell[i] = acc.mass * p.ws[i] - acc.cost;
@@ -720,6 +721,9 @@ template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT, (MAX
     o[4] = acc.m[3] + 2 * yi * acc.m[1] + yi * yi * mass;
     o[5] = acc.m[4] + xi * acc.m[1] + yi * acc.m[0] + xi * yi * mass;
   }
+}
+template <int MAXV, int NT, int MODE> constexpr size_t seg_smem_bytes() {
+  return (size_t)MAXV * NT * (8 + 8 + (MODE == MODE_KANTOROVICH ? 8 : 0));
 }
 
 // ================================================================================================

@@ -24,11 +24,9 @@
 //   g runs over {1, |u|^2} for kantorovich (mass, cost) and {1, ux, uy [, ux², uy², ux uy]} for the
 //   moments.  All line integrals are of degree <= 3 and are taken with Simpson's rule (exact).
 //
-// On a grid the sub-segments are found by walking each cell edge through the three families of mesh
-// lines (x = const, y = const, diagonals) and each mesh line through its chord of the convex cell;
-// no orientation predicate decides anything, so the result depends continuously on the input and
-// there is nothing to make robust.  One THREAD handles one cell (the polygon stays in shared memory
-// where K2 built it).  SURVEY.md §7.2 "two regimes", DESIGN.md §3.
+// On a grid the three families of mesh lines (x = const, y = const, diagonals) are enumerated directly:
+// no polygon is clipped and no orientation predicate decides anything, so the result depends continuously
+// on the input.  One THREAD handles one cell.  SURVEY.md §7.2 "two regimes", DESIGN.md §3.
 #pragma once
 #include "ma_block.cuh"
 
@@ -84,171 +82,262 @@ MA_DEV void seg_item_mesh(double ax, double ay, double bx, double by, double kh2
   }
 }
 
-// next crossing of u(t) = u0 + t*sl with an integer level: initial state of one line family
-MA_DEV void seg_family_init(double u0, double sl, int &kn, int &stp, double &inv, double &tn) {
-  if (sl > 0.0) { kn = (int)floor(u0) + 1; stp = 1; }
-  else if (sl < 0.0) { kn = (int)ceil(u0) - 1; stp = -1; }
-  else { kn = 0; stp = 0; inv = 0.0; tn = 1.0 / 0.0; return; }
-  inv = 1.0 / sl;
-  tn = ((double)kn - u0) * inv;
+// ------------------------------------------------------------------------------------------------
+// (A) and (B) with INDEPENDENT items (no walk along the edges).
+//
+// Along one cell edge u(t) = A + t d the integrand phi_T = lam_T g/(dg+3) + r_T g/(dg+2) changes face at every
+// crossing with a mesh line.  Across the mesh edge m on the line { n.u = h } (n = gradient direction of the
+// line's level function, kappa_m as in (B) above) phi jumps by
+//      after - before = - kappa_m g(u) [ (n_c.u - h_c)/(dg+3) - h_c/((dg+2)(dg+3)) ] ,
+// n_c = +-n the normal in the direction of travel, h_c = +-h.  So
+//      ∫_0^1 phi_{T(t)} dt = ∫_0^1 phi_{T0} dt + Σ_{crossings c} ∫_{t_c}^1 (jump of c) dt ,
+// T0 = the face at the start of the edge: one closed-form term per edge plus one per crossing, each of degree
+// <= 3 in t (Simpson, exact), and the Hessian's ∫ rho ds the same way (jump of rho = - kappa_m (n_c.u - h_c)).
+// The crossings are enumerated LINE by line together with part (B): a mesh line crosses the convex cell on two
+// edges; the two crossings give two jump terms and the end points of the chord whose unit intervals are (B).
+// Every item is O(1) and independent of the others; no DDA state, no midpoint classification.
+//
+// Consistency (what makes the sum exact whatever the alignment of the cell with the mesh): one sign rule,
+// g_v = level function at vertex v, "v is on the low side" <=> g_v < 0, decides (a) the face T0 of an edge
+// (floor of the start vertex' grid coordinates = the count of lines with g >= 0), (b) which edges a line crosses
+// and (c) hence whether its chord takes part in (B).  An edge lying ON a mesh line is then attributed to the high
+// side, and the line's chord (which runs along that very edge when the cell is on the low side) supplies the
+// difference.  Vertices closer than rounding are made identical first, so that they get identical signs.
+// ------------------------------------------------------------------------------------------------
+// one jump term: crossing point (cx, cy), end of the edge (bx, by), tau = 1 - t_c, dB = n_c.B - h_c >= 0,
+// hc = h_c, khl = kappa_m * (h_e |e|) of the edge
+template <int MODE>
+MA_DEV void seg_jump_item(double cx, double cy, double bx, double by, double tau, double dB, double hc, double khl, SegAcc &acc) {
+  const double mx = 0.5 * (cx + bx), my = 0.5 * (cy + by);
+  const double w6 = khl * tau * (1.0 / 6.0);
+  // psi(s) = dB(s)/(dg+3) - hc/((dg+2)(dg+3)) at s = 0, 1/2, 1 of [t_c, 1]
+  {  // g = 1 (dg = 0)
+    const double p0 = -hc * (1.0 / 6.0), pm = dB * (1.0 / 6.0) + p0, p1 = dB * (1.0 / 3.0) + p0;
+    acc.mass -= w6 * (p0 + 4.0 * pm + p1);
+  }
+  if (MODE == MODE_KANTOROVICH) {  // g = |u|^2 (dg = 2)
+    const double p0 = -hc * (1.0 / 20.0), pm = dB * (1.0 / 10.0) + p0, p1 = dB * (1.0 / 5.0) + p0;
+    const double qC = cx * cx + cy * cy, qM = mx * mx + my * my, qB = bx * bx + by * by;
+    acc.cost -= w6 * (qC * p0 + 4.0 * (qM * pm) + qB * p1);
+  } else {
+    {  // g = ux, uy (dg = 1)
+      const double p0 = -hc * (1.0 / 12.0), pm = dB * (1.0 / 8.0) + p0, p1 = dB * (1.0 / 4.0) + p0;
+      acc.m[0] -= w6 * (cx * p0 + 4.0 * (mx * pm) + bx * p1);
+      acc.m[1] -= w6 * (cy * p0 + 4.0 * (my * pm) + by * p1);
+    }
+    if (MODE == MODE_MOMENTS2) {  // g = ux^2, uy^2, ux uy (dg = 2)
+      const double p0 = -hc * (1.0 / 20.0), pm = dB * (1.0 / 10.0) + p0, p1 = dB * (1.0 / 5.0) + p0;
+      acc.m[2] -= w6 * (cx * cx * p0 + 4.0 * (mx * mx * pm) + bx * bx * p1);
+      acc.m[3] -= w6 * (cy * cy * p0 + 4.0 * (my * my * pm) + by * by * p1);
+      acc.m[4] -= w6 * (cx * cy * p0 + 4.0 * (mx * my * pm) + bx * by * p1);
+    }
+  }
 }
 
-// Integrals of one cell (polygon P of n vertices, local coordinates, vertex k = start of edge k whose
-// supporting line is named by tag k: site index >= 0, or < 0 for a side of the mesh bounding box).
-// MODE_KANTOROVICH additionally writes, for every Laguerre edge in polygon order (= the order of
-// cell_emit's neighbour list), hslot = ∫_edge rho ds / (2 |y_i - y_j|)  and returns the touched mask.
-template <int MODE, class Poly>
-MA_DEV unsigned long long cell_integrate_grid(const Params &p, int i, const Poly &P, int n, SegAcc &acc,
-                                              double *hslot_row) {
+// The line-major formulation reads the vertex densities from rho_p: the grid PADDED by one layer of replicated
+// values on every side (vertex (i, j), -1 <= i <= gn, at rho_p[(i + 1) * (gm + 2) + (j + 1)]).  The density is thereby
+// extended continuously (and piecewise linearly) one square beyond the domain, and the sign rule below needs no
+// special case on the rim: an edge lying ON the domain boundary is attributed to the (fictitious) square outside
+// and the boundary line's chord supplies the difference, exactly as for an interior mesh line.
+MA_DEV const double *seg_rv(const Params &p, int i, int j) { return p.rho_p + (size_t)(i + 1) * (p.gm + 2) + (j + 1); }
+
+// kappa of the unit mesh edge mm of line (fam, k): n.(grad rho_T1 - grad rho_T2), n the outward normal of T1
+MA_DEV double seg_kappa(const Params &p, int fam, int k, int mm, double inv_dx, double inv_dy, double dcoef) {
+  const int gs = p.gm + 2;
+  if (fam == 0) {  // vertical edge (k,mm)-(k,mm+1): left = face 0 of square (k-1,mm), right = face 1 of (k,mm)
+    const double *rv = seg_rv(p, k, mm);
+    return ((rv[0] - rv[-gs]) - (rv[gs + 1] - rv[1])) * inv_dx;
+  }
+  if (fam == 1) {  // horizontal edge (mm,k)-(mm+1,k): below = face 1 of square (mm,k-1), above = face 0 of (mm,k)
+    const double *rv = seg_rv(p, mm, k);
+    return ((rv[0] - rv[-1]) - (rv[gs + 1] - rv[gs])) * inv_dy;
+  }
+  const double *rv = seg_rv(p, mm, mm - k);  // diagonal of square (mm, mm-k)
+  return ((rv[0] + rv[gs + 1]) - (rv[1] + rv[gs])) * dcoef;
+}
+
+// E: per-edge accumulator of ∫_0^1 rho(u(t)) dt, element k at E[k * ES] (shared memory column of the thread)
+// tagof(k): the tag of edge k (only the Hessian slots at the very end need it, so it need not be staged with the vertices)
+template <int MODE, int ES, class Poly, class TagOf>
+MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Poly &P, int n, SegAcc &acc,
+                                               double *hslot_row, double *E, TagOf tagof) {
   const double xi = p.xs[i], yi = p.ys[i];
   const double inv_dx = 1.0 / p.gdx, inv_dy = 1.0 / p.gdy;
   const double ox = (xi - p.gx0) * inv_dx, oy = (yi - p.gy0) * inv_dy;  // grid coordinate f = u * inv + o
-  const int gn2 = p.gn - 2, gm2 = p.gm - 2;
+  const int gs = p.gm + 2;
+  // squares -1 .. gn-1 x -1 .. gm-1 (one fictitious layer around the gn-1 x gm-1 real ones)
+  const int sx_hi = p.gn - 1, sy_hi = p.gm - 1;
   acc.mass = acc.cost = 0.0;
 #pragma unroll
   for (int q = 0; q < 5; ++q) acc.m[q] = 0.0;
   unsigned long long touched = 0ull;
   if (n < 3) return touched;
-
-  // ---------------- (A) the cell's own edges ----------------
-  int slot = 0;
-  double fxmin = 1e300, fxmax = -1e300, fymin = 1e300, fymax = -1e300, fdmin = 1e300, fdmax = -1e300;
-  double Ax = P.X(0), Ay = P.Y(0);
-  for (int k = 0; k < n; ++k) {
-    const int kk = (k + 1 == n) ? 0 : k + 1;
-    const double Bx = P.X(kk), By = P.Y(kk);
-    const int tag = P.T(k);
-    const double dx = Bx - Ax, dy = By - Ay;
-    const double hL = dy * Ax - dx * Ay;  // h_e * |e|  (outward normal (dy,-dx)/|e| of a CCW polygon)
-    const double fAx = Ax * inv_dx + ox, fAy = Ay * inv_dy + oy;
-    const double sx = dx * inv_dx, sy = dy * inv_dy;
-    fxmin = fmin(fxmin, fAx); fxmax = fmax(fxmax, fAx);
-    fymin = fmin(fymin, fAy); fymax = fmax(fymax, fAy);
-    fdmin = fmin(fdmin, fAx - fAy); fdmax = fmax(fdmax, fAx - fAy);
-    int kx, ky, kd, stx, sty, std_;
-    double ivx, ivy, ivd, tx, ty, td;
-    const double u0d = fAx - fAy, sd = sx - sy;
-    seg_family_init(fAx, sx, kx, stx, ivx, tx);
-    seg_family_init(fAy, sy, ky, sty, ivy, ty);
-    seg_family_init(u0d, sd, kd, std_, ivd, td);
-    double tc = 0.0, cx = Ax, cy = Ay, E = 0.0;
-    const int cap = 3 * (p.gn + p.gm) + 16;  // more crossings than lines cannot happen
-    for (int it = 0; it < cap; ++it) {
-      const double t1 = fmin(fmin(tx, ty), fmin(td, 1.0));
-      if (t1 > tc) {
-        const double ex = Ax + t1 * dx, ey = Ay + t1 * dy;
-        const double tm = 0.5 * (tc + t1);
-        const double fmx = fAx + tm * sx, fmy = fAy + tm * sy;
-        const int si = seg_clampi((int)floor(fmx), 0, gn2), sj = seg_clampi((int)floor(fmy), 0, gm2);
-        const bool upper = (fmx - (double)si) < (fmy - (double)sj);  // face 1 of the square (above the diagonal)
-        // the face's plane from its three vertex densities: a, b and the value r at y_i
-        const double *rv = p.rho_v + (size_t)si * p.gm + sj;
-        const double r00 = rv[0], r11 = rv[p.gm + 1], rmid = upper ? rv[1] : rv[p.gm];  // r01 or r10
-        const double a = (upper ? (r11 - rmid) : (rmid - r00)) * inv_dx;
-        const double b = (upper ? (rmid - r00) : (r11 - rmid)) * inv_dy;
-        const double r = r00 - a * (((double)si - ox) * p.gdx) - b * (((double)sj - oy) * p.gdy);
-        const double dt = t1 - tc;
-        seg_item_cell<MODE>(cx, cy, ex, ey, a, b, r, hL * dt, acc);
-        if (MODE == MODE_KANTOROVICH) E += dt * (a * (0.5 * (cx + ex)) + b * (0.5 * (cy + ey)) + r);
-        tc = t1; cx = ex; cy = ey;
-      }
-      if (t1 >= 1.0) break;
-      if (tx <= t1) { kx += stx; tx = ((double)kx - fAx) * ivx; }
-      if (ty <= t1) { ky += sty; ty = ((double)ky - fAy) * ivy; }
-      if (td <= t1) { kd += std_; td = ((double)kd - u0d) * ivd; }
+  // Two clean-ups that make coincidences EXACT, so that the sign rule sees them the same way everywhere:
+  //  * vertices closer than rounding become identical (degenerate zero-length edges of co-circular sites);
+  //  * a coordinate within 1e-11 grid units of a mesh line is moved onto the value that line has in local
+  //    coordinates: all vertices on one mesh line (the two ends of an edge along the domain boundary, of an
+  //    edge of a pixel-aligned lattice cell) then share one bit pattern, the edge between them does not
+  //    "cross" its own line, and every position interpolated along it is that same value.
+  {
+    double sc = 0.0;
+    for (int k = 0; k < n; ++k) {
+      double X = P.X(k), Y = P.Y(k);
+      const double fx = X * inv_dx + ox, fy = Y * inv_dy + oy;
+      const double rx = rint(fx), ry = rint(fy);
+      if (fabs(fx - rx) < 1e-11) { X = (rx - ox) * p.gdx; P.X(k) = X; }
+      if (fabs(fy - ry) < 1e-11) { Y = (ry - oy) * p.gdy; P.Y(k) = Y; }
+      sc = fmax(sc, fmax(fabs(X), fabs(Y)));
     }
-    if (tag >= 0) {
-      if (MODE == MODE_KANTOROVICH) {
-        const double len = sqrt(dx * dx + dy * dy);
-        if (len > 0.0 && slot < p.kmax) {
-          const double Dx = p.xs[tag] - xi, Dy = p.ys[tag] - yi;
-          hslot_row[slot] = E * len * (0.5 / sqrt(Dx * Dx + Dy * Dy));
-          touched |= 1ull << slot;
-        }
-      }
-      ++slot;
+    const double eps2 = (1e-13 * sc) * (1e-13 * sc);
+    for (int k = 0; k + 1 < n; ++k) {
+      const double ex = P.X(k + 1) - P.X(k), ey = P.Y(k + 1) - P.Y(k);
+      if (ex * ex + ey * ey <= eps2) { P.X(k + 1) = P.X(k); P.Y(k + 1) = P.Y(k); }
     }
-    Ax = Bx; Ay = By;
   }
-
-  // ---------------- (B) interior mesh edges inside the cell ----------------
-  // chord of the line { fam(u) = level } in the convex polygon, as an interval [lo, hi] of the
-  // line's own parameter (fy on x-lines, fx on y-lines and diagonals)
+  // ---------------- per edge: the term of the face at its start ----------------
+  double fxmin = 1e300, fxmax = -1e300, fymin = 1e300, fymax = -1e300, fdmin = 1e300, fdmax = -1e300;
+  {
+    double Ax = P.X(0), Ay = P.Y(0);
+    for (int k = 0; k < n; ++k) {
+      const int kk = (k + 1 == n) ? 0 : k + 1;
+      const double Bx = P.X(kk), By = P.Y(kk);
+      const double dx = Bx - Ax, dy = By - Ay;
+      const double hL = dy * Ax - dx * Ay;  // h_e * |e|
+      const double fAx = Ax * inv_dx + ox, fAy = Ay * inv_dy + oy, fAd = fAx - fAy;
+      fxmin = fmin(fxmin, fAx); fxmax = fmax(fxmax, fAx);
+      fymin = fmin(fymin, fAy); fymax = fmax(fymax, fAy);
+      fdmin = fmin(fdmin, fAd); fdmax = fmax(fdmax, fAd);
+      const int si = seg_clampi((int)floor(fAx), -1, sx_hi), sj = seg_clampi((int)floor(fAy), -1, sy_hi);
+      const bool upper = (fAd - (double)(si - sj)) < 0.0;  // low side of the square's diagonal = face 1
+      const double *rv = seg_rv(p, si, sj);
+      const double r00 = rv[0], r11 = rv[gs + 1], rmid = upper ? rv[1] : rv[gs];
+      const double a = (upper ? (r11 - rmid) : (rmid - r00)) * inv_dx;
+      const double b = (upper ? (rmid - r00) : (r11 - rmid)) * inv_dy;
+      const double r = r00 - a * (((double)si - ox) * p.gdx) - b * (((double)sj - oy) * p.gdy);
+      seg_item_cell<MODE>(Ax, Ay, Bx, By, a, b, r, hL, acc);
+      if (MODE == MODE_KANTOROVICH) E[k * ES] = a * (0.5 * (Ax + Bx)) + b * (0.5 * (Ay + By)) + r;
+      Ax = Bx; Ay = By;
+    }
+  }
+  // ---------------- per mesh line: two jump terms + the chord's unit intervals ----------------
   const double ddiag = sqrt(p.gdx * p.gdx + p.gdy * p.gdy);
   const double ninv = 1.0 / sqrt(inv_dx * inv_dx + inv_dy * inv_dy);  // 1 / |(1/dx, -1/dy)|
+  const double dcoef = (inv_dx * inv_dx + inv_dy * inv_dy) * ninv;
   for (int fam = 0; fam < 3; ++fam) {
     const double lo_f = fam == 0 ? fxmin : (fam == 1 ? fymin : fdmin);
     const double hi_f = fam == 0 ? fxmax : (fam == 1 ? fymax : fdmax);
-    int k0 = (int)floor(lo_f) + 1, k1 = (int)ceil(hi_f) - 1;
-    if (fam == 0) { k0 = max(k0, 1); k1 = min(k1, gn2); }
-    else if (fam == 1) { k0 = max(k0, 1); k1 = min(k1, gm2); }
-    else { k0 = max(k0, -gm2); k1 = min(k1, gn2); }
+    // line k has a vertex on either side  <=>  min < k <= max; lines of the padded grid only
+    int k0 = (int)floor(lo_f) + 1, k1 = (int)floor(hi_f);
+    if (fam == 0) { k0 = max(k0, 0); k1 = min(k1, sx_hi); }
+    else if (fam == 1) { k0 = max(k0, 0); k1 = min(k1, sy_hi); }
+    else { k0 = max(k0, -sy_hi - 1); k1 = min(k1, sx_hi + 1); }
+    const double fscale = fam == 0 ? p.gdx : (fam == 1 ? p.gdy : ninv);  // level function -> distance
     for (int k = k0; k <= k1; ++k) {
-      double lo = 1e300, hi = -1e300;
-      {
-        // a convex polygon crosses the line on (at most) two edges: find them without doing any
-        // arithmetic inside the divergent branch, then intersect both after the loop, all lanes together
-        const double lev = (double)k;
-        double Px = P.X(0) * inv_dx + ox, Py = P.Y(0) * inv_dy + oy;
-        double gv = (fam == 0 ? Px : (fam == 1 ? Py : Px - Py)) - lev;
-        double sv = fam == 0 ? Py : Px;
-        double g1a = 0, g1b = 1, s1a = 0, s1b = 0, g2a = 0, g2b = 1, s2a = 0, s2b = 0;
-        int ncross = 0;
-        for (int v = 0; v < n; ++v) {
-          const int vv = (v + 1 == n) ? 0 : v + 1;
-          const double Qx = P.X(vv) * inv_dx + ox, Qy = P.Y(vv) * inv_dy + oy;
-          const double gw = (fam == 0 ? Qx : (fam == 1 ? Qy : Qx - Qy)) - lev;
-          const double sw = fam == 0 ? Qy : Qx;
-          const bool cross = (gv < 0.0) != (gw < 0.0);
-          const bool first = cross && ncross == 0, second = cross && ncross > 0;
-          g1a = first ? gv : g1a; g1b = first ? gw : g1b; s1a = first ? sv : s1a; s1b = first ? sw : s1b;
-          g2a = second ? gv : g2a; g2b = second ? gw : g2b; s2a = second ? sv : s2a; s2b = second ? sw : s2b;
-          ncross += cross ? 1 : 0;
-          gv = gw; sv = sw;
-        }
-        if (ncross >= 2) {
-          const double c1 = s1a + (g1a / (g1a - g1b)) * (s1b - s1a);
-          const double c2 = s2a + (g2a / (g2a - g2b)) * (s2b - s2a);
-          lo = fmin(c1, c2); hi = fmax(c1, c2);
-        }
+      const double lev = (double)k;
+      // the (at most two) edges with a sign change, without arithmetic inside the divergent branch
+      double Px = P.X(0) * inv_dx + ox, Py = P.Y(0) * inv_dy + oy;
+      double gv = (fam == 0 ? Px : (fam == 1 ? Py : Px - Py)) - lev;
+      int e1 = -1, e2 = -1;
+      double g1a = 0, g1b = 1, g2a = 0, g2b = 1;
+      for (int v = 0; v < n; ++v) {
+        const int vv = (v + 1 == n) ? 0 : v + 1;
+        const double Qx = P.X(vv) * inv_dx + ox, Qy = P.Y(vv) * inv_dy + oy;
+        const double gw = (fam == 0 ? Qx : (fam == 1 ? Qy : Qx - Qy)) - lev;
+        const bool cross = (gv < 0.0) != (gw < 0.0);
+        const bool first = cross && e1 < 0, second = cross && e1 >= 0;
+        if (second) { e2 = v; g2a = gv; g2b = gw; }
+        if (first) { e1 = v; g1a = gv; g1b = gw; }
+        gv = gw;
       }
+      if (e2 < 0) continue;
+      // unit mesh edges of this line in the padded grid: mm in [mlo, mhi]
+      int mlo, mhi;
+      if (fam == 0) { mlo = -1; mhi = sy_hi; }
+      else if (fam == 1) { mlo = -1; mhi = sx_hi; }
+      else { mlo = max(-1, k - 1); mhi = min(sx_hi, sy_hi + k); }
+      if (mhi < mlo) continue;
+      double hcoef;  // h of this line (n = the direction in which the level function grows)
+      if (fam == 0) hcoef = (lev - ox) * p.gdx;
+      else if (fam == 1) hcoef = (lev - oy) * p.gdy;
+      else hcoef = (lev - (ox - oy)) * ninv;
+      double send[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int e = c == 0 ? e1 : e2;
+        const double ga = c == 0 ? g1a : g2a, gb = c == 0 ? g1b : g2b;
+        const int ee = (e + 1 == n) ? 0 : e + 1;
+        const double Ax = P.X(e), Ay = P.Y(e), Bx = P.X(ee), By = P.Y(ee);
+        const double dx = Bx - Ax, dy = By - Ay;
+        const double tc = ga / (ga - gb), tau = 1.0 - tc;
+        // (exact at both ends: a crossing AT a vertex must get that vertex' own coordinates, whose floor decided
+        // the face of the edge that starts there)
+        const double cx = tc <= 0.5 ? Ax + tc * dx : Bx - tau * dx, cy = tc <= 0.5 ? Ay + tc * dy : By - tau * dy;
+        // Position of the crossing along the line -> the unit mesh edge that is crossed.  Interpolated between the
+        // grid coordinates of the edge's end points, the very values whose signs decide all crossings: when the
+        // edge runs along another mesh line within rounding, s then falls on the side of that line the edge
+        // is attributed to at t_c (recomputing it from (cx, cy) would round it anywhere).
+        const double fa = (fam == 0) ? (Ay * inv_dy + oy) : (Ax * inv_dx + ox);
+        const double fb = (fam == 0) ? (By * inv_dy + oy) : (Bx * inv_dx + ox);
+        const double s = tc <= 0.5 ? fa + tc * (fb - fa) : fb - tau * (fb - fa);
+        send[c] = s;
+        int mm = (int)floor(s);
+        if (fam == 2) {
+          // a diagonal's unit edge is square (mm, mm - k): take it from the coordinate that varies LESS along the
+          // edge (along a horizontal boundary edge fy is one exact value while fx passes the integers at the very
+          // places where the diagonals are crossed)
+          const double ga2 = Ay * inv_dy + oy, gb2 = By * inv_dy + oy;
+          if (fabs(gb2 - ga2) < fabs(fb - fa)) mm = (int)floor(tc <= 0.5 ? ga2 + tc * (gb2 - ga2) : gb2 - tau * (gb2 - ga2)) + k;
+        }
+        mm = seg_clampi(mm, mlo, mhi);
+        const double kap = seg_kappa(p, fam, k, mm, inv_dx, inv_dy, dcoef);
+        const double sgn = (ga < 0.0) ? 1.0 : -1.0;  // direction of travel across the line
+        const double dB = fabs(gb) * fscale;         // n_c.B - h_c
+        const double hL = dy * Ax - dx * Ay;
+        seg_jump_item<MODE>(cx, cy, Bx, By, tau, dB, sgn * hcoef, kap * hL, acc);
+        if (MODE == MODE_KANTOROVICH) E[e * ES] -= kap * dB * tau * 0.5;
+      }
+      // (B) the chord between the two crossings
+      const double lo = fmin(send[0], send[1]), hi = fmax(send[0], send[1]);
       if (!(hi > lo)) continue;
-      int m0 = (int)floor(lo), m1 = (int)floor(hi);
-      double hcoef;  // h of this line (constant along it)
-      if (fam == 0) { m0 = max(m0, 0); m1 = min(m1, gm2); hcoef = ((double)k - ox) * p.gdx; }
-      else if (fam == 1) { m0 = max(m0, 0); m1 = min(m1, gn2); hcoef = ((double)k - oy) * p.gdy; }
-      else {
-        m0 = max(m0, max(0, k)); m1 = min(m1, min(gn2, gm2 + k));
-        // n = (1/dx, -1/dy) * ninv; any point of the line has fx - fy = k:  n.u = ((fx-ox) - (fy-oy)) * ninv
-        hcoef = ((double)k - (ox - oy)) * ninv;
-      }
+      const int m0 = max((int)floor(lo), mlo), m1 = min((int)floor(hi), mhi);
       const double h2 = hcoef * hcoef;
       for (int mm = m0; mm <= m1; ++mm) {
         const double s0 = fmax(lo, (double)mm), s1 = fmin(hi, (double)(mm + 1));
         if (!(s1 > s0)) continue;
-        double ax, ay, bx, by, kappa, len;
-        if (fam == 0) {  // vertical edge (k,mm)-(k,mm+1): left = face 0 of square (k-1,mm), right = face 1 of (k,mm)
-          const double *rv = p.rho_v + (size_t)k * p.gm + mm;  // a_left - a_right
-          kappa = ((rv[0] - rv[-p.gm]) - (rv[p.gm + 1] - rv[1])) * inv_dx;
+        const double kappa = seg_kappa(p, fam, k, mm, inv_dx, inv_dy, dcoef);
+        double ax, ay, bx, by, len;
+        if (fam == 0) {
           ax = bx = hcoef;
           ay = (s0 - oy) * p.gdy; by = (s1 - oy) * p.gdy;
           len = (s1 - s0) * p.gdy;
-        } else if (fam == 1) {  // horizontal edge (mm,k)-(mm+1,k): below = face 1 of square (mm,k-1), above = face 0 of (mm,k)
-          const double *rv = p.rho_v + (size_t)mm * p.gm + k;  // b_below - b_above
-          kappa = ((rv[0] - rv[-1]) - (rv[p.gm + 1] - rv[p.gm])) * inv_dy;
+        } else if (fam == 1) {
           ay = by = hcoef;
           ax = (s0 - ox) * p.gdx; bx = (s1 - ox) * p.gdx;
           len = (s1 - s0) * p.gdx;
-        } else {  // diagonal of square (mm, mm-k): n points to face 0 (lower right), so T1 = face 1
-          const double *rv = p.rho_v + (size_t)mm * p.gm + (mm - k);
-          // n.(grad rho_1 - grad rho_0) = (r00 + r11 - r01 - r10) (1/dx^2 + 1/dy^2) / |(1/dx, -1/dy)|
-          kappa = ((rv[0] + rv[p.gm + 1]) - (rv[1] + rv[p.gm])) * (inv_dx * inv_dx + inv_dy * inv_dy) * ninv;
+        } else {
           ax = (s0 - ox) * p.gdx; bx = (s1 - ox) * p.gdx;
-          ay = ((s0 - (double)k) - oy) * p.gdy; by = ((s1 - (double)k) - oy) * p.gdy;
+          ay = ((s0 - lev) - oy) * p.gdy; by = ((s1 - lev) - oy) * p.gdy;
           len = (s1 - s0) * ddiag;
         }
         seg_item_mesh<MODE>(ax, ay, bx, by, kappa * h2 * len, acc);
       }
+    }
+  }
+  // ---------------- Hessian slots ----------------
+  if (MODE == MODE_KANTOROVICH) {
+    int slot = 0;
+    for (int k = 0; k < n; ++k) {
+      const int tag = tagof(k);
+      if (tag < 0) continue;
+      const int kk = (k + 1 == n) ? 0 : k + 1;
+      const double dx = P.X(kk) - P.X(k), dy = P.Y(kk) - P.Y(k);
+      const double len = sqrt(dx * dx + dy * dy);
+      if (len > 0.0 && slot < p.kmax) {
+        const double Dx = p.xs[tag] - xi, Dy = p.ys[tag] - yi;
+        hslot_row[slot] = E[k * ES] * len * (0.5 / sqrt(Dx * Dx + Dy * Dy));
+        touched |= 1ull << slot;
+      }
+      ++slot;
     }
   }
   return touched;

@@ -73,7 +73,7 @@ def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_t
     if seg and mesh["kind"] == "grid":
         assert rho is not None, "the segment path reads the vertex densities"
     rc = lib().emu_eval(*gargs, p(abc), p(rho) if rho is not None else None, N, p(x), p(y), p(w), kmax, maxv_piece, mode, C.c_double(filter_tol),
-                        bin_target, nlanes, int(bool(seg) and mesh["kind"] == "grid"), p(perm), p(mass), p(fcell), p(nbr_cnt), p(nbr), p(hslot), p(touched),
+                        bin_target, nlanes, (int(seg) if mesh["kind"] == "grid" else 0), p(perm), p(mass), p(fcell), p(nbr_cnt), p(nbr), p(hslot), p(touched),
                         p(mom), p(counters), C.byref(flags))
     assert rc == 0
     g = np.zeros(N); g[perm] = mass

@@ -89,6 +89,14 @@ extern "C" int emu_eval(int mesh_kind,
     }
     p.tbin_ptr = tbin_ptr.data(); p.tbin_face = tbin_face.data();
   }
+  std::vector<double> rho_pad;
+  if (mesh_kind == MESH_GRID && rho_v) {  // ma_set_grid's padded copy
+    rho_pad.resize((size_t)(gn + 2) * (gm + 2));
+    for (int a = -1; a <= gn; ++a)
+      for (int b = -1; b <= gm; ++b)
+        rho_pad[(size_t)(a + 1) * (gm + 2) + (b + 1)] = rho_v[(size_t)std::min(std::max(a, 0), gn - 1) * gm + std::min(std::max(b, 0), gm - 1)];
+    p.rho_p = rho_pad.data();
+  }
   // ---- K1 on the host ----
   double bx0 = 1e300, bx1 = -1e300, by0 = 1e300, by1 = -1e300;
   for (int i = 0; i < N; ++i) {
@@ -245,9 +253,12 @@ extern "C" int emu_eval(int mesh_kind,
       if (use_seg) {  // what k_cells_seg does after K2
         SegAcc acc;
         unsigned long long tch = 0;
-        if (mode == MODE_KANTOROVICH) tch = cell_integrate_grid<MODE_KANTOROVICH>(p, i, P, n, acc, hslot + (size_t)i * kmax);
-        else if (mode == MODE_MOMENTS1) cell_integrate_grid<MODE_MOMENTS1>(p, i, P, n, acc, nullptr);
-        else cell_integrate_grid<MODE_MOMENTS2>(p, i, P, n, acc, nullptr);
+        {  // line-major formulation (what k_seg runs)
+          double E[80];
+          if (mode == MODE_KANTOROVICH) tch = cell_integrate_lines<MODE_KANTOROVICH, 1>(p, i, P, n, acc, hslot + (size_t)i * kmax, E, [&](int k) { return P.T(k); });
+          else if (mode == MODE_MOMENTS1) cell_integrate_lines<MODE_MOMENTS1, 1>(p, i, P, n, acc, nullptr, E, [&](int k) { return P.T(k); });
+          else cell_integrate_lines<MODE_MOMENTS2, 1>(p, i, P, n, acc, nullptr, E, [&](int k) { return P.T(k); });
+        }
         mass[i] = acc.mass;
         fcell[i] = acc.mass * ws[i] - acc.cost;
         touched[i] = tch;

@@ -217,3 +217,66 @@ def test_block_kernel_degenerate_and_forced_exact(oracle_mod, emu_mod):
             assert common.same_pattern(H0, r["H"])
     finally:
         emu_mod.set_lean(False)
+
+
+def _grid_case(n, m, seed=0):
+    vx, vy = inputs.grid_vertices(n, m)
+    rng = np.random.default_rng(seed)
+    rho = inputs.gaussian_mixture_density(vx, vy) + 0.05 * rng.random(n * m)  # rough: every mesh edge has a kink
+    tri = inputs.grid_triangles(n, m)
+    abc = inputs.pl_coefficients(vx, vy, rho, tri)
+    return vx, vy, tri, abc, dict(kind="grid", n=n, m=m, abc=abc, rho=rho)
+
+
+@pytest.mark.parametrize("layout", ["pixel_centres", "pixel_corners", "every_second_corner", "quarter_shift", "rows_on_lines"])
+def test_segment_path_on_pixel_aligned_lattices(oracle_mod, emu_mod, layout):
+    """Cells whose edges lie ON mesh lines and whose vertices sit ON mesh vertices (Diracs on a lattice aligned with the
+    image grid, rough density): the sign rule of ma_seg.cuh attributes such an edge to one side and the line's chord
+    supplies the difference.  (The walk-along-the-edges formulation of round 1 was off by 4e-4 here.)  Checked against
+    the oracle's per-cell mode; its BFS mode, like vti.hpp:219-313, loses the traversal on exact ties."""
+    n, m = 17, 13
+    vx, vy, tri, abc, mesh = _grid_case(n, m, 3)
+    hx, hy = 2.0 / (n - 1), 2.0 / (m - 1)
+    if layout == "pixel_centres":
+        pts = [(-1 + hx * (a + 0.5), -1 + hy * (b + 0.5)) for a in range(n - 1) for b in range(m - 1)]
+    elif layout == "pixel_corners":
+        pts = [(-1 + hx * a, -1 + hy * b) for a in range(1, n - 1) for b in range(1, m - 1)]
+    elif layout == "every_second_corner":
+        pts = [(-1 + hx * a, -1 + hy * b) for a in range(1, n - 1, 2) for b in range(1, m - 1, 2)]
+    elif layout == "quarter_shift":
+        pts = [(-1 + hx * (a + 0.25), -1 + hy * (b + 0.75)) for a in range(n - 1) for b in range(m - 1)]
+    else:  # Diracs between the rows: horizontal cell edges on y-lines, vertical ones generic
+        pts = [(-1 + hx * (a + 0.37), -1 + hy * (b + 0.5)) for a in range(n - 1) for b in range(m - 1)]
+    X = np.array(pts)
+    orc = oracle_mod.Oracle(vx, vy, tri, abc)
+    orc.set_points(X)
+    for w in (np.zeros(len(X)), 1e-3 * np.sin(7 * X[:, 0]) * np.cos(5 * X[:, 1])):
+        f0, g0, H0 = orc.kantorovich(w, mode=oracle_mod.MODE_PER_CELL | 1)
+        r = emu_mod.evaluate(mesh, X, w, seg=True)
+        assert r["flags"] == 0
+        assert abs(g0.sum() - inputs.total_mass(vx, vy, tri, abc)) <= 1e-13
+        assert abs(r["f"] - f0) <= 1e-11 * abs(f0)
+        assert np.abs(r["g"] - g0).max() <= 1e-11 * np.abs(g0).max()
+        d = np.abs(H0.diagonal()).max()
+        assert abs(H0 - r["H"]).max() <= 1e-11 * d
+        mom0 = orc.moments(w, 2, mode=oracle_mod.MODE_PER_CELL | 1)
+        mom = emu_mod.evaluate(mesh, X, w, seg=True, mode=2)["mom"]
+        assert (np.abs(mom - mom0).max(axis=0) <= 1e-11 * np.abs(mom0).max(axis=0)).all()
+
+
+def test_segment_path_many_boundary_cells(oracle_mod, emu_mod):
+    """Few Diracs on a fine non-square grid: every cell spans many squares and most touch the domain boundary."""
+    n, m = 41, 29
+    vx, vy, tri, abc, mesh = _grid_case(n, m, 5)
+    rng = np.random.default_rng(1)
+    for N in (3, 17, 120):
+        X = rng.uniform(-0.999, 0.999, (N, 2))
+        orc = oracle_mod.Oracle(vx, vy, tri, abc)
+        orc.set_points(X)
+        w = rng.normal(0, 0.02 / N, N)
+        f0, g0, H0 = orc.kantorovich(w)
+        r = emu_mod.evaluate(mesh, X, w, seg=True)
+        assert abs(r["f"] - f0) <= 1e-11 * abs(f0)
+        assert np.abs(r["g"] - g0).max() <= 1e-11 * np.abs(g0).max()
+        assert common.same_pattern(H0, r["H"])
+        assert abs(H0 - r["H"]).max() <= 1e-11 * np.abs(H0.diagonal()).max()
