@@ -141,6 +141,12 @@ class Context:
         vx, vy, abc = _f64(vx), _f64(vy), _f64(abc).reshape(-1)
         tri = np.ascontiguousarray(tri, np.int32).reshape(-1)
         self._ck(self.L.ma_set_mesh(self.h, len(vx), _ptr(vx), _ptr(vy), len(tri) // 3, _ptr(tri), _ptr(abc)))
+        # sum_f area_f * rho_f(centroid_f) (functions.hpp:117), so that total_mass never describes an earlier mesh
+        t = tri.reshape(-1, 3)
+        a = abc.reshape(-1, 3)
+        ax, ay, bx, by, cx, cy = vx[t[:, 0]], vy[t[:, 0]], vx[t[:, 1]], vy[t[:, 1]], vx[t[:, 2]], vy[t[:, 2]]
+        area = ((bx - ax) * (cy - ay) - (cx - ax) * (by - ay)) / 2
+        self.total_mass = float(np.sum(area * (a[:, 0] * (ax + bx + cx) / 3 + a[:, 1] * (ay + by + cy) / 3 + a[:, 2])))
 
     def set_mesh_pl(self, vx, vy, rho, tri):
         vx, vy, rho = _f64(vx), _f64(vy), _f64(rho)
