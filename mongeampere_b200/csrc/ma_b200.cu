@@ -91,10 +91,19 @@ struct ma_ctx {
   int cells_nv = -1;  // ma_cells_build
 
   // pcg
-  Buf dinv, cgx, cgr, cgz, cgp0, cgp1, cgq, cgw1, cgpp, part_pq, part_rz, part_rr, scal, cgflag, cgbar;
+  Buf dinv, cgx, cgr, cgz, cgp0, cgp1, cgq, part_pq, part_rz, part_rr, scal, cgflag;
   int cg_warm = 1;    // Newton: start each PCG from (1 - tau) times the previous direction
-  int cg_single = 0;  // 1: single-reduction CG (one kernel per iteration); measured no faster than the two-kernel PCG (the time is in the kernels, not the launches)
-  int pcg_persist = 0, pcg_blocks_per_sm = 4;  // persistent cooperative PCG: measured slower than the graph of 2-kernel iterations (grid barriers cost more than launches)
+  // aggregation multigrid preconditioner (ma_amg.cuh): hierarchy per point set, matrices per solve
+  struct AmgHost {
+    int nlev = 0, n[AMG_MAX_LEVELS] = {};
+    bool ready = false;
+    AmgLevel lev[AMG_MAX_LEVELS];
+    Buf agg[AMG_MAX_LEVELS], cstart[AMG_MAX_LEVELS], code[AMG_MAX_LEVELS + 1], rowptr[AMG_MAX_LEVELS], col[AMG_MAX_LEVELS],
+        val[AMG_MAX_LEVELS], dinv[AMG_MAX_LEVELS], x[AMG_MAX_LEVELS], r[AMG_MAX_LEVELS], t[AMG_MAX_LEVELS], x2[AMG_MAX_LEVELS];
+    Buf excl, W, Ainv, flag;
+  } amg;
+  int amg_on = 1;
+  double amg_omega = 0.7, amg_alpha = 1.5;  // Jacobi damping, over-correction of the flat prolongation (tuned on the c2 Hessian)
   Buf nu_s, x0_s, d_s, g_s;
   size_t last_cg_iters = 0;
 
@@ -111,6 +120,8 @@ struct ma_ctx {
 };
 
 namespace {
+
+typedef ma_ctx::AmgHost AmgHost;
 
 int fail(ma_ctx *c, int code, const char *fmt, ...) {
   char buf[512];
@@ -284,9 +295,15 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
-                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->rho_p, &c->cgbar, &c->cgw1, &c->cgpp, &c->bin_rm,
+                  &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->rho_p, &c->bin_rm,
                   &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->hard1, &c->hard2, &c->hard_n};
     for (Buf *b : all) release(*b);
+    for (int l = 0; l < AMG_MAX_LEVELS; ++l) {
+      Buf *lv[] = {&c->amg.agg[l], &c->amg.cstart[l], &c->amg.code[l], &c->amg.rowptr[l], &c->amg.col[l], &c->amg.val[l],
+                   &c->amg.dinv[l], &c->amg.x[l], &c->amg.r[l], &c->amg.t[l], &c->amg.x2[l]};
+      for (Buf *b : lv) release(*b);
+    }
+    release(c->amg.code[AMG_MAX_LEVELS]); release(c->amg.excl); release(c->amg.W); release(c->amg.Ainv); release(c->amg.flag);
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_user)
@@ -320,10 +337,10 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   } else if (n == "bin_target") c->bin_target = std::max(1, (int)value);
   else if (n == "cg_rtol") c->cg_rtol = value;
   else if (n == "cg_maxit") c->cg_maxit = (int)value;
-  else if (n == "pcg_persist") c->pcg_persist = (int)value;
-  else if (n == "cg_single") c->cg_single = (int)value;
   else if (n == "cg_warm") c->cg_warm = (int)value;
-  else if (n == "pcg_blocks_per_sm") c->pcg_blocks_per_sm = std::max(1, (int)value);
+  else if (n == "amg") c->amg_on = (int)value;
+  else if (n == "amg_omega") c->amg_omega = value;
+  else if (n == "amg_alpha") c->amg_alpha = value;
   else if (n == "filter_tol") c->filter_tol = value;
   else if (n == "persist") c->persist = (int)value;
   else if (n == "lean") c->lean = (int)value;
@@ -518,6 +535,8 @@ extern "C" int ma_set_image(ma_ctx *c, int n, int m, const double *pixels, doubl
 // =============================================================================================
 // Diracs (K1, once per point set)
 // =============================================================================================
+namespace { int amg_build_hierarchy(ma_ctx *c); }
+
 extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y) {
   NEED_CTX();
   if (N < 1 || !x || !y) return fail(c, MA_INVALID, "ma_set_points: bad arguments");
@@ -599,7 +618,7 @@ extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y)
   CKR(moment_scan<0>(c, c->pre0.as<double>()));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
-  return MA_OK;
+  return amg_build_hierarchy(c);
 }
 
 // =============================================================================================
@@ -662,16 +681,22 @@ template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
   CK(cudaFuncSetAttribute(k_cells_block<2, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   CK(cudaFuncSetAttribute(k_cells_block<3, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(cudaFuncSetAttribute(k_cells_block<5, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int nblk = std::max(1, cdiv(ncells, NT));
   k_cells_block<2, MAXV, NT, POLY><<<nblk, NT, sm, c->stream>>>(p, nullptr, nullptr, c->hard1.as<int>(), cnt);
-  // the later stages see a fraction of the cells (or, with graded weights, all of them: k_cells_persist then ignores the list)
+  // the later stages see a fraction of the cells (or, with graded weights, all of them: k_cells_persist then ignores the
+  // list): radius 3 for the ~15 % the 5 x 5 block cannot certify, radius 5 for the ~0.4 % left after that (one by one
+  // through CellSearch those few cells cost 0.6 ms of pure latency, profiles/r02b), CellSearch for the rest
   const int nblk2 = std::max(1, std::min(nblk, c->sm_count * 8));
   k_cells_block<3, MAXV, NT, POLY><<<nblk2, NT, sm, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
+  k_cells_block<5, MAXV, NT, POLY><<<std::max(1, std::min(nblk, c->sm_count * 2)), NT, sm, c->stream>>>(p, c->hard2.as<int>(), cnt + 1,
+                                                                                                    c->hard1.as<int>(), cnt + 2);
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cells_persist<MAXV, NT, POLY>, NT, sm));
   const long long warps_target = (long long)c->sm_count * std::max(per_sm, 1) * (NT / 32) * c->persist_waves;
   const int nwarps = (int)std::max<long long>(1, std::min<long long>(warps_target, cdiv(ncells, c->persist_min_chunk)));
-  k_cells_persist<MAXV, NT, POLY><<<cdiv(nwarps, NT / 32), NT, sm, c->stream>>>(p, c->persist_min_chunk, c->hard2.as<int>(), cnt + 1);
+  k_cells_persist<MAXV, NT, POLY><<<cdiv(nwarps, NT / 32), NT, sm, c->stream>>>(p, c->persist_min_chunk, c->hard1.as<int>(), cnt + 2);
+  c->launches += 1;
   c->launches += 3;
   CK(cudaGetLastError());
   return MA_OK;
@@ -1233,80 +1258,124 @@ extern "C" int ma_cells_get(ma_ctx *c, int *ptr, double *xy, int *tag) {
 // =============================================================================================
 namespace {
 
-// Solve H d = sign * g on the device (internal order), grounded at `ground`.  d_out may alias nothing.
-// single-reduction CG, one kernel per iteration (ma_pcg.cuh)
-int cg1_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double *val, const double *g, double sign,
-              int ground, double *d_out, int *iters_out, double *relres_out) {
-  Cg1State s;
-  const int nblocks = std::min(PCG_MAX_BLOCKS, std::max(1, cdiv(n, PCG_NT)));
-  Buf *vecs[] = {&c->dinv, &c->cgx, &c->cgr, &c->cgz, &c->cgp0, &c->cgp1, &c->cgq, &c->cgw1, &c->cgpp};
-  for (Buf *b : vecs) CKR(ensure(c, *b, (size_t)n * 8));
-  CKR(ensure(c, c->part_pq, (size_t)6 * nblocks * 8)); CKR(ensure(c, c->scal, 64)); CKR(ensure(c, c->cgflag, 16));
-  s.n = n; s.ground = ground; s.nblocks = nblocks; s.rowptr = rowptr; s.col = col; s.val = val;
-  s.dinv = c->dinv.as<double>(); s.x = c->cgx.as<double>(); s.p = c->cgpp.as<double>();
-  s.r[0] = c->cgr.as<double>(); s.r[1] = c->cgz.as<double>();
-  s.s[0] = c->cgp0.as<double>(); s.s[1] = c->cgp1.as<double>();
-  s.w[0] = c->cgq.as<double>(); s.w[1] = c->cgw1.as<double>();
-  s.part = c->part_pq.as<double>(); s.scal = c->scal.as<double>();
-  CK(cudaMemsetAsync(c->cgflag.p, 0, 16, c->stream));
-  CK(cudaMemsetAsync(c->scal.p, 0, 64, c->stream));
-  k_cg1_init<<<nblocks, PCG_NT, 0, c->stream>>>(s, g, sign, c->cgflag.as<int>(), c->dinv.as<double>());
-  k_cg1_init2<<<nblocks, PCG_NT, 0, c->stream>>>(s);
-  k_cg1_rr<<<1, PCG_NT, 0, c->stream>>>(s, 0, 4);
-  c->launches += 3;
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(&c->hs->red[0], c->scal.as<double>() + 4, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&c->hs->flags, c->cgflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+// ---- aggregation multigrid (ma_amg.cuh) -------------------------------------------------------------------
+// hierarchy of aggregates from the Morton-sorted leaf codes: once per point set
+int amg_build_hierarchy(ma_ctx *c) {
+  AmgHost &A = c->amg;
+  A.nlev = 0;
+  A.ready = false;
+  const int N = c->N;
+  if (N < 2 * AMG_DENSE_MAX) return MA_OK;  // small systems: Jacobi PCG is fine
+  int n = N;
+  const unsigned *code = c->code_s.as<unsigned>();
+  for (int l = 0; l < AMG_MAX_LEVELS; ++l) {
+    A.n[l] = n;
+    A.nlev = l + 1;
+    if (n <= AMG_DENSE_MAX) break;
+    CKR(ensure(c, A.agg[l], (size_t)n * 4));
+    CKR(ensure(c, c->scratch_i, (size_t)n * 4));
+    CKR(ensure(c, A.excl, ((size_t)n + 1) * 4));
+    k_amg_flags<<<cdiv(n, 256), 256, 0, c->stream>>>(code, n, c->scratch_i.as<int>());
+    CKR(scan_i32(c, c->scratch_i.as<int>(), A.excl.as<int>(), n));
+    int nc = 0;
+    CK(cudaMemcpyAsync(&nc, A.excl.as<int>() + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (nc >= n || nc < 1) { A.nlev = 0; return MA_OK; }  // no coarsening possible (cannot happen: the root merges everything)
+    CKR(ensure(c, A.cstart[l], ((size_t)nc + 1) * 4));
+    CKR(ensure(c, A.code[l + 1], (size_t)nc * 4));
+    k_amg_index<<<cdiv(n, 256), 256, 0, c->stream>>>(code, c->scratch_i.as<int>(), A.excl.as<int>(), n, A.agg[l].as<int>(),
+                                                     A.cstart[l].as<int>(), A.code[l + 1].as<unsigned>());
+    CK(cudaGetLastError());
+    code = A.code[l + 1].as<unsigned>();
+    n = nc;
+  }
+  if (A.n[A.nlev - 1] > AMG_DENSE_MAX) { A.nlev = 0; return MA_OK; }
+  for (int l = 0; l < A.nlev; ++l) {
+    const size_t nl = A.n[l];
+    if (l > 0) { CKR(ensure(c, A.r[l], nl * 8)); CKR(ensure(c, A.dinv[l], nl * 8)); CKR(ensure(c, A.rowptr[l], (nl + 1) * 4)); }
+    CKR(ensure(c, A.x[l], nl * 8)); CKR(ensure(c, A.t[l], nl * 8)); CKR(ensure(c, A.x2[l], nl * 8));
+  }
+  const size_t nd = A.n[A.nlev - 1];
+  CKR(ensure(c, A.W, nd * 2 * nd * 8)); CKR(ensure(c, A.Ainv, nd * nd * 8)); CKR(ensure(c, A.flag, 16));
   CK(cudaStreamSynchronize(c->stream));
-  if (c->hs->flags & 1) {
-    fail(c, MA_SINGULAR_HESSIAN, "Error: hessian of Kantorovich's functional is not invertible (zero diagonal)");
-    return MA_SINGULAR_HESSIAN;
-  }
-  const double gg = c->hs->red[0];
-  int it = 0;
-  double rr = gg;
-  if (gg > 0) {
-    const int batch = 64;  // even, so the buffer parity is the same at every graph launch
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    // k only enters through its parity and through "k > 0"; iteration 0 of the solve needs k = 0, which the
-    // zero-initialised scalars emulate: gamma_prev = 0 => beta = 0, and 0 * gamma / alpha_prev is made finite below
-    for (int b = 0; b < batch; ++b) k_cg1_iter<<<nblocks, PCG_NT, 0, c->stream>>>(s, b + 2);
-    k_cg1_rr<<<1, PCG_NT, 0, c->stream>>>(s, 0, 5);
-    CK(cudaStreamEndCapture(c->stream, &graph));
-    CK(cudaGraphInstantiate(&exec, graph, 0));
-    // the very first iteration runs outside the graph with k = 0, then one more to restore even parity
-    k_cg1_iter<<<nblocks, PCG_NT, 0, c->stream>>>(s, 0);
-    k_cg1_iter<<<nblocks, PCG_NT, 0, c->stream>>>(s, 1);
-    c->launches += 2;
-    it = 2;
-    const double tol2 = c->cg_rtol * c->cg_rtol * gg;
-    while (it < c->cg_maxit) {
-      CK(cudaGraphLaunch(exec, c->stream));
-      c->launches += batch + 1;
-      CK(cudaMemcpyAsync(&c->hs->red[1], c->scal.as<double>() + 5, 8, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      rr = c->hs->red[1];
-      it += batch;
-      if (!(rr > tol2)) break;  // also stops on NaN
-    }
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
-  }
-  if (d_out) CK(cudaMemcpyAsync(d_out, s.x, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
-  if (iters_out) *iters_out = it;
-  if (relres_out) *relres_out = gg > 0 ? std::sqrt(rr / gg) : 0.0;
-  c->last_cg_iters = it;
-  if (!(rr == rr)) return fail(c, MA_LINSOLVE_RESIDUAL, "CG produced NaN");
+  A.ready = true;
   return MA_OK;
 }
 
+// coarse matrices of this solve: Galerkin products level by level + the dense inverse of the last one
+int amg_setup(ma_ctx *c, const int *rowptr, const int *col, const double *val, int nnz, const double *dinv0, int ground) {
+  AmgHost &A = c->amg;
+  CK(cudaMemsetAsync(A.flag.p, 0, 16, c->stream));
+  A.lev[0].rowptr = rowptr; A.lev[0].col = col; A.lev[0].val = val;
+  size_t cap = (size_t)std::max(nnz, 1);
+  for (int l = 0; l < A.nlev; ++l) {
+    AmgLevel &L = A.lev[l];
+    L.n = A.n[l];
+    L.agg = l + 1 < A.nlev ? A.agg[l].as<int>() : nullptr;
+    L.cstart = l + 1 < A.nlev ? A.cstart[l].as<int>() : nullptr;
+    L.dinv = l == 0 ? const_cast<double *>(dinv0) : A.dinv[l].as<double>();
+    L.x = A.x[l].as<double>(); L.t = A.t[l].as<double>(); L.x2 = A.x2[l].as<double>();
+    L.r = l == 0 ? nullptr : A.r[l].as<double>();
+  }
+  for (int l = 0; l + 1 < A.nlev; ++l) {
+    const AmgLevel &F = A.lev[l];
+    AmgLevel &C = A.lev[l + 1];
+    const int nc = A.n[l + 1];
+    cap = std::min(cap, (size_t)nc * AMG_ROW_CAP);
+    CKR(ensure(c, A.col[l + 1], cap * 4, 1.2)); CKR(ensure(c, A.val[l + 1], cap * 8, 1.2));
+    CKR(ensure(c, c->scratch_i, (size_t)nc * 4));
+    const int g = l == 0 ? ground : -1;
+    k_amg_galerkin<false><<<cdiv(nc, 128), 128, 0, c->stream>>>(nc, F.cstart, F.agg, F.rowptr, F.col, F.val, g, c->scratch_i.as<int>(),
+                                                                nullptr, nullptr, nullptr, nullptr, A.flag.as<int>());
+    CKR(scan_i32(c, c->scratch_i.as<int>(), A.rowptr[l + 1].as<int>(), nc));
+    k_amg_galerkin<true><<<cdiv(nc, 128), 128, 0, c->stream>>>(nc, F.cstart, F.agg, F.rowptr, F.col, F.val, g, nullptr,
+                                                               A.rowptr[l + 1].as<int>(), A.col[l + 1].as<int>(),
+                                                               A.val[l + 1].as<double>(), A.dinv[l + 1].as<double>(), A.flag.as<int>());
+    c->launches += 2;
+    C.rowptr = A.rowptr[l + 1].as<int>(); C.col = A.col[l + 1].as<int>(); C.val = A.val[l + 1].as<double>();
+  }
+  const AmgLevel &D = A.lev[A.nlev - 1];
+  k_amg_dense_inverse<<<1, 1024, 0, c->stream>>>(D.n, D.rowptr, D.col, D.val, A.W.as<double>(), A.Ainv.as<double>(), A.flag.as<int>());
+  c->launches++;
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+
+// z = M^-1 r (one V(1,1) cycle); leaves the partial sums of r.z in part_rz[0 .. nblocks)
+int amg_vcycle(ma_ctx *c, const double *r, double *z, double *part_rz, int nblocks, int ground) {
+  AmgHost &A = c->amg;
+  const double omega = c->amg_omega, alpha = c->amg_alpha;
+  auto grid = [&](int n) { return std::max(1, std::min(cdiv(n, 256), c->sm_count * 8)); };
+  const int last = A.nlev - 1;
+  for (int l = 0; l < last; ++l) {
+    const AmgLevel &L = A.lev[l];
+    const double *rl = l == 0 ? r : L.r;
+    k_amg_down<<<grid(L.n), 256, 0, c->stream>>>(L.n, L.rowptr, L.col, L.val, L.dinv, rl, omega, l == 0 ? ground : -1, L.x, L.t);
+    k_amg_restrict<<<grid(A.n[l + 1]), 256, 0, c->stream>>>(A.n[l + 1], L.cstart, L.t, A.lev[l + 1].r);
+  }
+  k_amg_dense_apply<<<1, AMG_DENSE_MAX, 0, c->stream>>>(A.lev[last].n, A.Ainv.as<double>(), A.lev[last].r, A.lev[last].x2);
+  for (int l = last - 1; l >= 0; --l) {
+    const AmgLevel &L = A.lev[l];
+    const double *ec = A.lev[l + 1].x2;
+    if (l == 0)
+      k_amg_up<true><<<nblocks, 256, 0, c->stream>>>(L.n, L.rowptr, L.col, L.val, L.dinv, r, L.x, L.agg, ec, alpha, omega, ground, z, part_rz);
+    else
+      k_amg_up<false><<<grid(L.n), 256, 0, c->stream>>>(L.n, L.rowptr, L.col, L.val, L.dinv, L.r, L.x, L.agg, ec, alpha, omega, -1, L.x2, nullptr);
+  }
+  c->launches += 3 * last + 1;
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+
+// Solve H d = sign * g on the device (internal order), grounded at `ground`.  d_out may alias nothing.
+// use_amg: precondition with the aggregation multigrid of ma_amg.cuh (needs the hierarchy of this context's point set,
+// i.e. the matrix must be a Hessian of these Diracs in internal order); otherwise Jacobi.
 int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double *val, const double *g, double sign,
               int ground, double *d_out, int *iters_out, double *relres_out, const double *x0 = nullptr,
-              double x0_scale = 1.0) {
-  if (c->cg_single) return cg1_solve(c, n, rowptr, col, val, g, sign, ground, d_out, iters_out, relres_out);
+              double x0_scale = 1.0, bool use_amg = false, int nnz = 0) {
+  static_assert(PCG_NT == 256, "k_amg_up<true> shares the r.z partials with the PCG kernels: same block size");
   PcgState s;
+  use_amg = use_amg && c->amg_on && c->amg.ready && c->amg.n[0] == n;
   // one resident wave at most (the kernels are grid-stride loops): a second, partial wave only adds a tail
   int per_sm = 8;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_A, PCG_NT, 0));
@@ -1321,18 +1390,31 @@ int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double 
   s.p[0] = c->cgp0.as<double>(); s.p[1] = c->cgp1.as<double>(); s.q = c->cgq.as<double>();
   s.part_pq = c->part_pq.as<double>(); s.part_rz = c->part_rz.as<double>(); s.part_rr = c->part_rr.as<double>();
   s.scal = c->scal.as<double>(); s.nblocks = nblocks; s.flag = c->cgflag.as<int>();
-  CK(cudaMemsetAsync(c->cgflag.p, 0, 16, c->stream));
-  CK(cudaMemsetAsync(c->part_rz.p, 0, (size_t)2 * nblocks * 8, c->stream));
-  k_pcg_init<<<nblocks, PCG_NT, 0, c->stream>>>(s, g, sign, x0, x0_scale);
-  if (x0) { k_pcg_resid<<<nblocks, PCG_NT, 0, c->stream>>>(s); c->launches++; }
-  k_pcg_init2<<<1, PCG_NT, 0, c->stream>>>(s);
-  c->launches += 2;
-  CK(cudaGetLastError());
   double h_scal[4];
-  int h_flag = 0;
-  CK(cudaMemcpyAsync(h_scal, c->scal.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&h_flag, c->cgflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  int h_flag = 0, h_amg = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CK(cudaMemsetAsync(c->cgflag.p, 0, 16, c->stream));
+    CK(cudaMemsetAsync(c->part_rz.p, 0, (size_t)2 * nblocks * 8, c->stream));
+    k_pcg_init<<<nblocks, PCG_NT, 0, c->stream>>>(s, g, sign, x0, x0_scale);
+    if (x0) { k_pcg_resid<<<nblocks, PCG_NT, 0, c->stream>>>(s); c->launches++; }
+    if (use_amg) {
+      CKR(amg_setup(c, rowptr, col, val, nnz, s.dinv, ground));
+      CKR(amg_vcycle(c, s.r, s.z, s.part_rz, nblocks, ground));
+      CK(cudaMemcpyAsync(&h_amg, c->amg.flag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    k_pcg_init2<<<1, PCG_NT, 0, c->stream>>>(s);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_scal, c->scal.p, sizeof h_scal, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&h_flag, c->cgflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (use_amg && h_amg) {  // a coarse row outgrew its merge buffer / a non-positive pivot: this solve runs with Jacobi
+      if (c->trace) fprintf(stderr, "[ma] multigrid setup flag %d: falling back to the Jacobi preconditioner\n", h_amg);
+      use_amg = false;
+      continue;
+    }
+    break;
+  }
   if (h_flag & 1) {
     fail(c, MA_SINGULAR_HESSIAN, "Error: hessian of Kantorovich's functional is not invertible (zero diagonal)");
     return MA_SINGULAR_HESSIAN;
@@ -1340,49 +1422,33 @@ int pcg_solve(ma_ctx *c, int n, const int *rowptr, const int *col, const double 
   const double gg = h_scal[2];
   int it = 0;
   double rr = gg;
-  if (gg > 0 && c->pcg_persist) {
-    // one persistent kernel per chunk of iterations, all blocks co-resident (cooperative launch)
-    int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist, PCG_NT, 0));
-    const int pb = std::max(1, std::min(nblocks, std::min(per_sm, c->pcg_blocks_per_sm) * c->sm_count));
-    CKR(ensure(c, c->cgbar, 64));
-    const double tol2 = c->cg_rtol * c->cg_rtol * gg;
-    PcgState sp = s;
-    while (it < c->cg_maxit) {
-      int chunk = std::min(c->cg_maxit - it, 4096);
-      chunk += chunk & 1;  // even: the parity of the p buffers is the same at every launch
-      CK(cudaMemsetAsync(c->cgbar.p, 0, 64, c->stream));
-      unsigned *bar = c->cgbar.as<unsigned>();
-      void *args[] = {&sp, &it, &chunk, (void *)&tol2, &bar};
-      CK(cudaLaunchCooperativeKernel((void *)k_pcg_persist, dim3(pb), dim3(PCG_NT), args, 0, c->stream));
-      c->launches++;
-      double two[2];
-      CK(cudaMemcpyAsync(two, c->scal.as<double>() + 3, 16, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      rr = two[0];
-      const int did = (int)two[1];
-      it += did;
-      if (!(rr > tol2) || did < chunk) break;
-      if (did & 1) break;  // (cannot happen: an odd count means an early stop, handled above)
-    }
-  } else if (gg > 0) {
-    const int batch = 32;  // even, so iteration parity is the same in every graph launch
+  if (gg > 0) {
+    const int batch = use_amg ? 8 : 32;  // even, so iteration parity is the same in every graph launch
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const long long l0 = c->launches;
     for (int b = 0; b < batch; ++b) {
       // iteration 0 of the very first batch must use beta = 0: p_old is zero-initialised and
       // part_rz parity 0 is zero, so beta = 0/rz = 0 falls out without a special case
       k_pcg_A<<<nblocks, PCG_NT, 0, c->stream>>>(s, b + 2);
-      k_pcg_B<<<nblocks, PCG_NT, 0, c->stream>>>(s, b + 2);
+      if (use_amg) {
+        k_pcg_B<false><<<nblocks, PCG_NT, 0, c->stream>>>(s, b + 2);
+        int rc_v = amg_vcycle(c, s.r, s.z, s.part_rz + (size_t)(((b + 2) & 1) ^ 1) * nblocks, nblocks, ground);
+        if (rc_v != MA_OK) { cudaStreamEndCapture(c->stream, &graph); if (graph) cudaGraphDestroy(graph); return rc_v; }
+      } else {
+        k_pcg_B<true><<<nblocks, PCG_NT, 0, c->stream>>>(s, b + 2);
+      }
     }
     k_pcg_rr<<<1, PCG_NT, 0, c->stream>>>(s);
+    const long long per_graph = (c->launches - l0) + 2 * batch + 1;
+    c->launches = l0;
     CK(cudaStreamEndCapture(c->stream, &graph));
     CK(cudaGraphInstantiate(&exec, graph, 0));
     const double tol2 = c->cg_rtol * c->cg_rtol * gg;
     while (it < c->cg_maxit) {
       CK(cudaGraphLaunch(exec, c->stream));
-      c->launches += 2 * batch + 1;
+      c->launches += per_graph;
       CK(cudaMemcpyAsync(&rr, c->scal.as<double>() + 3, 8, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       it += batch;
@@ -1563,7 +1629,7 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
     if (warm) CK(cudaMemcpyAsync(c->scratch_d.p, c->d_s.p, (size_t)N * 8, cudaMemcpyDeviceToDevice, c->stream));
     int rc = pcg_solve(c, N, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(), c->g_s.as<double>(), -1.0,
                        ground, c->d_s.as<double>(), &it, &relres, warm ? c->scratch_d.as<double>() : nullptr,
-                       1.0 - last_alpha);
+                       1.0 - last_alpha, /*use_amg=*/true, c->nnz);
     have_dir = true;
     t_pcg += secs(t0p, now());
     cg_total += it;

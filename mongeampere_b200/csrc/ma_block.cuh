@@ -86,13 +86,15 @@ MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv
         MA_COUNT(1);
         const int n = S.n;
         const int jj = p.rm2s[pos];
-        const unsigned long long in = S.sign_mask(p, P, jj, Dx, Dy, c, dd2, dw);
+        double r2_seen;
+        const unsigned long long in = S.sign_mask(p, P, jj, Dx, Dy, c, dd2, dw, r2_seen);
+        S.R2 = r2_seen;  // radius of the polygon as it is now (a clip below leaves it as an upper bound)
         if (in == 0ull) { S.n = 0; S.phase = 2; }
         else if (in != lowmask64(n)) { S.jc = jj; S.cDx = Dx; S.cDy = Dy; S.cc = c; S.cin = in; cut = true; }
       }
       MA_WARP_SYNC();
       if (MA_WARP_ANY(cut)) {
-        if (cut) S.clip(p, P, maxv);  // overflow: status = FLAG_CELL_OVERFLOW, n = 0, phase = 2
+        if (cut) S.template clip<false>(p, P, maxv);  // overflow: status = FLAG_CELL_OVERFLOW, n = 0, phase = 2
         MA_WARP_SYNC();
       }
     }

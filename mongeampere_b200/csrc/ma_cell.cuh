@@ -198,14 +198,20 @@ template <class Poly> struct CellSearch {
   // |.|-min per vertex: it compares the smallest |value| with a bound on the rounding error that holds for every
   // vertex, |u.D| <= sqrt(R2 dd2), and only then looks at the vertices one by one.
   MA_DEV unsigned long long sign_mask(const Params &p, const Poly &P, int jj, double Dx, double Dy, double c, double dd2,
-                                      double dw) const {
+                                      double dw, double &r2_seen) const {
     unsigned long long in = 0ull;
-    double amin = 1.0 / 0.0;
+    double amin = 1.0 / 0.0, r2 = 0.0;
+    unsigned long long o = P.ord;  // PACKED: the slot of vertex k is the k-th nibble, peeled off one by one
     for (int k = 0; k < n; ++k) {
-      const double val = c - (P.X(k) * Dx + P.Y(k) * Dy);
+      const int sl = Poly::PACK ? (int)(o & 15ull) : k;
+      o >>= 4;
+      const double X = P.SX(sl), Y = P.SY(sl);
+      const double val = c - (X * Dx + Y * Dy);
       if (val > 0.0) in |= 1ull << k;
       amin = fmin(amin, fabs(val));
+      r2 = fmax(r2, X * X + Y * Y);
     }
+    r2_seen = r2;  // the polygon's radius about y_i, for free (the block kernel keeps R2 current with it)
     const double cmag = 0.5 * (dd2 + fabs(dw));
     // (|c| + |ux Dx| + |uy Dy|)^2 <= 2 cmag^2 + 4 R2 dd2
     if (amin * amin <= (p.filter_tol * p.filter_tol) * (2.0 * cmag * cmag + 4.0 * R2 * dd2)) {
@@ -328,7 +334,8 @@ template <class Poly> struct CellSearch {
           // (margin 1e-9: anything closer to tangency than that goes through the filtered sign test below)
           if (!(e >= 0.0 && e * e >= rc2 * dd2 * (1.0 + 1e-9))) {
             MA_COUNT(1);
-            const unsigned long long in = sign_mask(p, P, jj, Dx, Dy, c, dd2, dw);
+            double r2_seen;
+            const unsigned long long in = sign_mask(p, P, jj, Dx, Dy, c, dd2, dw, r2_seen);
             const unsigned long long full = lowmask64(n);
             if (in == 0ull) { n = 0; phase = 2; }
             else if (in != full) { jc = jj; cDx = Dx; cDy = Dy; cc = c; cin = in; }
@@ -431,8 +438,9 @@ template <class Poly> struct CellSearch {
     }
   }
 
-  // clip by the held site (requires holding())
-  MA_DEV void clip(const Params &p, Poly &P, int maxv) {
+  // clip by the held site (requires holding()).  REFRESH = false: the caller keeps R2 current itself (block kernel:
+  // sign_mask hands it the radius at the next tested candidate; until then the old, larger value is a valid bound)
+  template <bool REFRESH = true> MA_DEV void clip(const Params &p, Poly &P, int maxv) {
     MA_COUNT(2);
     auto lo = [&](int tag, double &nx, double &ny, double &cl) { lineof(p, tag, nx, ny, cl); };
     int n2;
@@ -442,6 +450,7 @@ template <class Poly> struct CellSearch {
     else {
       n = n2;
       cut_in_pass = true;
+      if (REFRESH) {
       R2 = 0.0;
       for (int k = 0; k < n; ++k) R2 = fmax(R2, P.X(k) * P.X(k) + P.Y(k) * P.Y(k));
       if (use_m) {  // bounding-box centre, exact radius about it
@@ -458,6 +467,7 @@ template <class Poly> struct CellSearch {
         }
       } else {
         rc2 = R2;
+      }
       }
     }
     jc = -1;

@@ -223,31 +223,53 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
   const double ddiag = sqrt(p.gdx * p.gdx + p.gdy * p.gdy);
   const double ninv = 1.0 / sqrt(inv_dx * inv_dx + inv_dy * inv_dy);  // 1 / |(1/dx, -1/dy)|
   const double dcoef = (inv_dx * inv_dx + inv_dy * inv_dy) * ninv;
-  for (int fam = 0; fam < 3; ++fam) {
-    const double lo_f = fam == 0 ? fxmin : (fam == 1 ? fymin : fdmin);
-    const double hi_f = fam == 0 ? fxmax : (fam == 1 ? fymax : fdmax);
-    // line k has a vertex on either side  <=>  min < k <= max; lines of the padded grid only
-    int k0 = (int)floor(lo_f) + 1, k1 = (int)floor(hi_f);
-    if (fam == 0) { k0 = max(k0, 0); k1 = min(k1, sx_hi); }
-    else if (fam == 1) { k0 = max(k0, 0); k1 = min(k1, sy_hi); }
-    else { k0 = max(k0, -sy_hi - 1); k1 = min(k1, sx_hi + 1); }
+  // line k of a family has a vertex on either side  <=>  min < k <= max over the vertices; lines of the padded grid only.
+  // The three families are walked as ONE list (a cell's total number of lines varies much less than its split over
+  // the families, and all lanes of a warp run as long as the longest list).
+  const int kx0 = max((int)floor(fxmin) + 1, 0), kx1 = min((int)floor(fxmax), sx_hi);
+  const int ky0 = max((int)floor(fymin) + 1, 0), ky1 = min((int)floor(fymax), sy_hi);
+  const int kd0 = max((int)floor(fdmin) + 1, -sy_hi - 1), kd1 = min((int)floor(fdmax), sx_hi + 1);
+  const int Lx = max(kx1 - kx0 + 1, 0), Ly = max(ky1 - ky0 + 1, 0), Ld = max(kd1 - kd0 + 1, 0);
+  const unsigned nmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+  for (int q = 0; q < Lx + Ly + Ld; ++q) {
+    const int fam = (q >= Lx ? 1 : 0) + (q >= Lx + Ly ? 1 : 0);
+    const int k = fam == 0 ? kx0 + q : (fam == 1 ? ky0 + (q - Lx) : kd0 + (q - Lx - Ly));
     const double fscale = fam == 0 ? p.gdx : (fam == 1 ? p.gdy : ninv);  // level function -> distance
-    for (int k = k0; k <= k1; ++k) {
+    {
       const double lev = (double)k;
-      // the (at most two) edges with a sign change, without arithmetic inside the divergent branch
-      double Px = P.X(0) * inv_dx + ox, Py = P.Y(0) * inv_dy + oy;
-      double gv = (fam == 0 ? Px : (fam == 1 ? Py : Px - Py)) - lev;
+      // level function at vertex v (always this very expression: its sign is THE side of v)
+      auto gat = [&](int v) {
+        const double Qx = P.X(v) * inv_dx + ox, Qy = P.Y(v) * inv_dy + oy;
+        return (fam == 0 ? Qx : (fam == 1 ? Qy : Qx - Qy)) - lev;
+      };
+      // the edges with a sign change: one bit per vertex, then bit tricks (cells of more than 32 vertices, which only
+      // the largest capacity class can hold, scan edge by edge)
       int e1 = -1, e2 = -1;
       double g1a = 0, g1b = 1, g2a = 0, g2b = 1;
-      for (int v = 0; v < n; ++v) {
-        const int vv = (v + 1 == n) ? 0 : v + 1;
-        const double Qx = P.X(vv) * inv_dx + ox, Qy = P.Y(vv) * inv_dy + oy;
-        const double gw = (fam == 0 ? Qx : (fam == 1 ? Qy : Qx - Qy)) - lev;
-        const bool cross = (gv < 0.0) != (gw < 0.0);
-        const bool first = cross && e1 < 0, second = cross && e1 >= 0;
-        if (second) { e2 = v; g2a = gv; g2b = gw; }
-        if (first) { e1 = v; g1a = gv; g1b = gw; }
-        gv = gw;
+      if (n <= 32) {
+        unsigned neg = 0u;
+        for (int v = 0; v < n; ++v) neg |= (gat(v) < 0.0 ? 1u : 0u) << v;
+        const unsigned nxt = ((neg >> 1) | ((neg & 1u) << (n - 1))) & nmask;  // bit v = side of vertex v+1
+        const unsigned cr = (neg ^ nxt) & nmask;
+        if (cr & (cr - 1u)) {  // at least two crossings: the first and the last
+#ifdef __CUDA_ARCH__
+          e1 = __ffs((int)cr) - 1; e2 = 31 - __clz((int)cr);
+#else
+          e1 = __builtin_ctz(cr); e2 = 31 - __builtin_clz(cr);
+#endif
+          g1a = gat(e1); g1b = gat(e1 + 1 == n ? 0 : e1 + 1);
+          g2a = gat(e2); g2b = gat(e2 + 1 == n ? 0 : e2 + 1);
+        }
+      } else {
+        double gv = gat(0);
+        for (int v = 0; v < n; ++v) {
+          const double gw = gat(v + 1 == n ? 0 : v + 1);
+          const bool cross = (gv < 0.0) != (gw < 0.0);
+          const bool first = cross && e1 < 0, second = cross && e1 >= 0;
+          if (second) { e2 = v; g2a = gv; g2b = gw; }
+          if (first) { e1 = v; g1a = gv; g1b = gw; }
+          gv = gw;
+        }
       }
       if (e2 < 0) continue;
       // unit mesh edges of this line in the padded grid: mm in [mlo, mhi]

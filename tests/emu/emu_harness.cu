@@ -233,13 +233,14 @@ extern "C" int emu_eval(int mesh_kind,
       PolyRef<1, false> PA{px.data(), py.data(), pt.data()};
       int n = -2;
       if (kmax == 16 && emu_lean[0] && !graded) {
-        for (int pass = 0; pass < 2 && n == -2; ++pass) {
+        for (int pass = 0; pass < 3 && n == -2; ++pass) {
           CellSearch<PolyRef<1, true>> S;
           S.init(p, i, PP);
           bool cert = false;
           if (pass == 0) block_search<2>(p, S, PP, 16, true, cert);
-          else block_search<3>(p, S, PP, 16, true, cert);
-          if (cert) { n = S.n; emu_lean[1 + pass]++; }
+          else if (pass == 1) block_search<3>(p, S, PP, 16, true, cert);
+          else block_search<5>(p, S, PP, 16, true, cert);
+          if (cert) { n = S.n; emu_lean[1 + std::min(pass, 1)]++; }
         }
       }
       if (n == -2) {
