@@ -38,7 +38,7 @@ int ma_create(ma_ctx **out, int device);
 void ma_destroy(ma_ctx *ctx);
 const char *ma_last_error(const ma_ctx *ctx);
 /* ABI version, bumped on any signature change. */
-int ma_abi_version(void);
+int ma_abi_version(void);   /* 2: ma_comm_*, options "lean" / "block_target" / "amg*" */
 
 /* ---- source density: a triangulation with one linear function per face --------------------
  * Replaces the (T densityT, Functions densityF) pair of kantorovich.hpp:37-39 / lloyd.hpp:31-33:
@@ -144,6 +144,22 @@ int ma_evaluate(ma_ctx *ctx, int with_hessian);
  * row idv of h).  Masses and Hessian rows of the other tiles stay zero/empty in this context; fval,
  * mass_sum and mass_min are the tile's partial values, to be combined by the caller (sum, sum, min). */
 int ma_set_partition(ma_ctx *ctx, int rank, int nranks);
+
+/* Multi-GPU with NCCL inside the engine (one process per GPU).  ma_comm_unique_id fills 128
+ * bytes on ONE rank (ncclGetUniqueId); the caller ships them to the other ranks by any means (MPI, a file,
+ * torch.distributed, a socket) and every rank calls ma_comm_init, which creates the NCCL communicator on the context's
+ * device and makes the context evaluate Morton tile `rank` of `nranks` (as ma_set_partition does).  With a communicator
+ *   - ma_kantorovich returns the WHOLE problem's f, g and Hessian on every rank (tiles evaluated in parallel, slices
+ *     gathered over NVLink);
+ *   - ma_ot_solve runs the damped Newton loop of optimal_transport.hpp:89-193 collectively: evaluations are sharded,
+ *     per trial point 6 integers and 3 scalars are all-reduced, per accepted point the gradient / Hessian slices are
+ *     gathered and the grounded solve is replicated; all ranks return bit-identical weights;
+ *   - ma_evaluate keeps its results distributed (no collective except the flag / scalar all-reduces).
+ * All ranks must make the same sequence of calls.  libnccl.so.2 is loaded at the first ma_comm_* call; without it
+ * these functions return MA_CUDA_ERROR and everything else works. */
+int ma_comm_unique_id(void *id128);
+int ma_comm_init(ma_ctx *ctx, int rank, int nranks, const void *id128);
+int ma_comm_destroy(ma_ctx *ctx);
 
 /* Laguerre adjacency found by the last evaluation (caller ordering, CSR): the neighbours whose
  * bisector supports an edge of (cell ∩ mesh bounding box). */

@@ -29,6 +29,7 @@ SYMBOLS = (
     "ma_set_weights", "ma_evaluate",
     "ma_get_adjacency", "ma_set_profiling", "ma_get_timings", "ma_set_stats", "ma_get_counters", "ma_flush_l2",
     "ma_measure_fp64_peak", "ma_set_option", "ma_get_info", "ma_set_partition", "ma_timer_start", "ma_timer_stop",
+    "ma_comm_unique_id", "ma_comm_init", "ma_comm_destroy",
 )
 
 
@@ -92,6 +93,9 @@ def load_library(path: str | None = None):
     L.ma_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.ma_timer_start.argtypes = [vp]
     L.ma_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.ma_comm_unique_id.argtypes = [vp]
+    L.ma_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.ma_comm_destroy.argtypes = [vp]
     _lib = L
     return L
 
@@ -304,6 +308,14 @@ class Context:
     def set_partition(self, rank, nranks):
         self._ck(self.L.ma_set_partition(self.h, rank, nranks))
 
+    def comm_init(self, rank, nranks, unique_id: bytes):
+        """NCCL communicator of the ranks sharing this problem (ma_comm_init); unique_id from comm_unique_id() on one rank."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.L.ma_comm_init(self.h, rank, nranks, buf))
+
+    def comm_destroy(self):
+        self._ck(self.L.ma_comm_destroy(self.h))
+
     def timer_start(self):
         self._ck(self.L.ma_timer_start(self.h))
 
@@ -348,6 +360,15 @@ class Context:
 
     def info(self, name):
         return self.L.ma_get_info(self.h, name.encode())
+
+
+def comm_unique_id() -> bytes:
+    """128 bytes identifying a new NCCL communicator (ncclGetUniqueId): create on one rank, ship to the others."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.ma_comm_unique_id(buf) != MA_OK:
+        raise MAError(MA_CUDA_ERROR, "libnccl.so.2 could not be loaded")
+    return buf.raw
 
 
 def algorithmic_flops(c: dict) -> float:

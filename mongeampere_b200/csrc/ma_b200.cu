@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: libnccl is loaded at run time (ma_comm_init), single-GPU use never needs it
+
 #include "ma_pcg.cuh"
 
 using namespace ma;
@@ -49,6 +52,8 @@ struct ma_ctx {
   int strategy = 0;  // 0 auto (grid mesh: fused segment kernel, general mesh: pieces), 2: pieces always
   int part_rank = 0, part_n = 1;  // Morton tile of the Diracs this context evaluates
   void *comm = nullptr;           // ncclComm_t of the ranks that share the problem (ma_comm_init), else null
+  Buf dist_buf, rowptr_g, col_g, val_g;  // collectives' staging, the gathered (global) Hessian of the distributed Newton loop
+  int nnz_g = 0;
   long long launches = 0;         // kernels launched by this context (bench.py's gpu_launches)
   long long cell_fallbacks = 0;   // K2: vertices whose in/out sign went to the exact stage in the last evaluation
 
@@ -250,7 +255,7 @@ void invalidate_eval(ma_ctx *c) {
 // =============================================================================================
 // context
 // =============================================================================================
-extern "C" int ma_abi_version(void) { return 1; }
+extern "C" int ma_abi_version(void) { return 2; }
 
 extern "C" int ma_create(ma_ctx **out, int device) {
   if (!out) return MA_INVALID;
@@ -296,7 +301,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
                   &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->rho_p, &c->bin_rm,
-                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->hard1, &c->hard2, &c->hard_n};
+                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard_n};
     for (Buf *b : all) release(*b);
     for (int l = 0; l < AMG_MAX_LEVELS; ++l) {
       Buf *lv[] = {&c->amg.agg[l], &c->amg.cstart[l], &c->amg.code[l], &c->amg.rowptr[l], &c->amg.col[l], &c->amg.val[l],
@@ -310,6 +315,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
       if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->ev_chunk)
       if (ev) cudaEventDestroy(ev);
+    ma_comm_destroy(c);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     if (c->hs) cudaFreeHost(c->hs);
@@ -622,6 +628,193 @@ extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y)
 }
 
 // =============================================================================================
+// multi-GPU: NCCL inside the engine.  One process per GPU; every rank holds the points,
+// the weights and the mesh and evaluates its Morton tile of the Diracs; what crosses NVLink is
+//   * per evaluation: 6 integers (capacity / abort flags, so that all ranks take the same branch) and 3 scalars
+//     (f, sum of masses: sum; min mass: min);
+//   * per ACCEPTED Newton point: the tiles' slices of m - nu, of the row counts and of the Hessian's CSR
+//     (grouped ncclBroadcast, one per tile: the tiles differ in size by one row at most, but in nnz freely);
+// the grounded Laplacian solve is then replicated on every rank — with the multigrid preconditioner it is ~10 ms at
+// 1 M rows, less than a distributed CG would spend in its per-iteration all-gathers — and all ranks hold bit-identical
+// weights without ever exchanging them (every kernel of the solve reduces in a fixed order).
+// libnccl is dlopen()ed on first use so that libma_b200.so loads without it, and so that a process which already
+// has torch's NCCL mapped binds to that very copy.
+// =============================================================================================
+namespace {
+
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl_api() {
+  static NcclApi a;
+  static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+    a.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (a.h) break;
+  }
+  if (!a.h) return a;
+#define MA_NCCL_SYM(field, sym) a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.h, sym))
+  MA_NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); MA_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+  MA_NCCL_SYM(CommDestroy, "ncclCommDestroy"); MA_NCCL_SYM(AllReduce, "ncclAllReduce");
+  MA_NCCL_SYM(Broadcast, "ncclBroadcast"); MA_NCCL_SYM(GroupStart, "ncclGroupStart");
+  MA_NCCL_SYM(GroupEnd, "ncclGroupEnd"); MA_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef MA_NCCL_SYM
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Broadcast && a.GroupStart && a.GroupEnd;
+  return a;
+}
+#define NCK(call)                                                                                            \
+  do {                                                                                                       \
+    ncclResult_t r_ = (call);                                                                                \
+    if (r_ != ncclSuccess)                                                                                   \
+      return fail(c, MA_CUDA_ERROR, "%s failed: %s", #call, nccl_api().GetErrorString ? nccl_api().GetErrorString(r_) : "?"); \
+  } while (0)
+
+inline bool is_dist(const ma_ctx *c) { return c->comm != nullptr && c->part_n > 1; }
+inline int tile_lo(const ma_ctx *c, int r) { return (int)((long long)c->N * r / c->part_n); }
+
+// flags[0] bit field + flags[1] abort + flags[2] exact-stage count  <->  one integer per item, so that MAX / SUM apply
+__global__ void k_flags_unpack(const int *__restrict__ flags, int *__restrict__ out) {
+  if (threadIdx.x < 4) out[threadIdx.x] = (flags[0] >> threadIdx.x) & 1;
+  if (threadIdx.x == 4) out[4] = flags[1] != 0;
+  if (threadIdx.x == 5) out[5] = flags[2] > 0;
+}
+__global__ void k_flags_pack(const int *__restrict__ in, int *__restrict__ flags) {
+  if (threadIdx.x == 0) {
+    flags[0] = (in[0] ? 1 : 0) | (in[1] ? 2 : 0) | (in[2] ? 4 : 0) | (in[3] ? 8 : 0);
+    flags[1] = in[4];
+    flags[2] = max(flags[2], in[5]);
+  }
+}
+// every rank leaves with the union of all ranks' flags (they then take the same branch: escalate / abort / go on)
+int dist_sync_flags(ma_ctx *c) {
+  if (!is_dist(c)) return MA_OK;
+  CKR(ensure(c, c->dist_buf, 256));
+  int *b = c->dist_buf.as<int>();
+  k_flags_unpack<<<1, 32, 0, c->stream>>>(c->flags.as<int>(), b);
+  NCK(nccl_api().AllReduce(b, b, 6, ncclInt32, ncclMax, (ncclComm_t)c->comm, c->stream));
+  k_flags_pack<<<1, 32, 0, c->stream>>>(b, c->flags.as<int>());
+  c->launches += 2;
+  return MA_OK;
+}
+// red = {sum f, -, -, -, sum m, -, min m, -} of the tile (reduce4 layout)  ->  of all tiles
+__global__ void k_red_pack(const double *__restrict__ red, double *__restrict__ out) {
+  if (threadIdx.x == 0) { out[0] = red[0]; out[1] = red[4]; out[2] = red[6]; }
+}
+__global__ void k_red_unpack(const double *__restrict__ in, double *__restrict__ red) {
+  if (threadIdx.x == 0) { red[0] = in[0]; red[4] = in[1]; red[6] = in[2]; }
+}
+int dist_reduce_eval(ma_ctx *c) {
+  if (!is_dist(c)) return MA_OK;
+  CKR(ensure(c, c->dist_buf, 256));
+  double *b = reinterpret_cast<double *>(c->dist_buf.as<char>() + 64);
+  k_red_pack<<<1, 32, 0, c->stream>>>(c->red_out.as<double>(), b);
+  NCK(nccl_api().AllReduce(b, b, 2, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+  NCK(nccl_api().AllReduce(b + 2, b + 2, 1, ncclDouble, ncclMin, (ncclComm_t)c->comm, c->stream));
+  k_red_unpack<<<1, 32, 0, c->stream>>>(b, c->red_out.as<double>());
+  c->launches += 2;
+  return MA_OK;
+}
+// in-place gather of the tiles' slices of a full-length array (element size esz): rank r owns [tile_lo(r), tile_lo(r+1))
+int dist_gather_slices(ma_ctx *c, void *v, size_t esz) {
+  if (!is_dist(c)) return MA_OK;
+  NCK(nccl_api().GroupStart());
+  for (int r = 0; r < c->part_n; ++r) {
+    const int lo = tile_lo(c, r), hi = tile_lo(c, r + 1);
+    if (hi > lo) {
+      char *ptr = (char *)v + (size_t)lo * esz;
+      NCK(nccl_api().Broadcast(ptr, ptr, (size_t)(hi - lo) * esz, ncclChar, r, (ncclComm_t)c->comm, c->stream));
+    }
+  }
+  NCK(nccl_api().GroupEnd());
+  return MA_OK;
+}
+__global__ void k_copy_rows(const int *__restrict__ rowptr_l, const int *__restrict__ rowptr_g, int lo, int hi,
+                            const int *__restrict__ col_l, const double *__restrict__ val_l, int *__restrict__ col_g,
+                            double *__restrict__ val_g) {
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  const int s = rowptr_l[i], e = rowptr_l[i + 1], o = rowptr_g[i];
+  for (int q = s; q < e; ++q) { col_g[o + (q - s)] = col_l[q]; val_g[o + (q - s)] = val_l[q]; }
+}
+// The Hessian of ALL tiles on every rank (internal order): row counts -> global row pointers -> this tile's rows
+// copied to their global place -> one broadcast per tile.  Leaves rowptr_g / col_g / val_g / nnz_g.
+int dist_gather_hessian(ma_ctx *c) {
+  const int N = c->N;
+  CKR(dist_gather_slices(c, c->rowcnt.p, 4));
+  CKR(ensure(c, c->rowptr_g, ((size_t)N + 1) * 4));
+  CKR(scan_i32(c, c->rowcnt.as<int>(), c->rowptr_g.as<int>(), N));
+  std::vector<int> off(c->part_n + 1);
+  for (int r = 0; r <= c->part_n; ++r)
+    CK(cudaMemcpyAsync(&off[r], c->rowptr_g.as<int>() + tile_lo(c, r), 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->nnz_g = off[c->part_n];
+  CKR(ensure(c, c->col_g, (size_t)std::max(c->nnz_g, 1) * 4, 1.2));
+  CKR(ensure(c, c->val_g, (size_t)std::max(c->nnz_g, 1) * 8, 1.2));
+  const int lo = tile_lo(c, c->part_rank), hi = tile_lo(c, c->part_rank + 1);
+  if (hi > lo)
+    k_copy_rows<<<cdiv(hi - lo, 256), 256, 0, c->stream>>>(c->rowptr.as<int>(), c->rowptr_g.as<int>(), lo, hi, c->col.as<int>(),
+                                                          c->val.as<double>(), c->col_g.as<int>(), c->val_g.as<double>());
+  c->launches++;
+  NCK(nccl_api().GroupStart());
+  for (int r = 0; r < c->part_n; ++r) {
+    const size_t cnt = (size_t)(off[r + 1] - off[r]);
+    if (!cnt) continue;
+    NCK(nccl_api().Broadcast(c->col_g.as<int>() + off[r], c->col_g.as<int>() + off[r], cnt, ncclInt32, r, (ncclComm_t)c->comm, c->stream));
+    NCK(nccl_api().Broadcast(c->val_g.as<double>() + off[r], c->val_g.as<double>() + off[r], cnt, ncclDouble, r, (ncclComm_t)c->comm, c->stream));
+  }
+  NCK(nccl_api().GroupEnd());
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+
+}  // namespace
+
+extern "C" int ma_comm_unique_id(void *id128) {
+  if (!id128) return MA_INVALID;
+  NcclApi &a = nccl_api();
+  if (!a.ok) return MA_CUDA_ERROR;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (a.GetUniqueId(&id) != ncclSuccess) return MA_CUDA_ERROR;
+  memcpy(id128, &id, 128);
+  return MA_OK;
+}
+extern "C" int ma_comm_init(ma_ctx *c, int rank, int nranks, const void *id128) {
+  if (!c) return MA_INVALID;
+  if (!c->stream) return fail(c, MA_CUDA_ERROR, "context has no CUDA device");
+  cudaSetDevice(c->device);
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, MA_INVALID, "ma_comm_init: bad arguments");
+  NcclApi &a = nccl_api();
+  if (!a.ok) return fail(c, MA_CUDA_ERROR, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+  if (c->comm) { a.CommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclComm_t comm = nullptr;
+  NCK(a.CommInitRank(&comm, nranks, id, rank));
+  c->comm = comm;
+  c->part_rank = rank;
+  c->part_n = nranks;
+  c->cells_nv = -1; c->have_eval = false; c->have_hessian = false;
+  return MA_OK;
+}
+extern "C" int ma_comm_destroy(ma_ctx *c) {
+  if (!c) return MA_INVALID;
+  if (c->comm) { nccl_api().CommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
+  return MA_OK;
+}
+
+// =============================================================================================
 // evaluation (K1 per-eval + K2 + K3 + K4)
 // =============================================================================================
 namespace {
@@ -678,19 +871,18 @@ template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
   const int ncells = p.cell_hi - p.cell_lo;
   int *cnt = c->hard_n.as<int>();
   CK(cudaMemsetAsync(cnt, 0, 16, c->stream));
-  CK(cudaFuncSetAttribute(k_cells_block<2, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  CK(cudaFuncSetAttribute(k_cells_block<3, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(cudaFuncSetAttribute(k_cells_block<-1, 2, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(cudaFuncSetAttribute(k_cells_block<2, 3, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  CK(cudaFuncSetAttribute(k_cells_block<5, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int nblk = std::max(1, cdiv(ncells, NT));
-  k_cells_block<2, MAXV, NT, POLY><<<nblk, NT, sm, c->stream>>>(p, nullptr, nullptr, c->hard1.as<int>(), cnt);
-  // the later stages see a fraction of the cells (or, with graded weights, all of them: k_cells_persist then ignores the
-  // list): radius 3 for the ~15 % the 5 x 5 block cannot certify, radius 5 for the ~0.4 % left after that (one by one
-  // through CellSearch those few cells cost 0.6 ms of pure latency, profiles/r02b), CellSearch for the rest
+  k_cells_block<-1, 2, MAXV, NT, POLY><<<nblk, NT, sm, c->stream>>>(p, nullptr, nullptr, c->hard1.as<int>(), cnt);
+  // The later stages see a fraction of the cells (or, with graded weights, all of them: k_cells_persist then ignores the
+  // list): the ~15 % the 5 x 5 block cannot certify continue from their polygon with the ring of bins around it, the
+  // ~0.4 % left after that get a warp each and the block of radius 5 (one by one through CellSearch those few cells
+  // cost 0.6 ms of pure latency, profiles/r02b), CellSearch takes whatever remains.
   const int nblk2 = std::max(1, std::min(nblk, c->sm_count * 8));
-  k_cells_block<3, MAXV, NT, POLY><<<nblk2, NT, sm, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
-  k_cells_block<5, MAXV, NT, POLY><<<std::max(1, std::min(nblk, c->sm_count * 2)), NT, sm, c->stream>>>(p, c->hard2.as<int>(), cnt + 1,
-                                                                                                    c->hard1.as<int>(), cnt + 2);
+  k_cells_block<2, 3, MAXV, NT, POLY><<<nblk2, NT, sm, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
+  k_cells_warp<5, POLY><<<c->sm_count * 4, 128, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, c->hard1.as<int>(), cnt + 2);
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cells_persist<MAXV, NT, POLY>, NT, sm));
   const long long warps_target = (long long)c->sm_count * std::max(per_sm, 1) * (NT / 32) * c->persist_waves;
@@ -783,6 +975,10 @@ int alloc_eval(ma_ctx *c) {
   CKR(ensure(c, c->flags, 16));
   CKR(ensure(c, c->red_out, 16 * sizeof(double)));
   CKR(ensure(c, c->wstat, 4 * sizeof(double)));
+  // cell polygons: what k_seg integrates, and what the block kernels hand from one pass to the next
+  const size_t slots = (size_t)(c->kmax == 16 ? 16 : (c->kmax == 32 ? 36 : 64)) * N;
+  CKR(ensure(c, c->poly_x, slots * 8)); CKR(ensure(c, c->poly_y, slots * 8));
+  CKR(ensure(c, c->poly_t, slots * 4)); CKR(ensure(c, c->poly_n, N * 4));
   return MA_OK;
 }
 
@@ -853,6 +1049,7 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     if (c->abort_on_empty) {
       // line-search trial: an empty cell means min m = 0 < eps0, the point is rejected whatever the
       // rest of the evaluation says (optimal_transport.hpp:167), so stop here
+      CKR(dist_sync_flags(c));  // (multi-GPU: a cell of ANY tile)
       CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 8, cudaMemcpyDeviceToHost, c->stream));  // flags[0], flags[1]
       CK(cudaStreamSynchronize(c->stream));
       if (c->hs->flags & (FLAG_CELL_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
@@ -880,6 +1077,8 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       CKR(reduce4(c, c->fcell.as<double>() + lo, nullptr, nloc, c->red_out.as<double>()));
       CKR(reduce4(c, c->mass.as<double>() + lo, nullptr, nloc, c->red_out.as<double>() + 4));
     }
+    CKR(dist_sync_flags(c));
+    if (MODE == MODE_KANTOROVICH) CKR(dist_reduce_eval(c));  // f, sum m, min m over all tiles
     c->hs->flags = 0; c->hs->nnz = 0;
     CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 12, cudaMemcpyDeviceToHost, c->stream));  // flags, abort, K2 exact-stage count
     if (MODE == MODE_KANTOROVICH) {
@@ -990,8 +1189,12 @@ extern "C" int ma_kantorovich(ma_ctx *c, const double *w, double *fval, double *
   NEED_CTX();
   CKR(ma_set_weights(c, w));
   CKR(evaluate_mode<MODE_KANTOROVICH>(c, true));
+  if (is_dist(c)) {  // with a communicator the call returns the whole problem's g and h on every rank
+    CKR(dist_gather_slices(c, c->mass.p, 8));
+    CKR(dist_gather_hessian(c));
+  }
   if (fval) *fval = c->fval;
-  if (nnz) *nnz = c->nnz;
+  if (nnz) *nnz = is_dist(c) ? c->nnz_g : c->nnz;
   if (g) {
     CKR(ensure(c, c->cg_out, (size_t)c->N * 8));
     k_scatter_to_caller<<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->mass.as<double>(), c->perm.as<int>(), c->N,
@@ -1008,11 +1211,16 @@ extern "C" int ma_get_hessian_csr(ma_ctx *c, int *rowptr, int *col, double *val)
   if (!c->have_hessian) return fail(c, MA_INVALID, "no Hessian: call ma_kantorovich first");
   if (!rowptr || !col || !val) return fail(c, MA_INVALID, "ma_get_hessian_csr: null output");
   const int N = c->N;
+  const bool dist = is_dist(c);
+  const int nnz_all = dist ? c->nnz_g : c->nnz;
+  const int *rowptr_s = dist ? c->rowptr_g.as<int>() : c->rowptr.as<int>();
+  const int *col_s = dist ? c->col_g.as<int>() : c->col.as<int>();
+  const double *val_s = dist ? c->val_g.as<double>() : c->val.as<double>();
   CKR(ensure(c, c->scratch_i, (size_t)N * 4));
   CKR(ensure(c, c->cptr, (size_t)(N + 1) * 4));
-  CKR(ensure(c, c->ccol, (size_t)std::max(c->nnz, 1) * 4));
-  CKR(ensure(c, c->cval, (size_t)std::max(c->nnz, 1) * 8));
-  k_rowcnt_to_caller<<<cdiv(N, 256), 256, 0, c->stream>>>(c->rowptr.as<int>(), c->pos.as<int>(), N,
+  CKR(ensure(c, c->ccol, (size_t)std::max(nnz_all, 1) * 4));
+  CKR(ensure(c, c->cval, (size_t)std::max(nnz_all, 1) * 8));
+  k_rowcnt_to_caller<<<cdiv(N, 256), 256, 0, c->stream>>>(rowptr_s, c->pos.as<int>(), N,
                                                           c->scratch_i.as<int>());
   CKR(scan_i32(c, c->scratch_i.as<int>(), c->cptr.as<int>(), N));
   c->launches += 1;
@@ -1021,12 +1229,12 @@ extern "C" int ma_get_hessian_csr(ma_ctx *c, int *rowptr, int *col, double *val)
   CK(cudaStreamSynchronize(c->stream));
   // then chunk by chunk: rows of chunk q are put in caller order on the main stream while the copy engine
   // ships chunk q-1 on the second stream (the transfer is PCIe-bound, the conversion hides behind it)
-  const int Q = (c->nnz > (1 << 20)) ? 8 : 1;
+  const int Q = (nnz_all > (1 << 20)) ? 8 : 1;
   for (int q = 0; q < Q; ++q) {
     const int r0 = (int)((long long)N * q / Q), r1 = (int)((long long)N * (q + 1) / Q);
     if (r1 <= r0) continue;
-    k_csr_to_caller<<<cdiv(r1 - r0, 128), 128, 0, c->stream>>>(r0, r1, c->rowptr.as<int>(), c->col.as<int>(),
-                                                             c->val.as<double>(), c->pos.as<int>(), c->perm.as<int>(),
+    k_csr_to_caller<<<cdiv(r1 - r0, 128), 128, 0, c->stream>>>(r0, r1, rowptr_s, col_s,
+                                                             val_s, c->pos.as<int>(), c->perm.as<int>(),
                                                              c->cptr.as<int>(), c->ccol.as<int>(), c->cval.as<double>());
     c->launches += 1;
     CK(cudaEventRecord(c->ev_chunk[q], c->stream));
@@ -1570,10 +1778,13 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
       return MA_OK;
     }
     CKR(rc_e);
-    // ws is the sorted copy of the weights used by this evaluation
-    k_sub<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->mass.as<double>(), c->nu_s.as<double>(), c->g_s.as<double>());
+    // ws is the sorted copy of the weights used by this evaluation; g = m - nu on this context's tile (multi-GPU: the
+    // tiles' |g|^2 are summed over NVLink, the weights are replicated so nu.x needs nothing)
+    const int lo = tile_lo(c, c->part_rank), hi = tile_lo(c, c->part_rank + 1);
+    k_sub<<<cdiv(hi - lo, 256), 256, 0, c->stream>>>(hi - lo, c->mass.as<double>() + lo, c->nu_s.as<double>() + lo, c->g_s.as<double>() + lo);
     c->launches++;
-    CKR(reduce4(c, c->g_s.as<double>(), nullptr, N, c->red_out.as<double>()));
+    CKR(reduce4(c, c->g_s.as<double>() + lo, nullptr, hi - lo, c->red_out.as<double>()));
+    if (is_dist(c)) NCK(nccl_api().AllReduce(c->red_out.as<double>() + 1, c->red_out.as<double>() + 1, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
     CKR(reduce4(c, c->ws.as<double>(), c->nu_s.as<double>(), N, c->red_out.as<double>() + 4));
     double red[8];
     CK(cudaMemcpyAsync(red, c->red_out.p, sizeof red, cudaMemcpyDeviceToHost, c->stream));
@@ -1627,9 +1838,15 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
     // direction is close to (1 - tau) times the last one (still in d_s)
     const bool warm = c->cg_warm && have_dir;
     if (warm) CK(cudaMemcpyAsync(c->scratch_d.p, c->d_s.p, (size_t)N * 8, cudaMemcpyDeviceToDevice, c->stream));
-    int rc = pcg_solve(c, N, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(), c->g_s.as<double>(), -1.0,
+    const bool dist = is_dist(c);
+    if (dist) {  // the accepted point's gradient and Hessian of every tile, then the same solve on every rank
+      CKR(dist_gather_slices(c, c->g_s.p, 8));
+      CKR(dist_gather_hessian(c));
+    }
+    int rc = pcg_solve(c, N, dist ? c->rowptr_g.as<int>() : c->rowptr.as<int>(), dist ? c->col_g.as<int>() : c->col.as<int>(),
+                       dist ? c->val_g.as<double>() : c->val.as<double>(), c->g_s.as<double>(), -1.0,
                        ground, c->d_s.as<double>(), &it, &relres, warm ? c->scratch_d.as<double>() : nullptr,
-                       1.0 - last_alpha, /*use_amg=*/true, c->nnz);
+                       1.0 - last_alpha, /*use_amg=*/true, dist ? c->nnz_g : c->nnz);
     have_dir = true;
     t_pcg += secs(t0p, now());
     cg_total += it;

@@ -36,39 +36,101 @@ namespace ma {
 #define MA_WARP_MAX_INT(v) (v)
 #endif
 
-// Builds the cell of S.i (S.init() already done) from the block of radius R.  `active` = false lanes only
-// keep the warp's votes company.  On return S.phase == 0: polygon of S.n vertices in P, certified says whether
-// it is final; S.phase == 2: S.n == 0 and S.status tells an empty cell (0) from a capacity overflow.
+// The candidate runs of one cell: the bins of the block of radius R around bin (cbx, cby) that are NOT in the block
+// of radius R0 (R0 = -1: the whole block), row by row, nearest rows first.  Rows inside the inner block contribute
+// the two strips left and right of it, the others one full run.
+template <int R0, int R> struct BlockRuns {
+  static constexpr int NR = (R0 < 0) ? (2 * R + 1) : (2 * (2 * R0 + 1) + 2 * (R - R0));
+  int cum[NR + 1], off[NR];
+  MA_DEV void build(const Params &p, int cbx, int cby, bool active) {
+    const int G = p.bG;
+    int q = 0;
+    cum[0] = 0;
+    auto run = [&](int row, int xa, int xb) {  // bins [xa, xb] of row `row` (may be empty / outside)
+      int s = 0, len = 0;
+      xa = max(xa, 0); xb = min(xb, G - 1);
+      if (active && row >= 0 && row < G && xb >= xa) {
+        s = p.rm_start[(size_t)row * G + xa];
+        len = p.rm_start[(size_t)row * G + xb + 1] - s;
+      }
+      off[q] = s - cum[q];
+      cum[q + 1] = cum[q] + len;
+      ++q;
+    };
+#pragma unroll
+    for (int r = 0; r < 2 * R + 1; ++r) {
+      const int dy = (r == 0) ? 0 : ((r & 1) ? -((r + 1) >> 1) : (r >> 1));  // own row first, then -1, +1, -2, +2 ...
+      const int ady = dy < 0 ? -dy : dy;
+      if (ady <= R0) { run(cby + dy, cbx - R, cbx - R0 - 1); run(cby + dy, cbx + R0 + 1, cbx + R); }
+      else run(cby + dy, cbx - R, cbx + R);
+    }
+  }
+  MA_DEV int total() const { return cum[NR]; }
+  MA_DEV int position(int t) const {  // index of candidate t in the row-major arrays
+    int o = off[0];
+#pragma unroll
+    for (int r = 1; r < NR; ++r) o = (t >= cum[r]) ? off[r] : o;
+    return t + o;
+  }
+};
+
+// Does every vertex of the polygon keep its distance from the sites outside the block of radius R (see the header)?
 template <int R, class Poly>
+MA_DEV bool block_certified(const Params &p, const CellSearch<Poly> &S, const Poly &P, int cbx, int cby) {
+  const int G = p.bG;
+  const double INF = 1.0 / 0.0;
+  const double bl = (cbx - R > 0) ? p.px0 + (double)(cbx - R) * p.bph - S.xi : -INF;
+  const double br = (cbx + R < G - 1) ? p.px0 + (double)(cbx + R + 1) * p.bph - S.xi : INF;
+  const double bb = (cby - R > 0) ? p.py0 + (double)(cby - R) * p.bph - S.yi : -INF;
+  const double bt = (cby + R < G - 1) ? p.py0 + (double)(cby + R + 1) * p.bph - S.yi : INF;
+  const double dwg = p.wmax[0] - S.wi;  // >= 0
+  const double slack = 1e-9 * p.bph;    // a site sits in its bin up to the rounding of the bin index
+  bool ok = true;
+  for (int k = 0; k < S.n; ++k) {
+    const double X = P.X(k), Y = P.Y(k);
+    const double rp = X * X + Y * Y + dwg;
+    const double d = fmin(fmin(X - bl, br - X), fmin(Y - bb, bt - Y)) - slack;
+    ok = ok && (rp <= 0.0 || (d > 0.0 && d * d >= rp * (1.0 + 1e-9)));
+  }
+  return ok;
+}
+
+// Reloads the polygon a previous pass left for cell S.i (k_cells_block stores it for the cells it cannot certify);
+// false if there is none (the cell outgrew the 16-vertex class there: it goes straight to CellSearch).
+template <class Poly> MA_DEV bool block_reload(const Params &p, CellSearch<Poly> &S, Poly &P) {
+  const int n = p.poly_n[S.i];
+  if (n < 3 || n > 16) return false;
+  double r2 = 0.0;
+  for (int k = 0; k < n; ++k) {
+    const size_t o = (size_t)k * p.N + S.i;
+    const double X = p.poly_x[o], Y = p.poly_y[o];
+    P.SX(k) = X; P.SY(k) = Y; P.ST(k) = p.poly_t[o];
+    r2 = fmax(r2, X * X + Y * Y);
+  }
+  P.ord = 0xfedcba9876543210ull;  // vertex k in slot k
+  P.used = (1u << n) - 1u;
+  S.n = n;
+  S.R2 = r2;
+  return true;
+}
+
+// Builds the cell of S.i from the block of radius R.  R0 < 0: from scratch (S.init() already done); R0 >= 0: the
+// polygon in P is what the block of radius R0 left (a previous pass), only the bins beyond it are looked at.
+// `active` = false lanes only keep the warp's votes company.  On return S.phase == 0: polygon of S.n vertices in P,
+// certified says whether it is final; S.phase == 2: S.n == 0 and S.status tells an empty cell (0) from a capacity overflow.
+template <int R0, int R, class Poly>
 MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv, bool active, bool &certified) {
-  constexpr int NR = 2 * R + 1;
   const int G = p.bG;
   // the Dirac's bin of the block grid (same expression as k_blk_count, so a site is in the bin it was filed under)
   const int cbx = min(max((int)((S.xi - p.px0) * p.binv), 0), G - 1);
   const int cby = min(max((int)((S.yi - p.py0) * p.binv), 0), G - 1);
-  const int x0 = max(cbx - R, 0), x1 = min(cbx + R, G - 1);
-  int cum[NR + 1], off[NR];
-  cum[0] = 0;
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const int dy = (r == 0) ? 0 : ((r & 1) ? -((r + 1) >> 1) : (r >> 1));  // own row first, then -1, +1, -2, +2 ...
-    const int row = cby + dy;
-    int s = 0, len = 0;
-    if (active && row >= 0 && row < G) {
-      s = p.rm_start[(size_t)row * G + x0];
-      len = p.rm_start[(size_t)row * G + x1 + 1] - s;
-    }
-    off[r] = s - cum[r];
-    cum[r + 1] = cum[r] + len;
-  }
-  const int T = cum[NR];
+  BlockRuns<R0, R> runs;
+  runs.build(p, cbx, cby, active);
+  const int T = runs.total();
   const int Tmax = MA_WARP_MAX_INT(T);
   for (int t = 0; t < Tmax; ++t) {
     const bool act = active && S.phase == 0 && t < T;
-    int o = off[0];
-#pragma unroll
-    for (int r = 1; r < NR; ++r) o = (t >= cum[r]) ? off[r] : o;
-    const int pos = act ? t + o : 0;
+    const int pos = act ? runs.position(t) : 0;
     const double Dx = p.xr[pos] - S.xi, Dy = p.yr[pos] - S.yi, wj = p.wr[pos];
     const double dd2 = Dx * Dx + Dy * Dy;
     const double dw = S.wi - wj;
@@ -100,26 +162,8 @@ MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv
     }
   }
   // ---- certificate ----
-  certified = false;
-  if (S.phase == 0) {
-    const double INF = 1.0 / 0.0;
-    const double bl = (cbx - R > 0) ? p.px0 + (double)(cbx - R) * p.bph - S.xi : -INF;
-    const double br = (cbx + R < G - 1) ? p.px0 + (double)(cbx + R + 1) * p.bph - S.xi : INF;
-    const double bb = (cby - R > 0) ? p.py0 + (double)(cby - R) * p.bph - S.yi : -INF;
-    const double bt = (cby + R < G - 1) ? p.py0 + (double)(cby + R + 1) * p.bph - S.yi : INF;
-    const double dwg = p.wmax[0] - S.wi;  // >= 0
-    const double slack = 1e-9 * p.bph;    // a site sits in its bin up to the rounding of the bin index
-    bool ok = true;
-    for (int k = 0; k < S.n; ++k) {
-      const double X = P.X(k), Y = P.Y(k);
-      const double rp = X * X + Y * Y + dwg;
-      const double d = fmin(fmin(X - bl, br - X), fmin(Y - bb, bt - Y)) - slack;
-      ok = ok && (rp <= 0.0 || (d > 0.0 && d * d >= rp * (1.0 + 1e-9)));
-    }
-    certified = ok;
-  } else {
-    certified = S.status == 0;  // hidden Dirac: one site covers a superset of the cell, nothing to certify
-  }
+  if (S.phase == 0) certified = block_certified<R>(p, S, P, cbx, cby);
+  else certified = S.status == 0;  // hidden Dirac: one site covers a superset of the cell, nothing to certify
 }
 
 }  // namespace ma

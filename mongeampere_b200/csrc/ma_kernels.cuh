@@ -635,7 +635,8 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
 #ifndef MA_K2B_MINBLOCKS
 #define MA_K2B_MINBLOCKS 5
 #endif
-template <int R, int MAXV, int NT, bool POLY>
+// R0 >= 0: the pass continues from the polygon the pass of radius R0 stored and looks only at the bins beyond that block.
+template <int R0, int R, int MAXV, int NT, bool POLY>
 __global__ void __launch_bounds__(NT, MA_K2B_MINBLOCKS) k_cells_block(Params p, const int *__restrict__ in_list, const int *__restrict__ in_n,
                                                                       int *__restrict__ out_list, int *__restrict__ out_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -654,19 +655,23 @@ __global__ void __launch_bounds__(NT, MA_K2B_MINBLOCKS) k_cells_block(Params p, 
     Poly P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
     CellSearch<Poly> S;
     S.init(p, i, P);
-    bool cert = false;
-    block_search<R>(p, S, P, MAXV, valid, cert);
+    bool cert = false, usable = true;
+    if (R0 >= 0) usable = block_reload(p, S, P);
+    block_search<R0, R>(p, S, P, MAXV, valid && usable, cert);
+    cert = cert && usable;
     __syncwarp();
     if (valid && cert) {
       const int n = S.n;
       if (n == 0 && p.abort_on_empty) p.flags[1] = 1;  // a hidden Dirac: the line search rejects this trial point
       cell_emit(p, i, P, n);
-      if (POLY) {
-        p.poly_n[i] = n;
-        for (int k = 0; k < n; ++k) {
-          const size_t o = (size_t)k * p.N + i;
-          p.poly_x[o] = P.X(k); p.poly_y[o] = P.Y(k); p.poly_t[o] = P.T(k);
-        }
+    }
+    if (valid && usable && (cert ? POLY : true)) {
+      // certified: the polygon k_seg integrates; not certified: what the next pass continues from (-1: nothing usable)
+      const int n = (S.phase == 0 || cert) ? S.n : -1;
+      p.poly_n[i] = n;
+      for (int k = 0; k < n; ++k) {
+        const size_t o = (size_t)k * p.N + i;
+        p.poly_x[o] = P.X(k); p.poly_y[o] = P.Y(k); p.poly_t[o] = P.T(k);
       }
     }
     const bool hard = valid && !cert;
@@ -676,6 +681,98 @@ __global__ void __launch_bounds__(NT, MA_K2B_MINBLOCKS) k_cells_block(Params p, 
       if (lane == (unsigned)(__ffs(hm) - 1)) b = atomicAdd(out_n, __popc(hm));
       b = __shfl_sync(0xffffffffu, b, __ffs(hm) - 1);
       if (hard) out_list[b + __popc(hm & ((1u << lane) - 1u))] = i;
+    }
+    __syncwarp();
+  }
+}
+
+// K2, the tail: ONE WARP per cell for the few cells (0.4 % of a uniform point set) that even the 7 x 7 block cannot
+// certify.  Thread-per-cell kernels run them at the latency of a single lane walking 121 candidates; here the 32
+// lanes test 32 candidates of the block of radius R at once against the polygon (shared memory), the cutting ones are
+// clipped one after the other by their own lane and the survivors re-tested — the mapping of north_star (2).
+template <int R, bool POLY>
+__global__ void __launch_bounds__(128) k_cells_warp(Params p, const int *__restrict__ in_list, const int *__restrict__ in_n,
+                                                    int *__restrict__ out_list, int *__restrict__ out_n) {
+  __shared__ double sx[4][16], sy[4][16];
+  __shared__ int st[4][16];
+  if (weights_graded(p)) return;
+  typedef PolyRef<1, true> Poly;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n_in = *in_n;
+  for (int idx = blockIdx.x * 4 + wib; idx < n_in; idx += gridDim.x * 4) {
+    const int i = in_list[idx];
+    Poly P{sx[wib], sy[wib], st[wib]};
+    CellSearch<Poly> S;
+    S.init(p, i, P);  // every lane writes the same box into the warp's polygon
+    __syncwarp();
+    const int G = p.bG;
+    const int cbx = min(max((int)((S.xi - p.px0) * p.binv), 0), G - 1);
+    const int cby = min(max((int)((S.yi - p.py0) * p.binv), 0), G - 1);
+    BlockRuns<-1, R> runs;
+    runs.build(p, cbx, cby, true);
+    const int T = runs.total();
+    for (int t0 = 0; t0 < T && S.phase == 0; t0 += 32) {
+      const int t = t0 + lane;
+      const bool act = t < T;
+      const int pos = act ? runs.position(t) : 0;
+      const double Dx = p.xr[pos] - S.xi, Dy = p.yr[pos] - S.yi, wj = p.wr[pos];
+      const double dd2 = Dx * Dx + Dy * Dy, dw = S.wi - wj, c = 0.5 * (dd2 + dw);
+      const int jj = p.rm2s[pos];
+      bool kills = act && dd2 == 0.0 && jj != i && (wj > S.wi || (wj == S.wi && jj < i));  // coincident, heavier / earlier
+      bool pending = act && dd2 > 0.0;
+      for (;;) {
+        // every pending lane tests its candidate against the polygon as it is now
+        unsigned long long in = 0ull;
+        bool cut = false;
+        if (pending) {
+          if (c >= 0.0 && c * c >= S.R2 * dd2 * (1.0 + 1e-9)) pending = false;  // cannot reach the polygon any more
+          else {
+            double r2;
+            in = S.sign_mask(p, P, jj, Dx, Dy, c, dd2, dw, r2);
+            if (in == 0ull) kills = true;
+            cut = in != 0ull && in != lowmask64(S.n);
+            pending = cut;
+          }
+        }
+        if (__any_sync(0xffffffffu, kills)) { S.n = 0; S.phase = 2; break; }
+        const unsigned cm = __ballot_sync(0xffffffffu, cut);
+        if (!cm) break;
+        const int leader = __ffs(cm) - 1;
+        if (lane == leader) {
+          S.jc = jj; S.cDx = Dx; S.cDy = Dy; S.cc = c; S.cin = in;
+          S.template clip<true>(p, P, 16);
+          pending = false;
+        }
+        __syncwarp();
+        // the leader's polygon state to everybody
+        S.n = __shfl_sync(0xffffffffu, S.n, leader);
+        S.status = __shfl_sync(0xffffffffu, S.status, leader);
+        S.phase = __shfl_sync(0xffffffffu, S.phase, leader);
+        S.R2 = __shfl_sync(0xffffffffu, S.R2, leader);
+        P.ord = __shfl_sync(0xffffffffu, P.ord, leader);
+        P.used = __shfl_sync(0xffffffffu, P.used, leader);
+        if (S.phase != 0) break;  // the polygon outgrew the 16-vertex class
+      }
+    }
+    __syncwarp();
+    bool cert;
+    if (S.phase == 0) cert = block_certified<R>(p, S, P, cbx, cby);
+    else cert = S.status == 0;
+    if (lane == 0) {
+      if (cert) {
+        const int n = S.n;
+        if (n == 0 && p.abort_on_empty) p.flags[1] = 1;
+        cell_emit(p, i, P, n);
+        if (POLY) {
+          p.poly_n[i] = n;
+          for (int k = 0; k < n; ++k) {
+            const size_t o = (size_t)k * p.N + i;
+            p.poly_x[o] = P.X(k); p.poly_y[o] = P.Y(k); p.poly_t[o] = P.T(k);
+          }
+        }
+      } else {
+        out_list[atomicAdd(out_n, 1)] = i;
+      }
     }
     __syncwarp();
   }

@@ -224,17 +224,19 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
   const double ninv = 1.0 / sqrt(inv_dx * inv_dx + inv_dy * inv_dy);  // 1 / |(1/dx, -1/dy)|
   const double dcoef = (inv_dx * inv_dx + inv_dy * inv_dy) * ninv;
   // line k of a family has a vertex on either side  <=>  min < k <= max over the vertices; lines of the padded grid only.
-  // The three families are walked as ONE list (a cell's total number of lines varies much less than its split over
-  // the families, and all lanes of a warp run as long as the longest list).
-  const int kx0 = max((int)floor(fxmin) + 1, 0), kx1 = min((int)floor(fxmax), sx_hi);
-  const int ky0 = max((int)floor(fymin) + 1, 0), ky1 = min((int)floor(fymax), sy_hi);
-  const int kd0 = max((int)floor(fdmin) + 1, -sy_hi - 1), kd1 = min((int)floor(fdmax), sx_hi + 1);
-  const int Lx = max(kx1 - kx0 + 1, 0), Ly = max(ky1 - ky0 + 1, 0), Ld = max(kd1 - kd0 + 1, 0);
+  // (One loop per family with the family a compile-time constant: walking the three families as one list with a
+  // run-time family evens out the trip counts across a warp but costs more in selects than it saves — measured.)
   const unsigned nmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
-  for (int q = 0; q < Lx + Ly + Ld; ++q) {
-    const int fam = (q >= Lx ? 1 : 0) + (q >= Lx + Ly ? 1 : 0);
-    const int k = fam == 0 ? kx0 + q : (fam == 1 ? ky0 + (q - Lx) : kd0 + (q - Lx - Ly));
+#pragma unroll
+  for (int fam = 0; fam < 3; ++fam) {
+    const double lo_f = fam == 0 ? fxmin : (fam == 1 ? fymin : fdmin);
+    const double hi_f = fam == 0 ? fxmax : (fam == 1 ? fymax : fdmax);
+    int k0 = (int)floor(lo_f) + 1, k1 = (int)floor(hi_f);
+    if (fam == 0) { k0 = max(k0, 0); k1 = min(k1, sx_hi); }
+    else if (fam == 1) { k0 = max(k0, 0); k1 = min(k1, sy_hi); }
+    else { k0 = max(k0, -sy_hi - 1); k1 = min(k1, sx_hi + 1); }
     const double fscale = fam == 0 ? p.gdx : (fam == 1 ? p.gdy : ninv);  // level function -> distance
+    for (int k = k0; k <= k1; ++k)
     {
       const double lev = (double)k;
       // level function at vertex v (always this very expression: its sign is THE side of v)

@@ -233,14 +233,21 @@ extern "C" int emu_eval(int mesh_kind,
       PolyRef<1, false> PA{px.data(), py.data(), pt.data()};
       int n = -2;
       if (kmax == 16 && emu_lean[0] && !graded) {
-        for (int pass = 0; pass < 3 && n == -2; ++pass) {
+        {  // pass 1: block of radius 2; pass 2 continues from its polygon with the ring around it; pass 3: radius 5 from scratch
           CellSearch<PolyRef<1, true>> S;
           S.init(p, i, PP);
           bool cert = false;
-          if (pass == 0) block_search<2>(p, S, PP, 16, true, cert);
-          else if (pass == 1) block_search<3>(p, S, PP, 16, true, cert);
-          else block_search<5>(p, S, PP, 16, true, cert);
-          if (cert) { n = S.n; emu_lean[1 + std::min(pass, 1)]++; }
+          block_search<-1, 2>(p, S, PP, 16, true, cert);
+          if (cert) { n = S.n; emu_lean[1]++; }
+          else if (S.phase == 0) {
+            block_search<2, 3>(p, S, PP, 16, true, cert);
+            if (cert) { n = S.n; emu_lean[2]++; }
+          }
+          if (n == -2) {
+            S.init(p, i, PP);
+            block_search<-1, 5>(p, S, PP, 16, true, cert);
+            if (cert) { n = S.n; emu_lean[2]++; }
+          }
         }
       }
       if (n == -2) {
