@@ -16,10 +16,11 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
                 measured in the same run (MEASURED_PEAKS.json has no fp64 figure); roofline_hbm is the
                 CSR fill (K4) against the measured HBM copy bandwidth.
   cpu_baseline  the oracle (CPU restatement, "port": the reference itself needs CGAL/Eigen/Boost,
-                absent here) on a bounded sample of the same workload.
+                absent here) on a bounded sample of the SAME problem: a contiguous range of its cells.
   e2e           the same metric through the reference-facing call (ma_kantorovich + ma_get_hessian_csr)
                 with pinned HOST buffers: H2D of the weights, D2H of g and of the Hessian CSR.
-  newton        metric 2: full damped-Newton OT solve (ma_ot_solve) wall seconds.
+  newton        metric 2: full damped-Newton OT solve (ma_ot_solve) wall seconds on the same workload; with N > 1 GPUs
+                the solve is collective (NCCL inside the engine, ma_comm_init).
 """
 from __future__ import annotations
 
@@ -39,8 +40,11 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "laguerre_cell_evals_per_s"
-# DRAM bytes of the two roofline kernels per launch at c3 / w = 0, from the ncu capture named in traffic_source
-NCU_TRAFFIC_BYTES = 153.2e6 + 295.5e6 + 259.0e6 + 75.1e6  # k_cells_persist (read + write) + k_seg (read + write)
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, one launch each) of the roofline kernels at c3 / w = 0, from the
+# ncu --set full capture named in TRAFFIC_SOURCE; bench.py cannot measure DRAM traffic itself, so the figure is only quoted
+# for exactly that workload and is refreshed with every capture under profiles/
+NCU_TRAFFIC_BYTES = (149.4e6 + 197.5e6) + (120.8e6 + 74.1e6) + (258.1e6 + 72.3e6)  # k_cells_block<2> + k_cells_block<3> + k_seg
+TRAFFIC_SOURCE = "profiles/r02b_summary.md"
 UNIT = "cell-evals/s"
 
 
@@ -55,9 +59,10 @@ def parse_args():
     ap.add_argument("--weights", default="zero", help="'zero' or a float: random weights of that relative size")
     ap.add_argument("--no-newton", action="store_true", help="skip the metric-2 Newton solve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--newton-workload", default="c2")
-    ap.add_argument("--newton-maxiter", type=int, default=1000)
-    ap.add_argument("--cpu-sample", type=float, default=0.1, help="fraction of the cells the CPU legs evaluate")
+    ap.add_argument("--newton-workload", default=None, help="default: the bench workload itself")
+    ap.add_argument("--newton-maxiter", type=int, default=3000)
+    ap.add_argument("--cpu-sample", type=float, default=0.1, help="fraction of the cells the cpu_baseline leg evaluates")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="time budget of the whole --impl reference run")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (ma_set_option), repeatable")
     return ap.parse_args()
 
@@ -125,8 +130,14 @@ class ClockSampler:
 
 
 def make_case(args, name=None):
-    from tests import common
-    return common.make_case(name or args.workload, args.scale, args.weights)
+    from mongeampere_b200 import workloads
+    return workloads.make_case(name or args.workload, args.scale, args.weights)
+
+
+def bench_config(args, case):
+    """The workload description: identical in the engine's line and in the reference arm's."""
+    return {"workload": workload_name(args), "N": int(case["N"]), "faces": int(case["cfg"]["tri"].shape[0]),
+            "weights": args.weights, "hessian": True}
 
 
 def load_peaks():
@@ -139,66 +150,74 @@ def load_peaks():
 # --------------------------------------------------------------------------------------------------
 # CPU legs (the oracle as the timed baseline; the only place bench.py touches oracle/)
 # --------------------------------------------------------------------------------------------------
-def cpu_sample_case(args):
-    """Bounded sample of the workload: the same density/Dirac distribution at `cpu_sample` of the size
-    (N and the number of faces shrink together, so pieces per cell — the per-cell work — is unchanged)."""
-    from tests import common
-    scale = args.scale * args.cpu_sample
-    return common.make_case(args.workload, scale, args.weights), scale
-
-
-def run_cpu(case, nthreads, mode, repeats=1):
+def oracle_for(case, nthreads):
     from oracle import oracle as O
-    from tests import common
-    orc = common.oracle_for(O, case, nthreads=nthreads)
+    O.build()
+    cfg = case["cfg"]
+    orc = O.Oracle(cfg["vx"], cfg["vy"], cfg["tri"], case["abc"], nthreads=nthreads)
+    orc.set_points(case["X"])
+    return O, orc
+
+
+def time_cells(O, orc, w, lo, hi, repeats=1):
+    """Seconds of one evaluation of the cells [lo, hi) of the problem (neighbour search + overlay + assembly)."""
+    orc.set_cell_range(lo, hi)
     best = None
     for _ in range(repeats):
         t = time.perf_counter()
-        orc.kantorovich(case["w"], mode=mode)
+        orc.kantorovich(w, mode=O.MODE_PER_CELL)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
-    return case["N"] / best, best
+    return best
 
 
-def cpu_baseline(args):
-    from oracle import oracle as O
-    O.build()
-    case, scale = cpu_sample_case(args)
+def cpu_baseline(args, case):
+    """Bounded sample of the SAME problem: the first cpu_sample * N cells (the Diracs are i.i.d., so any index range is a
+    uniform sample of the cells), all host cores; plus one core on a smaller range (the reference is single-threaded)."""
     cores = os.cpu_count() or 1
-    v_all, t_all = run_cpu(case, cores, O.MODE_PER_CELL, repeats=2)
-    v_one, t_one = run_cpu(case, 1, 0, repeats=1)  # the reference's own structure: serial global BFS
-    return {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{args.workload} at scale {scale:g}: {case['N']} Diracs, {case['cfg'].get('n', 2)}^2 grid, "
-                      f"one full evaluation, best of 2 ({t_all:.2f} s)",
-            "single_thread_bfs": {"value": v_one, "seconds": t_one, "cores": 1,
-                                  "note": "serial overlay BFS as in vti.hpp:219-313 (the reference is single-threaded)"}}
+    N = case["N"]
+    O, orc = oracle_for(case, cores)
+    n_all = max(1, int(N * args.cpu_sample))
+    t_all = time_cells(O, orc, case["w"], 0, n_all, repeats=2)
+    orc.nthreads = 1
+    n_one = max(1, min(n_all, 20000))
+    t_one = time_cells(O, orc, case["w"], 0, n_one)
+    return {"value": n_all / t_all, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"cells [0, {n_all}) of the {N}-Dirac problem (same mesh, same points), one evaluation of them on "
+                      f"{cores} threads, best of 2 ({t_all:.2f} s)",
+            "single_thread": {"value": n_one / t_one, "seconds": t_one, "cores": 1, "cells": n_one,
+                              "note": "one thread (the reference is single-threaded: no TBB / OpenMP in its CMakeLists)"}}
 
 
 def main_reference(args, rank, world):
     if rank != 0:
         return
-    from oracle import oracle as O
-    O.build()
-    case, scale = cpu_sample_case(args)
+    case = make_case(args)
+    N = case["N"]
     cores = os.cpu_count() or 1
-    from tests import common
-    orc = common.oracle_for(O, case, nthreads=cores)
+    O, orc = oracle_for(case, cores)
+    # size the per-step sample from a probe so that warmup + steps fit the time budget; the whole problem if it fits
+    n_probe = max(1, min(N, 20000))
+    t_probe = time_cells(O, orc, case["w"], 0, n_probe)
+    per_cell = t_probe / n_probe
+    budget = args.ref_seconds / max(1, args.steps + args.warmup)
+    n_step = int(max(min(N, budget / per_cell), min(N, 1000)))
     for _ in range(args.warmup):
-        orc.kantorovich(case["w"], mode=O.MODE_PER_CELL)
+        time_cells(O, orc, case["w"], 0, n_step)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.kantorovich(case["w"], mode=O.MODE_PER_CELL)
+        time_cells(O, orc, case["w"], 0, n_step)
     dt = time.perf_counter() - t0
-    v = case["N"] * args.steps / dt
-    sample = (f"{args.workload} at scale {scale:g}: {case['N']} Diracs, {case['cfg'].get('n', 2)}^2 grid per step, "
-              f"OpenMP per-cell overlay on {cores} threads")
+    v = n_step * args.steps / dt
+    sample = (f"cells [0, {n_step}) of the {N}-Dirac problem per step ({'the whole problem' if n_step == N else 'a contiguous index range = a uniform sample of the i.i.d. Diracs'}), "
+              f"OpenMP per-cell overlay on {cores} threads, oracle built -O3 -march=native")
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(args), "sample": sample},
+           "config": bench_config(args, case),
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0,
+           "gpu_launches": 0, "cells_per_step": n_step,
            "note": "CPU restatement of the reference path (oracle/ma_oracle.cpp); the reference itself needs "
                    "CGAL/Eigen/Boost/CImg which are not in this image"}
     print(json.dumps(out), flush=True)
@@ -238,7 +257,7 @@ def main_b200(args, rank, world, local_rank):
     case = make_case(args)
     N = case["N"]
     ctx = capi.Context(local_rank)  # raises without the CUDA library / a device: no fallback
-    from tests import common
+    from mongeampere_b200 import workloads as common
     for kv in args.opt:
         k, v = kv.split("=")
         ctx.set_option(k, float(v))
@@ -296,51 +315,80 @@ def main_b200(args, rank, world, local_rank):
     # F_alg counts the reference's work for neighbour lines + clipping + quadrature, which here is
     # K2 (k_cells) + K3 (k_seg on grid meshes, k_pieces otherwise): the roofline is quoted on the pair
     kern_ms = k2_ms + k3_ms
-    kern_name = ("k_cells (K2: Laguerre cells) + " + ("k_seg (K3: boundary-segment integration)" if seg
-                                                       else "k_pieces (K3: clipping + exact integration)"))
+    kern_name = ("k_cells_block / k_cells_warp / k_cells_persist (K2: Laguerre cells) + "
+                 + ("k_seg (K3: boundary integration)" if seg else "k_pieces (K3: clipping + exact integration)"))
     flops_total = sum_over_ranks(flops_local)
     nnz_total = int(sum_over_ranks(nnz_local))
 
     # ---- end to end through the reference-facing call, host (pinned) buffers ----
+    # 1 GPU: ma_kantorovich + ma_get_hessian_csr (g and the CSR of h in the caller's ordering).  N GPUs: every rank
+    # uploads the weights, evaluates its Morton tile and reads back ITS rows (ma_get_tile_rows: masses + CSR rows with
+    # caller column indices), so the transfers shrink with the tile.
     w_h = torch.from_numpy(np.ascontiguousarray(case["w"])).pin_memory().numpy()
-    g_h = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
     cap = int(nnz_local * 1.05) + 64
-    ptr_h = torch.empty(N + 1, dtype=torch.int32).pin_memory().numpy()
     col_h = torch.empty(cap, dtype=torch.int32).pin_memory().numpy()
     val_h = torch.empty(cap, dtype=torch.float64).pin_memory().numpy()
+    if world == 1:
+        g_h = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
+        ptr_h = torch.empty(N + 1, dtype=torch.int32).pin_memory().numpy()
+
+        def e2e_step():
+            f, nnz = ctx.kantorovich_into(w_h, g_h, ptr_h, col_h, val_h)
+            return nnz, 8 * N + 4 * (N + 1) + 12 * nnz
+        e2e_call = "ma_kantorovich + ma_get_hessian_csr, pinned host buffers"
+    else:
+        g_h = torch.empty(n_local, dtype=torch.float64).pin_memory().numpy()
+        ptr_h = torch.empty(n_local + 1, dtype=torch.int32).pin_memory().numpy()
+        ids_h = torch.empty(n_local, dtype=torch.int32).pin_memory().numpy()
+
+        def e2e_step():
+            ctx.set_weights(w_h)
+            ctx.evaluate(True)
+            nt, nnz = ctx.tile_rows_into(ids_h, g_h, ptr_h, col_h, val_h)
+            return nnz, 4 * nt + 8 * nt + 4 * (nt + 1) + 12 * nnz
+        e2e_call = "per rank: ma_set_weights + ma_evaluate + ma_get_tile_rows (its tile's masses and Hessian rows), pinned host buffers"
     for _ in range(max(1, args.warmup)):
-        ctx.kantorovich_into(w_h, g_h, ptr_h, col_h, val_h)
+        e2e_step()
     e2e_steps = max(3, args.steps // 2)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        f_e2e, nnz_e2e = ctx.kantorovich_into(w_h, g_h, ptr_h, col_h, val_h)
+        nnz_e2e, d2h = e2e_step()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     h2d = 8 * N
-    d2h = 8 * N + 4 * (N + 1) + 12 * nnz_e2e
+    d2h = int(sum_over_ranks(d2h)) if world > 1 else d2h
+    h2d = h2d * world
     mass_sum = sum_over_ranks(float(g_h.sum()))
 
-    # ---- metric 2: full Newton solve (single GPU engine; the multi-GPU solve is not built yet) ----
+    # ---- metric 2: full damped-Newton solve of the same workload (collective over all ranks when N > 1) ----
     newton = None
-    if not args.no_newton and rank == 0:
+    if not args.no_newton:
+        nname = args.newton_workload or args.workload
+        ncase = case if nname == args.workload else make_case(args, nname)
         nctx = capi.Context(local_rank)
-        ncase = make_case(args, args.newton_workload)
         common.load_engine(nctx, ncase)
+        if world > 1:
+            ids = [capi.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            nctx.comm_init(rank, world, ids[0])
         nu = np.full(ncase["N"], nctx.total_mass / ncase["N"])
+        barrier()
         t0 = time.perf_counter()
-        # the reference's default maxiter = 100 stops this solve at |g| = 9e-4 (the damped Newton of
-        # optimal_transport.hpp crawls from w = 0 on such a density); 1000 lets it reach eps_g = 1e-7
+        # (the reference's default maxiter = 100 stops such solves early: the damped Newton of optimal_transport.hpp
+        # crawls from w = 0 on a non-uniform density; the bench lets it reach eps_g = 1e-7)
         _, st, rc = nctx.ot_solve(nu, eps_g=1e-7, maxiter=args.newton_maxiter, verbose=False)
-        newton = {"workload": args.newton_workload, "N": ncase["N"], "seconds": time.perf_counter() - t0,
+        barrier()
+        newton = {"workload": nname, "N": ncase["N"], "seconds": max_over_ranks(time.perf_counter() - t0),
                   "status": capi.STATUS_NAMES[rc], "niter": st["niter"], "neval": st["neval"],
                   "cg_iters": st["cg_iters"], "final_norm": st["final_norm"], "eps_g": 1e-7,
-                  "maxiter": args.newton_maxiter, "gpus": 1}
+                  "maxiter": args.newton_maxiter, "gpus": world,
+                  "linear_solver": "PCG, quadtree-aggregation multigrid V(1,1) preconditioner, rtol 1e-12"}
         nctx.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args)
+        cpu = cpu_baseline(args, case)
 
     if rank == 0:
         peaks = load_peaks()
@@ -350,12 +398,11 @@ def main_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "N": N, "faces": int(case["cfg"]["tri"].shape[0]),
-                       "weights": args.weights, "hessian": True, "nnz": nnz_total,
-                       "partition": f"{world} Morton tile(s) of Diracs, points/weights/mesh replicated",
-                       "l2": "no flush: one evaluation moves ~1 GB through DRAM (ncu: K2 0.45 GB, K3 0.33 GB, K4 0.26 GB of "
-                             "per-cell polygons / slot tables / CSR), several times the 126 MB L2; only the 33.5 MB of vertex "
-                             "densities can stay L2-resident from step to step"},
+            "config": bench_config(args, case),
+            "details": {"nnz": nnz_total, "partition": f"{world} Morton tile(s) of Diracs, points/weights/mesh replicated",
+                        "l2": "no flush: one evaluation streams ~0.9 GB through DRAM (per-cell polygons, slot tables, CSR), "
+                              "several times the 126 MB L2; only the vertex densities (2 x 33.5 MB) can stay L2-resident "
+                              "from step to step"},
             "stages_ms": {"prep_K1": stage["prep"] / args.steps, "cells_K2": k2_ms, "pieces_K3": k3_ms,
                           "reduce_scan": stage["reduce"] / args.steps, "csr_K4": k4_ms},
             "roofline": {"bound": "fp64", "kernel": kern_name,
@@ -364,8 +411,8 @@ def main_b200(args, rank, world, local_rank):
                          "frac": (flops_local / (kern_ms * 1e-3)) / fp64_peak if kern_ms > 0 else None,
                          "traffic": NCU_TRAFFIC_BYTES if (seg and world == 1 and args.workload == "c3" and args.scale == 1.0
                                                           and args.weights == "zero") else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_cells_persist + k_seg, one "
-                                           "launch each, ncu --set full capture of this workload (profiles/r01n_summary.md)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the K2 block kernels + k_seg, one "
+                                           "launch each, ncu --set full capture of this workload (" + TRAFFIC_SOURCE + ")",
                          "peak_source": "DFMA probe in this run (MEASURED_PEAKS.json has no fp64 figure)",
                          "algorithmic_flops_per_launch": flops_local,
                          "flops_per_cell": flops_total / N},
@@ -376,7 +423,7 @@ def main_b200(args, rank, world, local_rank):
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
             "e2e": {"value": N / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "call": "ma_kantorovich + ma_get_hessian_csr, pinned host buffers"},
+                    "call": e2e_call},
             "gpu_launches": launches,
             "clocks": clk,
             "check": {"mass_sum": mass_sum, "total_mass": ctx.total_mass,

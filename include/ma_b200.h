@@ -145,6 +145,13 @@ int ma_evaluate(ma_ctx *ctx, int with_hessian);
  * mass_sum and mass_min are the tile's partial values, to be combined by the caller (sum, sum, min). */
 int ma_set_partition(ma_ctx *ctx, int rank, int nranks);
 
+/* The rows this context owns after ma_evaluate / ma_kantorovich (all rows without a partition), in the engine's
+ * internal (Morton) order: row k is Dirac row_ids[k] of the caller's ordering, g[k] its mass, and
+ * col[rowptr[k] .. rowptr[k+1]) / val its Hessian row with CALLER column indices (ordered along the Morton curve, not
+ * ascending).  What a multi-GPU caller reads back per rank: the transfer shrinks with the tile instead of staying at N.
+ * Call with all array pointers NULL to get the sizes. */
+int ma_get_tile_rows(ma_ctx *ctx, int *ntile, int *nnz_tile, int *row_ids, double *g, int *rowptr, int *col, double *val);
+
 /* Multi-GPU with NCCL inside the engine (one process per GPU).  ma_comm_unique_id fills 128
  * bytes on ONE rank (ncclGetUniqueId); the caller ships them to the other ranks by any means (MPI, a file,
  * torch.distributed, a socket) and every rank calls ma_comm_init, which creates the NCCL communicator on the context's

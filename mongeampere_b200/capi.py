@@ -29,7 +29,7 @@ SYMBOLS = (
     "ma_set_weights", "ma_evaluate",
     "ma_get_adjacency", "ma_set_profiling", "ma_get_timings", "ma_set_stats", "ma_get_counters", "ma_flush_l2",
     "ma_measure_fp64_peak", "ma_set_option", "ma_get_info", "ma_set_partition", "ma_timer_start", "ma_timer_stop",
-    "ma_comm_unique_id", "ma_comm_init", "ma_comm_destroy",
+    "ma_comm_unique_id", "ma_comm_init", "ma_comm_destroy", "ma_get_tile_rows",
 )
 
 
@@ -93,6 +93,7 @@ def load_library(path: str | None = None):
     L.ma_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.ma_timer_start.argtypes = [vp]
     L.ma_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.ma_get_tile_rows.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp]
     L.ma_comm_unique_id.argtypes = [vp]
     L.ma_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.ma_comm_destroy.argtypes = [vp]
@@ -307,6 +308,26 @@ class Context:
 
     def set_partition(self, rank, nranks):
         self._ck(self.L.ma_set_partition(self.h, rank, nranks))
+
+    def tile_sizes(self):
+        nt, nz = C.c_int(), C.c_int()
+        self._ck(self.L.ma_get_tile_rows(self.h, C.byref(nt), C.byref(nz), None, None, None, None, None))
+        return nt.value, nz.value
+
+    def tile_rows_into(self, row_ids, g, rowptr, col, val):
+        """ma_get_tile_rows into caller-owned (e.g. pinned) buffers -> (ntile, nnz_tile)."""
+        nt, nz = C.c_int(), C.c_int()
+        self._ck(self.L.ma_get_tile_rows(self.h, C.byref(nt), C.byref(nz), _ptr(row_ids), _ptr(g), _ptr(rowptr), _ptr(col), _ptr(val)))
+        return nt.value, nz.value
+
+    def tile_rows(self):
+        """-> row_ids, g, H_tile (csr_matrix of shape (ntile, N), caller column indices)."""
+        import scipy.sparse as sp
+        nt, nz = self.tile_sizes()
+        ids = np.empty(nt, np.int32); g = np.empty(nt); ptr = np.empty(nt + 1, np.int32)
+        col = np.empty(max(nz, 1), np.int32); val = np.empty(max(nz, 1))
+        self.tile_rows_into(ids, g, ptr, col, val)
+        return ids, g, sp.csr_matrix((val[:nz], col[:nz], ptr), shape=(nt, self.N))
 
     def comm_init(self, rank, nranks, unique_id: bytes):
         """NCCL communicator of the ranks sharing this problem (ma_comm_init); unique_id from comm_unique_id() on one rank."""

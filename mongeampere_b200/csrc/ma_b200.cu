@@ -1251,6 +1251,42 @@ extern "C" int ma_get_hessian_csr(ma_ctx *c, int *rowptr, int *col, double *val)
   return MA_OK;
 }
 
+// dst[q] = perm[src[q]]
+__global__ void k_map_ids(const int *__restrict__ src, const int *__restrict__ perm, int n, int *__restrict__ dst) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) dst[q] = perm[src[q]];
+}
+
+extern "C" int ma_get_tile_rows(ma_ctx *c, int *ntile, int *nnz_tile, int *row_ids, double *g, int *rowptr, int *col, double *val) {
+  NEED_CTX();
+  if (!c->have_eval) return fail(c, MA_INVALID, "no evaluation yet");
+  const int lo = (int)((long long)c->N * c->part_rank / c->part_n), hi = (int)((long long)c->N * (c->part_rank + 1) / c->part_n);
+  const int nt = hi - lo;
+  if (ntile) *ntile = nt;
+  if (nnz_tile) *nnz_tile = c->have_hessian ? c->nnz : 0;  // a partitioned context stores exactly its tile's rows
+  if (!row_ids && !g && !rowptr && !col && !val) return MA_OK;  // size query
+  if (row_ids) CK(cudaMemcpyAsync(row_ids, c->perm.as<int>() + lo, (size_t)nt * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (g) CK(cudaMemcpyAsync(g, c->mass.as<double>() + lo, (size_t)nt * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (rowptr || col || val) {
+    if (!c->have_hessian) return fail(c, MA_INVALID, "no Hessian: evaluate with the Hessian first");
+    // rowptr[lo] = 0 on a partitioned context (the rows before the tile are empty): the device array is the answer as it is
+    if (rowptr) CK(cudaMemcpyAsync(rowptr, c->rowptr.as<int>() + lo, ((size_t)nt + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (col) {
+      CKR(ensure(c, c->ccol, (size_t)std::max(c->nnz, 1) * 4));
+      k_map_ids<<<cdiv(std::max(c->nnz, 1), 256), 256, 0, c->stream>>>(c->col.as<int>(), c->perm.as<int>(), c->nnz, c->ccol.as<int>());
+      c->launches++;
+      CK(cudaMemcpyAsync(col, c->ccol.p, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (val) CK(cudaMemcpyAsync(val, c->val.p, (size_t)c->nnz * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  if (rowptr && rowptr[0] != 0) {  // part_n == 1 with lo == 0 never gets here; defensive for future layouts
+    const int b = rowptr[0];
+    for (int k = 0; k <= nt; ++k) rowptr[k] -= b;
+  }
+  return MA_OK;
+}
+
 extern "C" int ma_get_adjacency(ma_ctx *c, int *ptr, int *idx, int capacity) {
   NEED_CTX();
   if (!c->have_eval) return fail(c, MA_INVALID, "no evaluation yet");

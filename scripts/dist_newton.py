@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 from mongeampere_b200 import capi
 from mongeampere_b200.distributed import ContextTile, DistributedKantorovich
-from tests import common
+from mongeampere_b200 import workloads as common
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)

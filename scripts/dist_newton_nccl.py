@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from mongeampere_b200 import capi
-from tests import common
+from mongeampere_b200 import workloads as common
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 dist.init_process_group("gloo")

@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mongeampere_b200 import capi
-from tests import common
+from mongeampere_b200 import workloads as common
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 nev = int(sys.argv[3]) if len(sys.argv) > 3 else 3

@@ -4,7 +4,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mongeampere_b200 import capi
-from tests import common
+from mongeampere_b200 import workloads as common
 
 out = {}
 only = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
