@@ -882,14 +882,17 @@ template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
   // cost 0.6 ms of pure latency, profiles/r02b), CellSearch takes whatever remains.
   const int nblk2 = std::max(1, std::min(nblk, c->sm_count * 8));
   k_cells_block<2, 3, MAXV, NT, POLY><<<nblk2, NT, sm, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
-  k_cells_warp<5, POLY><<<c->sm_count * 4, 128, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, c->hard1.as<int>(), cnt + 2);
+  k_cells_warp<5, POLY><<<c->sm_count * 16, 128, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, c->hard1.as<int>(), cnt + 2);
+  // CellSearch: a small grid for the leftovers of the list (a handful of cells, if any) ...
+  k_cells_persist<MAXV, NT, POLY><<<c->sm_count * 2, NT, sm, c->stream>>>(p, 1, c->hard1.as<int>(), cnt + 2);
+  // ... and a grid sized for the whole tile that only works when the weights are graded (the regime of the Newton iterates)
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cells_persist<MAXV, NT, POLY>, NT, sm));
   const long long warps_target = (long long)c->sm_count * std::max(per_sm, 1) * (NT / 32) * c->persist_waves;
-  const int nwarps = (int)std::max<long long>(1, std::min<long long>(warps_target, cdiv(ncells, c->persist_min_chunk)));
-  k_cells_persist<MAXV, NT, POLY><<<cdiv(nwarps, NT / 32), NT, sm, c->stream>>>(p, c->persist_min_chunk, c->hard1.as<int>(), cnt + 2);
-  c->launches += 1;
-  c->launches += 3;
+  const int chunk = (int)std::max<long long>(c->persist_min_chunk, (ncells + warps_target - 1) / warps_target);
+  const int nwarps = std::max(1, cdiv(ncells, chunk));
+  k_cells_persist<MAXV, NT, POLY><<<cdiv(nwarps, NT / 32), NT, sm, c->stream>>>(p, chunk, nullptr, cnt + 2);
+  c->launches += 5;
   CK(cudaGetLastError());
   return MA_OK;
 }

@@ -542,9 +542,10 @@ template <int MAXV, int NT> constexpr size_t cells_smem_bytes() { return (size_t
 #ifndef MA_K2_MINBLOCKS
 #define MA_K2_MINBLOCKS 5  // 5 blocks of 128 threads per SM: <= 102 registers, 41 KB of polygons each
 #endif
-// `list` != null: the kernel handles the cells list[0 .. *list_n) left over by the block kernels (k_cells_block)
-// — unless the weights are graded (then the block kernels did nothing and it takes the whole tile) — and sizes
-// its chunks itself from the device-side count (the host never reads it).
+// `list` != null: the kernel handles the cells list[0 .. *list_n) left over by the block kernels (k_cells_block) and
+// sizes its chunks itself from the device-side count (the host never reads it); it returns at once when the weights are
+// graded.  list == null with list_n != null is the complementary launch: the whole tile, but only when the weights are
+// graded (the block kernels then did nothing).
 template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K2_MINBLOCKS : 1)) k_cells_persist(Params p, int chunk, const int *__restrict__ list, const int *__restrict__ list_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
@@ -556,10 +557,14 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
   const long long warp_global = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
   int lo = p.cell_lo, hi = p.cell_hi;
   if (list) {
-    if (weights_graded(p)) list = nullptr;
-    else { lo = 0; hi = *list_n; }
+    // the cells the block kernels left over; with graded weights those kernels did nothing and the launch with
+    // list == null && list_n != null (a full grid, sized for the whole tile) does the work instead
+    if (weights_graded(p)) return;
+    lo = 0; hi = *list_n;
     const long long nwarps = (long long)gridDim.x * (NT / 32);
-    chunk = (int)max((long long)chunk, ((long long)(hi - lo) + nwarps - 1) / nwarps);
+    chunk = (int)max(1ll, ((long long)(hi - lo) + nwarps - 1) / nwarps);
+  } else if (list_n) {
+    if (!weights_graded(p)) return;
   }
   long long first = (long long)lo + warp_global * chunk;
   int next = (int)(first < hi ? first : hi);                       // warp-uniform
