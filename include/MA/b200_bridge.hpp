@@ -135,19 +135,20 @@ class Engine {
   void invalidate() { mesh_key = points_key = 0; }
 
   template <class T, class Functions> void set_mesh(const T &t, const Functions &fs) {
-    // fingerprint: identity + size of both containers + a strided sample of the functions
+    // Fingerprint of the CONTENT: every face's three vertex coordinates and its function's three coefficients (the
+    // reference API is stateless, so a caller may rebuild a triangulation at the same address or edit densities in place:
+    // addresses and samples prove nothing).  One pass over the faces, cheap next to the extraction + upload it saves.
     uint64_t key = fnv(&t, 0);
-    const void *pt = &t, *pf = &fs;
     size_t nf = fs.size();
-    key = fnv(&pt, sizeof pt, key); key = fnv(&pf, sizeof pf, key); key = fnv(&nf, sizeof nf, key);
+    key = fnv(&nf, sizeof nf, key);
     {
       typedef typename std::decay<decltype(t.finite_faces_begin()->vertex(0)->point())>::type Pt;
-      size_t step = nf / 257 + 1, k = 0;
-      for (typename Functions::const_iterator it = fs.begin(); it != fs.end(); ++it, ++k)
-        if (k % step == 0) {
-          double s[3] = {it->second(Pt(0, 0)), it->second(Pt(1, 0)), it->second(Pt(0, 1))};
-          key = fnv(s, sizeof s, key);
-        }
+      for (typename Functions::const_iterator it = fs.begin(); it != fs.end(); ++it) {
+        double s[9];
+        for (int k = 0; k < 3; ++k) { s[2 * k] = it->first->vertex(k)->point().x(); s[2 * k + 1] = it->first->vertex(k)->point().y(); }
+        s[6] = it->second(Pt(0, 0)); s[7] = it->second(Pt(1, 0)); s[8] = it->second(Pt(0, 1));
+        key = fnv(s, sizeof s, key);
+      }
     }
     if (key == mesh_key && !std::getenv("MA_B200_NOCACHE")) return;
     MeshArrays M;

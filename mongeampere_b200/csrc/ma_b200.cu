@@ -1049,51 +1049,56 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     if (seg) CKR(run_cells<true>(c, p));
     else CKR(run_cells<false>(c, p));
     c->aborted = false;
-    if (c->abort_on_empty) {
-      // line-search trial: an empty cell means min m = 0 < eps0, the point is rejected whatever the
-      // rest of the evaluation says (optimal_transport.hpp:167), so stop here
-      CKR(dist_sync_flags(c));  // (multi-GPU: a cell of ANY tile)
-      CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 8, cudaMemcpyDeviceToHost, c->stream));  // flags[0], flags[1]
-      CK(cudaStreamSynchronize(c->stream));
-      if (c->hs->flags & (FLAG_CELL_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
-        // a cell outgrew this capacity class: the abort flag (if any) says nothing yet, escalate first
-        if (c->kmax >= 64) {
-          c->capacity_hit = true;
-          return fail(c, MA_INVALID, "polygon capacity exceeded even at kmax=64 (flags=%d)", c->hs->flags);
-        }
-        c->kmax *= 2;
-        continue;
-      }
-      if (c->hs->abort_) {
-        c->aborted = true;
-        c->mass_min = 0.0;
-        invalidate_eval(c);
-        if (c->trace) fprintf(stderr, "[ma] eval aborted after K2: a cell is empty\n");
-        return MA_OK;
-      }
-    }
+    // (line-search trials: once K2 has found an empty cell the point is rejected whatever the rest says,
+    // optimal_transport.hpp:167 — K3 / K4 then return at once on the device-side flag, the host learns it at the one
+    // synchronisation below)
     if (seg) CKR(launch_seg_kmax<SEG_MODE>(c, p));
     else CKR(launch_pieces_mode<MODE>(c, p));
     if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
+    const bool hess = (MODE == MODE_KANTOROVICH) && with_hessian;
     if (MODE == MODE_KANTOROVICH) {
-      if (with_hessian) CKR(scan_i32(c, c->rowcnt.as<int>(), c->rowptr.as<int>(), c->N));
+      // row pointers of this context's rows only (rowptr[lo] = 0 ... rowptr[hi] = nnz); rows of other tiles have none
+      if (hess) CKR(scan_i32(c, c->rowcnt.as<int>() + lo, c->rowptr.as<int>() + lo, nloc));
       CKR(reduce4(c, c->fcell.as<double>() + lo, nullptr, nloc, c->red_out.as<double>()));
       CKR(reduce4(c, c->mass.as<double>() + lo, nullptr, nloc, c->red_out.as<double>() + 4));
     }
-    CKR(dist_sync_flags(c));
+    if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
+    auto csr_fill = [&]() -> int {
+      const int cap = (int)std::min<size_t>(c->col.cap / 4, c->val.cap / 8);
+      const int *skip = c->abort_on_empty ? c->flags.as<int>() + 1 : nullptr;
+      switch (c->kmax) {
+        case 16: k_csr_fill<16><<<std::max(1, cdiv(nloc, 32 * csr_wpb<16>())), 32 * csr_wpb<16>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(), cap, skip); break;
+        case 32: k_csr_fill<32><<<std::max(1, cdiv(nloc, 32 * csr_wpb<32>())), 32 * csr_wpb<32>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(), cap, skip); break;
+        default: k_csr_fill<64><<<std::max(1, cdiv(nloc, 32 * csr_wpb<64>())), 32 * csr_wpb<64>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>(), cap, skip); break;
+      }
+      c->launches++;
+      CK(cudaGetLastError());
+      return MA_OK;
+    };
+    if (hess) {
+      // K4 is launched BEFORE the host knows nnz (no synchronisation in the middle of an evaluation): col / val keep the
+      // size of the largest Hessian seen so far plus headroom (8 entries per row to start with), the kernel drops what
+      // does not fit and the fill is repeated in the rare case that it did not
+      const size_t want = std::max<size_t>((size_t)8 * nloc, 1024);
+      if (c->col.cap / 4 < want || c->val.cap / 8 < want) { CKR(ensure(c, c->col, want * 4)); CKR(ensure(c, c->val, want * 8)); }
+      CKR(csr_fill());
+      if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CSR + 1], c->stream));
+    }
+    CKR(dist_sync_flags(c));  // multi-GPU: every rank learns about an overflow / an empty cell of ANY tile
     if (MODE == MODE_KANTOROVICH) CKR(dist_reduce_eval(c));  // f, sum m, min m over all tiles
     c->hs->flags = 0; c->hs->nnz = 0;
     CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 12, cudaMemcpyDeviceToHost, c->stream));  // flags, abort, K2 exact-stage count
     if (MODE == MODE_KANTOROVICH) {
       CK(cudaMemcpyAsync(c->hs->red, c->red_out.p, sizeof c->hs->red, cudaMemcpyDeviceToHost, c->stream));
-      if (with_hessian)
-        CK(cudaMemcpyAsync(&c->hs->nnz, c->rowptr.as<int>() + c->N, 4, cudaMemcpyDeviceToHost, c->stream));
+      if (hess) CK(cudaMemcpyAsync(&c->hs->nnz, c->rowptr.as<int>() + p.cell_hi, 4, cudaMemcpyDeviceToHost, c->stream));
     }
+    if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_COUNT + 1], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     const int h_flags = c->hs->flags, h_nnz = c->hs->nnz;
     c->cell_fallbacks = c->hs->cell_fallbacks;
     const double *red = c->hs->red;
     if (h_flags & (FLAG_CELL_OVERFLOW | FLAG_PIECE_OVERFLOW | FLAG_KMAX_OVERFLOW)) {
+      // (before the abort flag: a cell that outgrew its capacity class is not an empty cell)
       if (c->trace) fprintf(stderr, "[ma] eval kmax=%d overflow flags=%d\n", c->kmax, h_flags);
       if (c->kmax >= 64) {
         c->capacity_hit = true;
@@ -1103,28 +1108,28 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       continue;
     }
     if (h_flags & FLAG_STACK_OVERFLOW) return fail(c, MA_INVALID, "quadtree stack overflow");
+    if (c->abort_on_empty && c->hs->abort_) {
+      c->aborted = true;
+      c->mass_min = 0.0;
+      invalidate_eval(c);
+      if (c->trace) fprintf(stderr, "[ma] eval aborted after K2: a cell is empty\n");
+      return MA_OK;
+    }
     if (MODE == MODE_KANTOROVICH) {
       c->fval = red[0];
       c->mass_sum = red[4];
       c->mass_min = red[6];
-      if (with_hessian) {
+      if (hess) {
         c->nnz = h_nnz;
-        CKR(ensure(c, c->col, (size_t)std::max(h_nnz, 1) * 4, 1.3));
-        CKR(ensure(c, c->val, (size_t)std::max(h_nnz, 1) * 8, 1.3));
-        if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
-        switch (c->kmax) {
-          case 16: k_csr_fill<16><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, 32 * csr_wpb<16>())), 32 * csr_wpb<16>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
-          case 32: k_csr_fill<32><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, 32 * csr_wpb<32>())), 32 * csr_wpb<32>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
-          default: k_csr_fill<64><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, 32 * csr_wpb<64>())), 32 * csr_wpb<64>(), 0, c->stream>>>(p.cell_lo, p.cell_hi, p.nbr, p.hslot, p.touched, c->rowptr.as<int>(), c->col.as<int>(), c->val.as<double>()); break;
+        if ((size_t)h_nnz > std::min<size_t>(c->col.cap / 4, c->val.cap / 8)) {  // did not fit: grow and fill again
+          CKR(ensure(c, c->col, (size_t)h_nnz * 4, 1.3));
+          CKR(ensure(c, c->val, (size_t)h_nnz * 8, 1.3));
+          CKR(csr_fill());
+          CK(cudaStreamSynchronize(c->stream));
         }
-        c->launches++;
-        CK(cudaGetLastError());
-        if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CSR + 1], c->stream));
       }
     }
     if (c->profiling) {
-      CK(cudaEventRecord(c->ev[MA_T_COUNT + 1], c->stream));
-      CK(cudaStreamSynchronize(c->stream));
       for (auto &t : c->t_ms) t = 0;
       cudaEventElapsedTime(&c->t_ms[MA_T_TOTAL], c->ev[0], c->ev[MA_T_COUNT + 1]);
       cudaEventElapsedTime(&c->t_ms[MA_T_PREP], c->ev[0], c->ev[MA_T_PREP + 1]);
@@ -1223,7 +1228,7 @@ extern "C" int ma_get_hessian_csr(ma_ctx *c, int *rowptr, int *col, double *val)
   CKR(ensure(c, c->cptr, (size_t)(N + 1) * 4));
   CKR(ensure(c, c->ccol, (size_t)std::max(nnz_all, 1) * 4));
   CKR(ensure(c, c->cval, (size_t)std::max(nnz_all, 1) * 8));
-  k_rowcnt_to_caller<<<cdiv(N, 256), 256, 0, c->stream>>>(rowptr_s, c->pos.as<int>(), N,
+  k_rowcnt_to_caller<<<cdiv(N, 256), 256, 0, c->stream>>>(c->rowcnt.as<int>(), c->pos.as<int>(), N,
                                                           c->scratch_i.as<int>());
   CKR(scan_i32(c, c->scratch_i.as<int>(), c->cptr.as<int>(), N));
   c->launches += 1;

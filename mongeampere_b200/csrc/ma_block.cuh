@@ -127,58 +127,48 @@ MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv
   BlockRuns<R0, R> runs;
   runs.build(p, cbx, cby, active);
   const int T = runs.total();
-  // Every lane walks ITS candidate list with its own cursor t.  A search step takes a lane to its next candidate that
-  // can reach the polygon at all (up to 3 hopeless ones are skipped on the way) and tests it; a lane whose candidate
-  // cuts HOLDS it.  The warp clips when enough lanes hold (same vote as CellSearch: n_hold * clip_a >= n_search * clip_b),
-  // so a clip — the expensive, poorly converged part — runs for many lanes at once instead of in every iteration.
-  int t = 0;
-  bool hold = false;
-  for (;;) {
-    for (;;) {
-      const bool searching = active && S.phase == 0 && !hold && t < T;
-      const int n_search = MA_WARP_COUNT(searching), n_hold = MA_WARP_COUNT(hold);
-      if (n_search == 0 || n_hold * p.clip_a >= n_search * p.clip_b) break;
-      if (searching) {
-        int pos = 0, jj = -1;
-        double Dx = 0, Dy = 0, dd2 = 0, dw = 0, c = 0;
-        bool test = false;
-#pragma unroll 1
-        for (int skip = 0; skip < 3 && t < T && !test && S.phase == 0; ++skip) {
-          pos = runs.position(t);
-          ++t;
-          MA_COUNT(0);
-          Dx = p.xr[pos] - S.xi; Dy = p.yr[pos] - S.yi;
-          const double wj = p.wr[pos];
-          dd2 = Dx * Dx + Dy * Dy;
-          dw = S.wi - wj;
-          c = 0.5 * (dd2 + dw);
-          if (dd2 == 0.0) {  // itself, or a coincident site: the heavier (then the earlier) one keeps the cell
-            jj = p.rm2s[pos];
-            if (jj != S.i && (wj > S.wi || (wj == S.wi && jj < S.i))) { S.n = 0; S.phase = 2; }
-          } else {
-            // the bisector misses the disk of radius sqrt(R2) around y_i that contains the polygon => it cannot cut
-            test = !(c >= 0.0 && c * c >= S.R2 * dd2 * (1.0 + 1e-9));
-          }
-        }
-        if (test && S.phase == 0) {
-          MA_COUNT(1);
-          const int n = S.n;
-          jj = p.rm2s[pos];
-          double r2_seen;
-          const unsigned long long in = S.sign_mask(p, P, jj, Dx, Dy, c, dd2, dw, r2_seen);
-          S.R2 = r2_seen;  // radius of the polygon as it is now (a clip leaves it as an upper bound)
-          if (in == 0ull) { S.n = 0; S.phase = 2; }
-          else if (in != lowmask64(n)) { S.jc = jj; S.cDx = Dx; S.cDy = Dy; S.cc = c; S.cin = in; hold = true; }
-        }
+  // All lanes step through their lists together, candidate t of every lane in iteration t.  (Per-lane cursors with
+  // vote-scheduled clips — the CellSearch scheme — were measured on this kernel: 7 % fewer instructions, 15 of 32 lanes
+  // instead of 14, but 18 % SLOWER: the candidate loads then issue lane by lane behind data-dependent branches and the
+  // kernel is bound by their latency at 20 warps per SM, profiles/r02g.)
+  const int Tmax = MA_WARP_MAX_INT(T);
+  // (the next candidate's coordinates are fetched one iteration ahead: the loads then fly while this one is tested / clipped)
+  int npos = (active && 0 < T) ? runs.position(0) : 0;
+  double nxr = p.xr[npos], nyr = p.yr[npos], nwr = p.wr[npos];
+  for (int t = 0; t < Tmax; ++t) {
+    const bool act = active && S.phase == 0 && t < T;
+    const int pos = npos;
+    const double Dx = nxr - S.xi, Dy = nyr - S.yi, wj = nwr;
+    npos = (active && t + 1 < T) ? runs.position(t + 1) : 0;
+    nxr = p.xr[npos]; nyr = p.yr[npos]; nwr = p.wr[npos];
+    const double dd2 = Dx * Dx + Dy * Dy;
+    const double dw = S.wi - wj;
+    const double c = 0.5 * (dd2 + dw);
+    MA_COUNT(0);
+    if (act && dd2 == 0.0) {  // itself, or a coincident site: the heavier (then the earlier) one keeps the cell
+      const int jj = p.rm2s[pos];
+      if (jj != S.i && (wj > S.wi || (wj == S.wi && jj < S.i))) { S.n = 0; S.phase = 2; }
+    }
+    // the bisector misses the disk of radius sqrt(R2) around y_i that contains the polygon => it cannot cut
+    const bool test = act && S.phase == 0 && dd2 > 0.0 && !(c >= 0.0 && c * c >= S.R2 * dd2 * (1.0 + 1e-9));
+    bool cut = false;
+    if (MA_WARP_ANY(test)) {
+      if (test) {
+        MA_COUNT(1);
+        const int n = S.n;
+        const int jj = p.rm2s[pos];
+        double r2_seen;
+        const unsigned long long in = S.sign_mask(p, P, jj, Dx, Dy, c, dd2, dw, r2_seen);
+        S.R2 = r2_seen;  // radius of the polygon as it is now (a clip below leaves it as an upper bound)
+        if (in == 0ull) { S.n = 0; S.phase = 2; }
+        else if (in != lowmask64(n)) { S.jc = jj; S.cDx = Dx; S.cDy = Dy; S.cc = c; S.cin = in; cut = true; }
       }
       MA_WARP_SYNC();
+      if (MA_WARP_ANY(cut)) {
+        if (cut) S.template clip<false>(p, P, maxv);  // overflow: status = FLAG_CELL_OVERFLOW, n = 0, phase = 2
+        MA_WARP_SYNC();
+      }
     }
-    if (!MA_WARP_ANY(hold)) break;
-    if (hold) {
-      S.template clip<false>(p, P, maxv);  // overflow: status = FLAG_CELL_OVERFLOW, n = 0, phase = 2
-      hold = false;
-    }
-    MA_WARP_SYNC();
   }
   // ---- certificate ----
   if (S.phase == 0) certified = block_certified<R>(p, S, P, cbx, cby);

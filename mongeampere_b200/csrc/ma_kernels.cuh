@@ -798,6 +798,7 @@ template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT, (MAX
   double *se = sy + MAXV * NT;  // per-edge accumulators of the Hessian's edge integrals (kantorovich mode)
   const int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
   if (i >= p.cell_hi) return;
+  if (p.abort_on_empty && *p.abort_flag) return;  // line-search trial already rejected by K2 (an empty cell)
   PolyRef<NT, false> P{sx + threadIdx.x, sy + threadIdx.x, nullptr};  // the tags stay in global memory
   const int n = p.poly_n[i];
   for (int k = 0; k < n; ++k) {
@@ -841,6 +842,7 @@ template <int KMAX, int MAXV, int MODE> __global__ void __launch_bounds__(PIECES
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = p.cell_lo + blockIdx.x * PIECES_WPB + warp;
   if (i >= p.cell_hi) return;  // warp-uniform; no block-level barrier below
+  if (p.abort_on_empty && *p.abort_flag) return;  // line-search trial already rejected by K2 (an empty cell)
   unsigned char *base = smem_raw + (size_t)warp * pieces_warp_bytes<KMAX, MAXV>();
   double *d = reinterpret_cast<double *>(base);
   CellTable T;
@@ -953,7 +955,10 @@ template <int KMAX>
 __global__ void __launch_bounds__(csr_wpb<KMAX>() * 32) k_csr_fill(int row_lo, int N, const int *__restrict__ nbr, const double *__restrict__ hslot,
                                                           const unsigned long long *__restrict__ touched,
                                                           const int *__restrict__ rowptr, int *__restrict__ col,
-                                                          double *__restrict__ val) {
+                                                          double *__restrict__ val, int cap, const int *__restrict__ skip_flag) {
+  // cap: entries col / val can hold (the kernel is launched before the host knows nnz; what does not fit is dropped and
+  // the host repeats the fill with larger arrays); skip_flag: the evaluation was abandoned (empty cell in a trial)
+  if (skip_flag && *skip_flag) return;
   constexpr int LD = KMAX + 1, CSR_WPB = csr_wpb<KMAX>();
   __shared__ double sh_h[CSR_WPB][32 * LD];
   __shared__ int sh_j[CSR_WPB][32 * LD];
@@ -1007,7 +1012,7 @@ __global__ void __launch_bounds__(csr_wpb<KMAX>() * 32) k_csr_fill(int row_lo, i
     for (int rr = 0; rr < 32; ++rr) r += (__shfl_sync(0xffffffffu, my_start, rr) <= e) ? 1 : 0;
     r = max(r, 0);
     const int rs = __shfl_sync(0xffffffffu, my_start, r);
-    if (e < total) {
+    if (e < total && o0 + e < cap) {
       col[o0 + e] = J[r * LD + (e - rs)];
       val[o0 + e] = H[r * LD + (e - rs)];
     }
@@ -1020,10 +1025,10 @@ __global__ void k_scatter_to_caller(const double *__restrict__ src_sorted, const
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) dst_caller[perm[k]] = src_sorted[k];
 }
-__global__ void k_rowcnt_to_caller(const int *__restrict__ rowptr_sorted, const int *__restrict__ pos, int n,
+__global__ void k_rowcnt_to_caller(const int *__restrict__ rowcnt_sorted, const int *__restrict__ pos, int n,
                                    int *__restrict__ cnt_caller) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { int k = pos[i]; cnt_caller[i] = rowptr_sorted[k + 1] - rowptr_sorted[k]; }
+  if (i < n) cnt_caller[i] = rowcnt_sorted[pos[i]];
 }
 // caller rows [r0, n)
 __global__ void k_csr_to_caller(int r0, int n, const int *__restrict__ rowptr_s, const int *__restrict__ col_s,
@@ -1033,7 +1038,9 @@ __global__ void k_csr_to_caller(int r0, int n, const int *__restrict__ rowptr_s,
   int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int k = pos[i];
-  int s = rowptr_s[k], e = rowptr_s[k + 1], o = rowptr_c[i];
+  const int cnt = rowptr_c[i + 1] - rowptr_c[i];  // rows of other tiles are empty here (and their rowptr_s is not defined)
+  if (cnt == 0) return;
+  int s = rowptr_s[k], e = s + cnt, o = rowptr_c[i];
   for (int q = s; q < e; ++q) {  // insertion sort by caller column while copying
     int cj = perm[col_s[q]];
     double vj = val_s[q];
