@@ -111,9 +111,9 @@ int ma_ot_solve(ma_ctx *ctx, const double *nu, double *w, int have_initial, doub
  * voronoi_triangulation_intersection(t, dt, out)  voronoi_triangulation_intersection.hpp:315-343:
  * enumerates every non-empty piece.  Two-call protocol: ma_pieces_build computes them on the device
  * and returns the counts, ma_pieces_get copies them out: piece p belongs to cell[p] and face[p] and
- * has vertices xy[2*ptr[p] .. 2*ptr[p+1]) (CCW); tag[k] is the Laguerre neighbour across the edge
- * starting at vertex k, or -1 for an edge of the source triangle (the EDGE_DT / EDGE_T tags of
- * vti.hpp:54-96). */
+ * has vertices xy[2*ptr[p] .. 2*ptr[p+1]) (CCW); tag[k] names the edge starting at vertex k: the Laguerre
+ * neighbour across it (>= 0: an EDGE_DT of vti.hpp:54-96), or -1 / -2 / -3 for the edge (0,1) / (1,2) / (2,0)
+ * of the source triangle tri[3 f ..] (an EDGE_T). */
 int ma_pieces_build(ma_ctx *ctx, const double *weights, int *npieces, int *nvertices);
 int ma_pieces_get(ma_ctx *ctx, int *cell, int *face, int *ptr, int *tag, double *xy);
 

@@ -1429,7 +1429,7 @@ extern "C" int ma_pieces_get(ma_ctx *c, int *cell, int *face, int *ptr, int *tag
     if (xy) CK(cudaMemcpy(xy, c->pc_xy.p, (size_t)nv * 16, cudaMemcpyDeviceToHost));
   }
   if (cell) for (int k = 0; k < np; ++k) cell[k] = perm[hc[k]];
-  if (tag) for (int k = 0; k < nv; ++k) tag[k] = ht[k] >= 0 ? perm[ht[k]] : -1;
+  if (tag) for (int k = 0; k < nv; ++k) tag[k] = ht[k] >= 0 ? perm[ht[k]] : ht[k];
   return MA_OK;
 }
 

@@ -695,7 +695,7 @@ MA_DEV void lane_face(const Params &p, int i, const PolyRef<NT> &P, int maxv, co
       p.pc_xy[2 * (size_t)(vi + k)] = P.X(k) + xi;
       p.pc_xy[2 * (size_t)(vi + k) + 1] = P.Y(k) + yi;
       int tg = P.T(k);
-      p.pc_tag[vi + k] = tg >= 0 ? T.J[tg] : -1;
+      p.pc_tag[vi + k] = tg >= 0 ? T.J[tg] : tg;  // -1, -2, -3: edge (0,1), (1,2), (2,0) of the face
     }
     acc.npieces++; acc.nverts += n;
     return;

@@ -638,7 +638,7 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
 // quadtree walk with supporting planes is the path for that regime).
 // ================================================================================================
 #ifndef MA_K2B_MINBLOCKS
-#define MA_K2B_MINBLOCKS 5
+#define MA_K2B_MINBLOCKS 4  // measured: 128 registers (no spills) at 16 warps per SM beat 96 registers at 20 (1.43 vs 1.54 ms of K2 at c3)
 #endif
 // R0 >= 0: the pass continues from the polygon the pass of radius R0 stored and looks only at the bins beyond that block.
 template <int R0, int R, int MAXV, int NT, bool POLY>

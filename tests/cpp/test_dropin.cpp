@@ -105,6 +105,37 @@ int main(int argc, const char **argv) {
       ++pieces;
     });
     printf("area_sum %.17g\npieces %zu\ncell_area0 %.17g\n", area, pieces, cell_area[0]);
+    // the raw traversal (vti.hpp:219-313): symbolic polygons, EDGE_T / EDGE_DT tagged edges.  Rebuild the points from the
+    // tags the way kantorovich.hpp:95-102 does (vertex i = line(R[i]) ∩ line(R[i+1])) and compare the areas.
+    typedef MA::Pgon_edge_t<T::Vertex_handle, MA::lite::Weighted_sites::Vertex_handle> Edge;
+    double raw_area = 0;
+    size_t raw_pieces = 0, n_edge_t = 0, n_edge_dt = 0;
+    MA::voronoi_triangulation_intersection_raw(t, dt, [&](const std::vector<Edge> &R, T::Face_handle, MA::lite::Weighted_sites::Vertex_handle v) {
+      const size_t n = R.size();
+      std::vector<double> la(n), lb(n), lc(n);  // a x + b y = c
+      for (size_t i = 0; i < n; ++i) {
+        if (R[i].type == Edge::EDGE_T) {
+          const Point p = R[i].edge_t.first->point(), q = R[i].edge_t.second->point();
+          la[i] = p.y() - q.y(); lb[i] = q.x() - p.x(); lc[i] = la[i] * p.x() + lb[i] * p.y();
+          ++n_edge_t;
+        } else {
+          const double xv = R[i].edge_dt.first->point().x(), yv = R[i].edge_dt.first->point().y(), wv = R[i].edge_dt.first->point().weight();
+          const double xw = R[i].edge_dt.second->point().x(), yw = R[i].edge_dt.second->point().y(), ww = R[i].edge_dt.second->point().weight();
+          if (R[i].edge_dt.first != v) { printf("raw: EDGE_DT does not start at the cell's site\n"); }
+          la[i] = 2 * (xw - xv); lb[i] = 2 * (yw - yv); lc[i] = xw * xw + yw * yw - xv * xv - yv * yv + wv - ww;
+          ++n_edge_dt;
+        }
+      }
+      MA::lite::Polygon poly;
+      for (size_t i = 0; i < n; ++i) {
+        const size_t j = (i + 1) % n;
+        const double det = la[i] * lb[j] - la[j] * lb[i];
+        poly.push_back(Point((lc[i] * lb[j] - lc[j] * lb[i]) / det, (la[i] * lc[j] - la[j] * lc[i]) / det));
+      }
+      raw_area += poly.area();
+      ++raw_pieces;
+    });
+    printf("raw_area_sum %.17g\nraw_pieces %zu\nraw_edge_t %zu\nraw_edge_dt %zu\n", raw_area, raw_pieces, n_edge_t, n_edge_dt);
   }
   // ---- voronoi_polygon_intersection (voronoi_polygon_intersection.hpp:153-188; tests/test_power.cpp:43-50) ----
   {

@@ -91,6 +91,10 @@ def test_cpp_dropin_matches_c_abi(gpu_ctx):
     # tests/test_voronoi_tri.cpp:67: the pieces tile the domain; cell 0's pieces have the cell's area
     assert abs(out["area_sum"][0] - 4.0) <= 1e-11
     assert out["pieces"][0] >= N
+    # voronoi_triangulation_intersection_raw (vti.hpp:219-313): the symbolic polygons rebuilt from their EDGE_T / EDGE_DT
+    # tags are the same pieces
+    assert out["raw_pieces"][0] == out["pieces"][0] and out["raw_edge_t"][0] > 0 and out["raw_edge_dt"][0] > 0
+    assert abs(out["raw_area_sum"][0] - 4.0) <= 1e-9
     # tests/test_power.cpp:51: the cells clipped to a convex polygon tile it
     assert abs(out["cells_area_sum"][0] - out["pentagon_area"][0]) <= 1e-12
 

@@ -160,7 +160,8 @@ def test_pieces_match_oracle(gpu_ctx, oracle_mod):
         b = key1[kf]
         A, B = xy0[p0[a]:p0[a + 1]], xy1[p1[b]:p1[b + 1]]
         assert len(A) == len(B)
-        ta, tb = list(t0[p0[a]:p0[a + 1]]), list(t1[p1[b]:p1[b + 1]])
+        # (the engine names the triangle edge of an EDGE_T, -1 / -2 / -3; the oracle only says "mesh edge", -1)
+        ta, tb = list(t0[p0[a]:p0[a + 1]]), [int(v) if v >= 0 else -1 for v in t1[p1[b]:p1[b + 1]]]
         # same cyclic sequence of (tag, vertex) up to rotation
         rot = [r for r in range(len(A)) if tb[r:] + tb[:r] == ta]
         assert rot, (kf, ta, tb)
