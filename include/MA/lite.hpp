@@ -12,6 +12,11 @@
 #include <cassert>
 #include <cmath>
 #include <cstddef>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace MA {
@@ -282,6 +287,42 @@ class Image {
  public:
   Image() : w(0), h(0) {}
   Image(int width, int height) : w(width), h(height), px((size_t)width * height, 0.0) {}
+  // from a PGM file (P2 ascii / P5 binary, 8 or 16 bit), the way the reference's drivers build a CImg<double> from a
+  // path (tests/test_opttransport.cpp:45-49); values are kept as stored (0..maxval), (i, j) = (column, row from the top)
+  explicit Image(const char *path) : w(0), h(0) {
+    std::FILE *f = std::fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("MA::lite::Image: cannot open ") + path);
+    auto token = [&](std::string &t) {
+      t.clear();
+      int ch;
+      for (;;) {  // skip white space and # comments
+        ch = std::fgetc(f);
+        if (ch == '#') { while (ch != '\n' && ch != EOF) ch = std::fgetc(f); continue; }
+        if (ch == EOF || !std::isspace(ch)) break;
+      }
+      while (ch != EOF && !std::isspace(ch)) { t.push_back((char)ch); ch = std::fgetc(f); }
+      return !t.empty();
+    };
+    std::string magic, t;
+    long maxval = 0;
+    bool ok = token(magic) && (magic == "P2" || magic == "P5") && token(t);
+    if (ok) { w = std::atoi(t.c_str()); ok = token(t); }
+    if (ok) { h = std::atoi(t.c_str()); ok = token(t); }
+    if (ok) { maxval = std::atol(t.c_str()); ok = w > 0 && h > 0 && maxval > 0 && maxval < 65536; }
+    if (ok) {
+      px.resize((size_t)w * h);
+      if (magic == "P2") {
+        for (size_t k = 0; k < px.size() && ok; ++k) { ok = token(t); px[k] = ok ? std::atof(t.c_str()) : 0.0; }
+      } else {  // exactly one white-space byte was consumed after maxval by token()
+        const size_t bps = maxval < 256 ? 1 : 2;
+        std::vector<unsigned char> raw(px.size() * bps);
+        ok = std::fread(raw.data(), 1, raw.size(), f) == raw.size();
+        for (size_t k = 0; k < px.size() && ok; ++k) px[k] = bps == 1 ? (double)raw[k] : (double)((raw[2 * k] << 8) | raw[2 * k + 1]);
+      }
+    }
+    std::fclose(f);
+    if (!ok) throw std::runtime_error(std::string("MA::lite::Image: not a valid PGM file: ") + path);
+  }
   int width() const { return w; }
   int height() const { return h; }
   Image &fill(double v) { std::fill(px.begin(), px.end(), v); return *this; }

@@ -1,12 +1,15 @@
 // MA/voronoi_polygon_intersection.hpp — drop-in for the reference's
 // include/MA/voronoi_polygon_intersection.hpp:153-188:
 //   Polygon MA::voronoi_polygon_intersection(P, dt, v)
-// = (Voronoi / Laguerre cell of vertex v of dt) ∩ P for a CONVEX polygon P given counter-clockwise
-// (tests/test_voronoi.cpp:41-48 and tests/test_power.cpp:43-50 call it for every vertex with P = the
-// unit square and sum the areas).  The cells come from the GPU neighbour search (ma_cells_build /
-// ma_cells_get: cell ∩ bounding box of P); clipping a convex cell by the convex P is then a
-// Sutherland–Hodgman pass per side of P on the host.  All cells of one (P, dt) pair are computed by
-// the first call and cached, so the driver's loop over the vertices costs one GPU evaluation.
+// = (Voronoi / Laguerre cell of vertex v of dt) ∩ P for a simple polygon P given counter-clockwise, convex or not
+// (tests/test_voronoi.cpp:41-48 and tests/test_power.cpp:43-50 call it for every vertex with P = the unit square and
+// sum the areas; tests/test_voronoi_ad.cpp uses a non-convex cross).  dt may be weighted (regular triangulation) or
+// not (Delaunay: the overloads of predicates.hpp:38-44,63-70,89-98 — the weight is simply absent).  The cells come
+// from the GPU neighbour search (ma_cells_build / ma_cells_get: cell ∩ bounding box of P); as the reference's
+// Pgon_intersector does (voronoi_polygon_intersection.hpp:27-151), P is then clipped by the half-planes of the cell, one
+// Sutherland–Hodgman pass per cell edge on the host; for a non-convex P the result may contain zero-width bridges,
+// its area is exact.  The result has the caller's Polygon type (:153-158).  All cells of one (P, dt) pair are computed
+// by the first call and cached, so the driver's loop over the vertices costs one GPU evaluation.
 #ifndef MA_VORONOI_POLYGON_INTERSECTION_HPP
 #define MA_VORONOI_POLYGON_INTERSECTION_HPP
 
@@ -28,7 +31,7 @@ inline CellCache &cell_cache() {
 }
 }  // namespace details
 
-template <class Polygon, class DT, class VH> lite::Polygon voronoi_polygon_intersection(const Polygon &P, const DT &dt, const VH &v) {
+template <class Polygon, class DT, class VH> Polygon voronoi_polygon_intersection(const Polygon &P, const DT &dt, const VH &v) {
   typedef decltype(dt.finite_vertices_begin()) VIt;
   details::CellCache &cc = details::cell_cache();
   // fingerprint of (P, dt): every coordinate and weight
@@ -63,23 +66,27 @@ template <class Polygon, class DT, class VH> lite::Polygon voronoi_polygon_inter
   }
   std::map<const void *, size_t>::const_iterator it = cc.index.find((const void *)&*v);
   if (it == cc.index.end()) throw std::runtime_error("MA::voronoi_polygon_intersection: v is not a vertex of dt");
-  std::vector<double> qx, qy;
-  for (int k = cc.ptr[it->second]; k < cc.ptr[it->second + 1]; ++k) { qx.push_back(cc.xy[2 * (size_t)k]); qy.push_back(cc.xy[2 * (size_t)k + 1]); }
-  // clip by every side of P (inside = left of the directed side)
-  for (size_t s = 0; s < px.size() && !qx.empty(); ++s) {
-    const double ax = px[s], ay = py[s], bx = px[(s + 1) % px.size()], by = py[(s + 1) % px.size()];
+  // the cell (convex, counter-clockwise, already inside the bounding box of P) ...
+  std::vector<double> cx, cy;
+  for (int k = cc.ptr[it->second]; k < cc.ptr[it->second + 1]; ++k) { cx.push_back(cc.xy[2 * (size_t)k]); cy.push_back(cc.xy[2 * (size_t)k + 1]); }
+  // ... clips P: one pass per cell edge, inside = left of the directed edge
+  std::vector<double> qx(px), qy(py);
+  if (cx.size() < 3) { qx.clear(); qy.clear(); }
+  for (size_t s = 0; s < cx.size() && !qx.empty(); ++s) {
+    const double ax = cx[s], ay = cy[s], bx = cx[(s + 1) % cx.size()], by = cy[(s + 1) % cx.size()];
     std::vector<double> ox, oy;
     const size_t n = qx.size();
     for (size_t k = 0; k < n; ++k) {
-      const double cx = qx[k], cy = qy[k], dx = qx[(k + 1) % n], dy = qy[(k + 1) % n];
-      const double sc = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax), sd = (bx - ax) * (dy - ay) - (by - ay) * (dx - ax);
-      if (sc >= 0) { ox.push_back(cx); oy.push_back(cy); }
-      if ((sc >= 0) != (sd >= 0)) { const double t = sc / (sc - sd); ox.push_back(cx + t * (dx - cx)); oy.push_back(cy + t * (dy - cy)); }
+      const double ux = qx[k], uy = qy[k], vx = qx[(k + 1) % n], vy = qy[(k + 1) % n];
+      const double sc = (bx - ax) * (uy - ay) - (by - ay) * (ux - ax), sd = (bx - ax) * (vy - ay) - (by - ay) * (vx - ax);
+      if (sc >= 0) { ox.push_back(ux); oy.push_back(uy); }
+      if ((sc >= 0) != (sd >= 0)) { const double t = sc / (sc - sd); ox.push_back(ux + t * (vx - ux)); oy.push_back(uy + t * (vy - uy)); }
     }
     qx.swap(ox); qy.swap(oy);
   }
-  lite::Polygon R;
-  for (size_t k = 0; k < qx.size(); ++k) R.push_back(lite::Point(qx[k], qy[k]));
+  typedef typename std::decay<decltype(P[0])>::type PointT;
+  Polygon R;
+  for (size_t k = 0; k < qx.size(); ++k) R.push_back(PointT(qx[k], qy[k]));
   return R;
 }
 

@@ -117,6 +117,13 @@ int ma_ot_solve(ma_ctx *ctx, const double *nu, double *w, int have_initial, doub
 int ma_pieces_build(ma_ctx *ctx, const double *weights, int *npieces, int *nvertices);
 int ma_pieces_get(ma_ctx *ctx, int *cell, int *face, int *ptr, int *tag, double *xy);
 
+/* draw_laguerre_diagram(densityT, densityF, X, weights, colors, x0, y0, x1, y1, w, h, put_pixel)  rasterization.hpp:512-547:
+ * every piece (cell ∩ face) drawn into a w x h image over the box [x0,x1] x [y0,y1] with exact pixel coverage;
+ * image[y * w + x] = sum over the pieces of coverage(piece, pixel) * (mean density at the piece's vertices) * colors[cell]
+ * (what the reference's put_pixel callback accumulates).  colors[N] in the caller's ordering; image is overwritten. */
+int ma_draw_laguerre_diagram(ma_ctx *ctx, const double *weights, const double *colors, double x0, double y0, double x1, double y1,
+                             int w, int h, double *image);
+
 /* ---- Laguerre cells as polygons ---------------------------------------------------------------
  * The power cell of every Dirac clipped to the bounding box of the source mesh, i.e. what
  * voronoi_polygon_intersection(P, dt, v) (voronoi_polygon_intersection.hpp:153-188) returns for P = that box

@@ -29,7 +29,7 @@ SYMBOLS = (
     "ma_set_weights", "ma_evaluate",
     "ma_get_adjacency", "ma_set_profiling", "ma_get_timings", "ma_set_stats", "ma_get_counters", "ma_flush_l2",
     "ma_measure_fp64_peak", "ma_set_option", "ma_get_info", "ma_set_partition", "ma_timer_start", "ma_timer_stop",
-    "ma_comm_unique_id", "ma_comm_init", "ma_comm_destroy", "ma_get_tile_rows",
+    "ma_comm_unique_id", "ma_comm_init", "ma_comm_destroy", "ma_get_tile_rows", "ma_draw_laguerre_diagram",
 )
 
 
@@ -94,6 +94,7 @@ def load_library(path: str | None = None):
     L.ma_timer_start.argtypes = [vp]
     L.ma_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.ma_get_tile_rows.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp]
+    L.ma_draw_laguerre_diagram.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp]
     L.ma_comm_unique_id.argtypes = [vp]
     L.ma_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.ma_comm_destroy.argtypes = [vp]
@@ -285,6 +286,13 @@ class Context:
         tag = np.empty(max(V, 1), np.int32)
         self._ck(self.L.ma_cells_get(self.h, _ptr(ptr), _ptr(xy), _ptr(tag)))
         return ptr, xy[:V], tag[:V]
+
+    def draw_laguerre_diagram(self, w, colors, box, width, height):
+        """draw_laguerre_diagram (rasterization.hpp:512-547) -> image[height, width] (row y, column x)."""
+        w, colors = _f64(w), _f64(colors)
+        img = np.zeros((height, width))
+        self._ck(self.L.ma_draw_laguerre_diagram(self.h, _ptr(w), _ptr(colors), box[0], box[1], box[2], box[3], width, height, _ptr(img)))
+        return img
 
     def has_empty_cell(self, w):
         """True iff some Dirac of this context's tile has an empty Laguerre cell at weights w (K1 + K2 only, stops at

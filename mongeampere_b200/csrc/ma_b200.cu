@@ -1433,6 +1433,34 @@ extern "C" int ma_pieces_get(ma_ctx *c, int *cell, int *face, int *ptr, int *tag
   return MA_OK;
 }
 
+// draw_laguerre_diagram (rasterization.hpp:512-547)
+extern "C" int ma_draw_laguerre_diagram(ma_ctx *c, const double *weights, const double *colors, double x0, double y0, double x1,
+                                        double y1, int w, int h, double *image) {
+  NEED_CTX();
+  if (!weights || !colors || !image || w < 1 || h < 1 || !(x1 > x0) || !(y1 > y0))
+    return fail(c, MA_INVALID, "ma_draw_laguerre_diagram: bad arguments");
+  int np = 0, nv = 0;
+  CKR(ma_pieces_build(c, weights, &np, &nv));
+  Buf b_col, b_img;
+  int rc = MA_OK;
+  do {
+    if ((rc = upload(c, b_col, colors, (size_t)c->N * 8))) break;
+    if ((rc = ensure(c, b_img, (size_t)w * h * 8))) break;
+    if (cudaMemsetAsync(b_img.p, 0, (size_t)w * h * 8, c->stream) != cudaSuccess) { rc = fail(c, MA_CUDA_ERROR, "memset failed"); break; }
+    if (np > 0)
+      k_raster_pieces<<<cdiv(np, 128), 128, 0, c->stream>>>(np, c->pc_cell.as<int>(), c->pc_face.as<int>(), c->pc_ptr.as<int>(),
+                                                           c->pc_xy.as<double>(), c->abc.as<double>(), c->perm.as<int>(),
+                                                           b_col.as<double>(), x0, y0, (double)w / (x1 - x0), (double)h / (y1 - y0), w, h,
+                                                           b_img.as<double>());
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(image, b_img.p, (size_t)w * h * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess)
+      rc = fail(c, MA_CUDA_ERROR, "rasterisation failed");
+  } while (0);
+  release(b_col); release(b_img);
+  return rc;
+}
+
 // =============================================================================================
 // Laguerre cells (cell ∩ mesh bounding box) as polygons: K1 + K2 only
 // =============================================================================================

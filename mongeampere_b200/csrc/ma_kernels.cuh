@@ -1085,6 +1085,71 @@ __global__ void k_cellpoly_fill(int n, const int *__restrict__ poly_n, const dou
   }
 }
 
+// ================================================================================================
+// Rasterised Laguerre diagram (rasterization.hpp:403-547, draw_laguerre_diagram): every piece (cell ∩ face) is drawn
+// into a w x h image with EXACT pixel coverage, value = coverage * (mean density at the piece's vertices) * colour of
+// the cell.  One thread per piece: the piece, mapped to pixel coordinates, is clipped to every pixel square of its
+// bounding box (four Sutherland–Hodgman passes) and the area added to the pixel.  (The reference reaches the same
+// coverage with a DDA over the edges plus a per-pixel case analysis, after nudging near-integer coordinates by 1e-6;
+// clipping needs neither.)
+// ================================================================================================
+constexpr int RAST_MAXV = 48;
+__global__ void __launch_bounds__(128) k_raster_pieces(int np, const int *__restrict__ pc_cell, const int *__restrict__ pc_face,
+                                                       const int *__restrict__ pc_ptr, const double *__restrict__ pc_xy,
+                                                       const double *__restrict__ abc, const int *__restrict__ perm,
+                                                       const double *__restrict__ colors, double x0, double y0, double sx,
+                                                       double sy, int w, int h, double *__restrict__ image) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  const int v0 = pc_ptr[p], n = min(pc_ptr[p + 1] - v0, RAST_MAXV - 4);  // (pieces have at most 40 vertices)
+  if (n < 3) return;
+  const int f = pc_face[p];
+  const double a = abc[3 * (size_t)f], b = abc[3 * (size_t)f + 1], c0 = abc[3 * (size_t)f + 2];
+  double X[RAST_MAXV], Y[RAST_MAXV], U[RAST_MAXV], V[RAST_MAXV], U2[RAST_MAXV], V2[RAST_MAXV];
+  double ff = 0.0, bx0 = 1e300, bx1 = -1e300, by0 = 1e300, by1 = -1e300;
+  for (int k = 0; k < n; ++k) {
+    const double gx = pc_xy[2 * (size_t)(v0 + k)], gy = pc_xy[2 * (size_t)(v0 + k) + 1];
+    ff += a * gx + b * gy + c0;
+    X[k] = (gx - x0) * sx; Y[k] = (gy - y0) * sy;
+    bx0 = fmin(bx0, X[k]); bx1 = fmax(bx1, X[k]); by0 = fmin(by0, Y[k]); by1 = fmax(by1, Y[k]);
+  }
+  const double value = ff / (double)n * colors[perm[pc_cell[p]]];
+  const int ix0 = max((int)floor(bx0), 0), ix1 = min((int)floor(bx1), w - 1);
+  const int iy0 = max((int)floor(by0), 0), iy1 = min((int)floor(by1), h - 1);
+  for (int iy = iy0; iy <= iy1; ++iy)
+    for (int ix = ix0; ix <= ix1; ++ix) {
+      // clip (X, Y)[0..n) to [ix, ix+1] x [iy, iy+1]: keep s >= 0 for s = x - ix, ix+1 - x, y - iy, iy+1 - y
+      int m = n;
+      const double *sxp = X, *syp = Y;
+      double *dxp = U, *dyp = V;
+      for (int side = 0; side < 4 && m > 0; ++side) {
+        const double A = side == 0 ? 1.0 : (side == 1 ? -1.0 : 0.0), B = side == 2 ? 1.0 : (side == 3 ? -1.0 : 0.0);
+        const double C = side == 0 ? -(double)ix : (side == 1 ? (double)(ix + 1) : (side == 2 ? -(double)iy : (double)(iy + 1)));
+        int q = 0;
+        for (int k = 0; k < m; ++k) {
+          const int kk = (k + 1 == m) ? 0 : k + 1;
+          const double s0 = A * sxp[k] + B * syp[k] + C, s1 = A * sxp[kk] + B * syp[kk] + C;
+          if (s0 >= 0.0) { dxp[q] = sxp[k]; dyp[q] = syp[k]; ++q; }
+          if ((s0 >= 0.0) != (s1 >= 0.0)) {
+            const double t = s0 / (s0 - s1);
+            dxp[q] = sxp[k] + t * (sxp[kk] - sxp[k]); dyp[q] = syp[k] + t * (syp[kk] - syp[k]); ++q;
+          }
+        }
+        m = q;
+        sxp = dxp; syp = dyp;  // ping-pong between the two scratch polygons
+        dxp = (dxp == U) ? U2 : U; dyp = (dyp == V) ? V2 : V;
+      }
+      if (m < 3) continue;
+      double area = 0.0;
+      for (int k = 0; k < m; ++k) {
+        const int kk = (k + 1 == m) ? 0 : k + 1;
+        area += sxp[k] * syp[kk] - sxp[kk] * syp[k];
+      }
+      area *= 0.5;
+      if (area > 0.0) atomicAdd(&image[(size_t)iy * w + ix], area * value);
+    }
+}
+
 __global__ void k_fill_bytes(unsigned long long *p, size_t n, unsigned long long v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -214,3 +214,54 @@ def config(name: str, scale: float = 1.0):
         X = uniform_points(N, 7, (-1 / 1.1, -1 / 1.1), (1 / 1.1, 1 / 1.1))
         return dict(kind="grid", n=2, m=2, vx=vx, vy=vy, tri=grid_triangles(2, 2), rho=rho, X=X)
     raise KeyError(name)
+
+
+# ------------------------------------------------------------------------------------------------
+# image files / irregular meshes
+# ------------------------------------------------------------------------------------------------
+def read_pgm(path):
+    """PGM (P2 ascii / P5 binary, 8 or 16 bit) -> image[i, j] = pixel (column i, row j from the top), the CImg(i, j)
+    indexing that image_vertex_density / ma_set_image expect (the reference's drivers load their density with
+    cimg_library::CImg<double>(path), tests/test_opttransport.cpp:45-49; CImg itself is not available here)."""
+    import re
+    with open(path, "rb") as fh:
+        data = fh.read()
+    m = re.match(rb"(P[25])\s+(?:#[^\n]*\n\s*)*(\d+)\s+(?:#[^\n]*\n\s*)*(\d+)\s+(?:#[^\n]*\n\s*)*(\d+)\s", data)
+    if not m:
+        raise ValueError(f"{path}: not a PGM file")
+    w, h, maxval = int(m.group(2)), int(m.group(3)), int(m.group(4))
+    if m.group(1) == b"P2":
+        px = np.array(data[m.end():].split(), dtype=np.float64)
+    else:
+        dt = np.dtype(">u2") if maxval > 255 else np.uint8
+        px = np.frombuffer(data, dtype=dt, count=w * h, offset=m.end()).astype(np.float64)
+    if px.size != w * h:
+        raise ValueError(f"{path}: truncated PGM file")
+    return np.ascontiguousarray(px.reshape(h, w).T)
+
+
+def l_shaped_mesh(nv: int = 400, seed: int = 0):
+    """An irregular triangulation of the NON-convex domain [-1,1]^2 minus (0,1]x(0,1] (Delaunay of random interior
+    points + points on the boundary, triangles of the removed quadrant dropped) with a random PL density:
+    (vx, vy, tri CCW, rho) in the format of ma_set_mesh_pl / Triangulation_incremental_builder_2."""
+    from scipy.spatial import Delaunay
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = np.linspace(-1, 1, 17)
+    s = np.linspace(0, 1, 9)
+    bnd = np.r_[np.c_[t, -np.ones_like(t)], np.c_[-np.ones_like(t), t], np.c_[t[t <= 0], np.ones((t <= 0).sum())],
+                np.c_[np.ones((t <= 0).sum()), t[t <= 0]], np.c_[s, np.zeros_like(s)], np.c_[np.zeros_like(s), s]]
+    P = rng.uniform(-1, 1, (3 * nv, 2))
+    P = P[~((P[:, 0] > 0.02) & (P[:, 1] > 0.02))]
+    P = P[~((P[:, 0] > -0.02) & (P[:, 1] > -0.02) & ((P[:, 0] < 0.02) | (P[:, 1] < 0.02)))][:nv]
+    pts = np.unique(np.r_[bnd, P].round(12), axis=0)
+    d = Delaunay(pts)
+    tri = d.simplices
+    c = pts[tri].mean(axis=1)
+    tri = tri[~((c[:, 0] > 0) & (c[:, 1] > 0))]
+    a, b, cc = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
+    area2 = (b[:, 0] - a[:, 0]) * (cc[:, 1] - a[:, 1]) - (cc[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
+    tri = tri[np.abs(area2) > 1e-12]
+    area2 = area2[np.abs(area2) > 1e-12]
+    tri = np.where(area2[:, None] > 0, tri, tri[:, ::-1]).astype(np.int32)
+    rho = 0.3 + rng.random(len(pts)) + np.exp(-((pts[:, 0] + 0.4) ** 2 + (pts[:, 1] + 0.3) ** 2) / 0.08)
+    return np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1]), np.ascontiguousarray(tri), rho

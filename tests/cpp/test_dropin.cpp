@@ -8,6 +8,7 @@
 #include <MA/lloyd.hpp>
 #include <MA/optimal_transport.hpp>
 #include <MA/voronoi_polygon_intersection.hpp>
+#include <MA/rasterization.hpp>
 #include <MA/voronoi_triangulation_intersection.hpp>
 
 #include <cstdio>
@@ -137,6 +138,17 @@ int main(int argc, const char **argv) {
     });
     printf("raw_area_sum %.17g\nraw_pieces %zu\nraw_edge_t %zu\nraw_edge_dt %zu\n", raw_area, raw_pieces, n_edge_t, n_edge_dt);
   }
+  // ---- draw_laguerre_diagram (rasterization.hpp:512-547): colour 1 everywhere => the image integrates the density ----
+  {
+    MA::lite::Vector colors = MA::lite::Vector::Constant(N, 1.0);
+    const size_t W = 37, Hh = 29;
+    std::vector<double> img(W * Hh, 0.0);
+    MA::draw_laguerre_diagram(t, functions, X, res, colors, -1.0, -1.0, 1.0, 1.0, W, Hh,
+                              [&](int x, int y, double v) { img[(size_t)y * W + x] += v; });
+    double s = 0;
+    for (double v : img) s += v;
+    printf("raster_sum %.17g\n", s * (2.0 / W) * (2.0 / Hh));  // pixel area in domain units
+  }
   // ---- voronoi_polygon_intersection (voronoi_polygon_intersection.hpp:153-188; tests/test_power.cpp:43-50) ----
   {
     MA::lite::Weighted_sites dt(X, res);
@@ -147,6 +159,15 @@ int main(int argc, const char **argv) {
     for (MA::lite::Weighted_sites::Finite_vertices_iterator v = dt.finite_vertices_begin(); v != dt.finite_vertices_end(); ++v)
       area += MA::voronoi_polygon_intersection(P, dt, v).area();
     printf("pentagon_area %.17g\ncells_area_sum %.17g\n", P.area(), area);
+    // a NON-convex polygon (the cross of tests/test_voronoi_ad.cpp, scaled into the domain): the cells ∩ cross tile it
+    MA::lite::Polygon C;
+    const double a = 0.3, b = 0.9;
+    const double cxs[12] = {-a, a, a, b, b, a, a, -a, -a, -b, -b, -a}, cys[12] = {-b, -b, -a, -a, a, a, b, b, a, a, -a, -a};
+    for (int k = 0; k < 12; ++k) C.push_back(Point(cxs[k], cys[k]));
+    double carea = 0;
+    for (MA::lite::Weighted_sites::Finite_vertices_iterator v = dt.finite_vertices_begin(); v != dt.finite_vertices_end(); ++v)
+      carea += MA::voronoi_polygon_intersection(C, dt, v).area();
+    printf("cross_area %.17g\ncross_cells_area_sum %.17g\n", C.area(), carea);
   }
   return 0;
 }

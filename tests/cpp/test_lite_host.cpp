@@ -51,6 +51,24 @@ int main() {
   MA::lite::Matrix X(4, 2);
   X(3, 1) = 7;
   CHECK(X.data()[4 + 3] == 7);  // column-major like Eigen::MatrixXd
+  // PGM reader (what stands in for CImg<double>(path), tests/test_opttransport.cpp:45-49): ascii and binary
+  {
+    const char *pa = "/tmp/ma_lite_test_ascii.pgm", *pb = "/tmp/ma_lite_test_bin.pgm";
+    FILE *fa = fopen(pa, "w");
+    fprintf(fa, "P2\n# a comment\n3 2\n255\n0 10 20\n30 40 255\n");
+    fclose(fa);
+    FILE *fb = fopen(pb, "wb");
+    fprintf(fb, "P5\n3 2\n255\n");
+    const unsigned char raw[6] = {0, 10, 20, 30, 40, 255};
+    fwrite(raw, 1, 6, fb);
+    fclose(fb);
+    MA::lite::Image ia(pa), ib(pb);
+    CHECK(ia.width() == 3 && ia.height() == 2 && ib.width() == 3 && ib.height() == 2);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) CHECK(ia(i, j) == raw[j * 3 + i] && ib(i, j) == raw[j * 3 + i]);
+    bool threw = false;
+    try { MA::lite::Image bad("/tmp/ma_lite_no_such_file.pgm"); } catch (const std::runtime_error &) { threw = true; }
+    CHECK(threw);
+  }
   printf("ok\n");
   return 0;
 }

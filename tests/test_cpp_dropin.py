@@ -95,8 +95,13 @@ def test_cpp_dropin_matches_c_abi(gpu_ctx):
     # tags are the same pieces
     assert out["raw_pieces"][0] == out["pieces"][0] and out["raw_edge_t"][0] > 0 and out["raw_edge_dt"][0] > 0
     assert abs(out["raw_area_sum"][0] - 4.0) <= 1e-9
+    # draw_laguerre_diagram with colour 1: the image integrates (mean vertex density per piece), close to the total mass
+    assert abs(out["raster_sum"][0] - tm) <= 0.05 * tm
     # tests/test_power.cpp:51: the cells clipped to a convex polygon tile it
     assert abs(out["cells_area_sum"][0] - out["pentagon_area"][0]) <= 1e-12
+    # tests/test_voronoi_ad.cpp:60: the same with a non-convex polygon (a cross)
+    assert abs(out["cross_area"][0] - (4 * 0.3 * 0.9 + 4 * 0.3 * 0.6)) <= 1e-14  # 2a*2b + 2*(b-a)*2a
+    assert abs(out["cross_cells_area_sum"][0] - out["cross_area"][0]) <= 1e-12
 
 
 def test_header_layer_host_parts():

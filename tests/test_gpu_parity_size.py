@@ -281,3 +281,99 @@ def test_ot_solve_with_capacity_escalation(gpu_ctx, oracle_mod):
     assert np.abs((x1 - x1[-1]) - (x0 - x0[-1])).max() <= 1e-8
     # the trial-point probe used by the multi-GPU line search must not mistake the overflow for an empty cell
     assert not gpu_ctx.has_empty_cell(np.zeros(N))
+
+
+def test_irregular_non_convex_mesh(gpu_ctx, oracle_mod):
+    """an explicit (points, CCW triples) mesh that is neither a grid nor convex — an irregular
+    Delaunay triangulation of an L-shaped domain with a random PL density.  Diracs inside the domain AND in the
+    removed quadrant (their cells only count where the domain is)."""
+    vx, vy, tri, rho = inputs.l_shaped_mesh(400, 1)
+    abc = inputs.pl_coefficients(vx, vy, rho, tri)
+    rng = np.random.default_rng(2)
+    X = rng.uniform(-0.98, 0.98, (1500, 2))
+    orc = oracle_mod.Oracle(vx, vy, tri, abc, nthreads=NT)
+    orc.set_points(X)
+    tm = gpu_ctx.set_mesh_pl(vx, vy, rho, tri)
+    assert abs(tm - inputs.total_mass(vx, vy, tri, abc)) <= 1e-13 * tm
+    gpu_ctx.set_points(X)
+    for w in (np.zeros(len(X)), rng.normal(0, 0.3 * 4.0 / len(X), len(X))):
+        f0, g0, H0 = orc.kantorovich(w)
+        f1, g1, H1 = gpu_ctx.kantorovich(w)
+        assert abs(g1.sum() - tm) <= 1e-11 * tm
+        assert abs(f1 - f0) <= 1e-10 * abs(f0)
+        assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
+        assert common.same_pattern(H0, H1)
+        assert abs(H0 - H1).max() <= 1e-10 * np.abs(H0.diagonal()).max()
+    # and the damped Newton solve on it (target masses: uniform over the Diracs whose cell meets the domain)
+    f1, g1, H1 = gpu_ctx.kantorovich(np.zeros(len(X)))
+    keep = g1 > 0
+    Xk = X[keep]
+    orc.set_points(Xk)
+    gpu_ctx.set_points(Xk)
+    nu = np.full(len(Xk), tm / len(Xk))
+    x0, st0, _ = oracle_mod.ot_solve(orc, nu, eps_g=1e-8)
+    x1, st1, rc = gpu_ctx.ot_solve(nu, eps_g=1e-8)
+    assert rc == 0 and st0["status"] == "ok"
+    assert st1["niter"] == st0["niter"] and st1["neval"] == st0["neval"], (st0, st1)
+    assert np.abs((x1 - x1[-1]) - (x0 - x0[-1])).max() <= 1e-8
+
+
+def test_pgm_image_ingestion(gpu_ctx, tmp_path):
+    """image_to_pl_function from a FILE (functions.hpp:82-120 takes a CImg loaded from a path): PGM -> ma_set_image."""
+    img = inputs.synthetic_image(33, 21, seed=9)
+    path = tmp_path / "density.pgm"
+    with open(path, "wb") as fh:
+        fh.write(b"P5\n# test\n33 21\n255\n" + img.T.astype(np.uint8).tobytes())
+    back = inputs.read_pgm(str(path))
+    assert back.shape == (33, 21) and np.array_equal(back, img)
+    tm = gpu_ctx.set_image(back)
+    vxg, vyg = inputs.grid_vertices(33, 21)
+    rho = inputs.image_vertex_density(img)
+    assert abs(tm - inputs.total_mass(vxg, vyg, inputs.grid_triangles(33, 21), inputs.pl_coefficients(vxg, vyg, rho, inputs.grid_triangles(33, 21)))) <= 1e-13 * tm
+
+
+def test_rasterised_laguerre_diagram(gpu_ctx, oracle_mod):
+    """draw_laguerre_diagram (rasterization.hpp:512-547): exact pixel coverage of every piece times the mean density at
+    its vertices times the cell's colour.  Reference image: the ORACLE's pieces clipped to every pixel square in numpy."""
+    case = common.make_case("c2", 0.002, "0.3")   # 200 Diracs on a 23 x 23 grid
+    cfg = case["cfg"]
+    orc = common.oracle_for(oracle_mod, case)
+    orc.kantorovich(case["w"], mode=oracle_mod.MODE_RECORD | oracle_mod.MODE_BRUTE)
+    cell, face, ptr, tag, xy = orc.pieces()
+    rng = np.random.default_rng(4)
+    colors = rng.uniform(0.2, 1.0, case["N"])
+    W, H = 31, 19
+    box = (-1.0, -1.0, 1.0, 1.0)
+
+    def clip(P, a, b, c):  # keep a x + b y + c >= 0
+        out = []
+        for k in range(len(P)):
+            p, q = P[k], P[(k + 1) % len(P)]
+            s0, s1 = a * p[0] + b * p[1] + c, a * q[0] + b * q[1] + c
+            if s0 >= 0:
+                out.append(p)
+            if (s0 >= 0) != (s1 >= 0):
+                t = s0 / (s0 - s1)
+                out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+        return out
+
+    ref = np.zeros((H, W))
+    abc = case["abc"]
+    for p in range(len(cell)):
+        V = xy[ptr[p]:ptr[p + 1]]
+        ff = np.mean(abc[face[p], 0] * V[:, 0] + abc[face[p], 1] * V[:, 1] + abc[face[p], 2])
+        P = [((x - box[0]) * W / (box[2] - box[0]), (y - box[1]) * H / (box[3] - box[1])) for x, y in V]
+        xs, ys = [q[0] for q in P], [q[1] for q in P]
+        for iy in range(max(int(np.floor(min(ys))), 0), min(int(np.floor(max(ys))), H - 1) + 1):
+            for ix in range(max(int(np.floor(min(xs))), 0), min(int(np.floor(max(xs))), W - 1) + 1):
+                Q = P
+                for a, b, c in ((1, 0, -ix), (-1, 0, ix + 1), (0, 1, -iy), (0, -1, iy + 1)):
+                    Q = clip(Q, a, b, c) if Q else Q
+                if len(Q) >= 3:
+                    ar = 0.5 * sum(Q[k][0] * Q[(k + 1) % len(Q)][1] - Q[(k + 1) % len(Q)][0] * Q[k][1] for k in range(len(Q)))
+                    ref[iy, ix] += ar * ff * colors[cell[p]]
+    common.load_engine(gpu_ctx, case)
+    img = gpu_ctx.draw_laguerre_diagram(case["w"], colors, box, W, H)
+    assert img.shape == (H, W)
+    assert np.abs(img - ref).max() <= 1e-11 * np.abs(ref).max()
+    assert (ref > 0).all()  # the pieces tile the domain: every pixel is covered
