@@ -1325,10 +1325,12 @@ extern "C" int ma_moments(ma_ctx *c, const double *w, int order, double *masses,
   NEED_CTX();
   if (order != 1 && order != 2) return fail(c, MA_INVALID, "ma_moments: order must be 1 or 2");
   if (order == 2 && !m2) return fail(c, MA_INVALID, "ma_moments: m2 is required for order 2");
-  if (c->part_n > 1) return fail(c, MA_INVALID, "ma_moments: not available on a partitioned context (ma_set_partition)");
+  if (c->part_n > 1 && !c->comm)
+    return fail(c, MA_INVALID, "ma_moments on a partitioned context needs a communicator (ma_comm_init): it returns all cells");
   CKR(ma_set_weights(c, w));
   if (order == 1) CKR(evaluate_mode<MODE_MOMENTS1>(c, false));
   else CKR(evaluate_mode<MODE_MOMENTS2>(c, false));
+  if (is_dist(c)) CKR(dist_gather_slices(c, c->mom.p, 48));  // every rank returns the moments of ALL cells
   const int N = c->N;
   std::vector<double> h((size_t)N * 6);
   std::vector<int> perm(N);

@@ -1,62 +1,86 @@
-"""Runs every BASELINE.json config once at full size on one GPU (short versions of the long ones) and prints a
-JSON summary: a smoke test of the whole path at the named sizes plus the timings quoted in DESIGN.md §5."""
+"""The BASELINE.json configs as the reference's drivers state them, at full size on the GPU(s):
+  c1  tests/test_opttransport.cpp            10 k Diracs, uniform density on the unit square: damped-Newton solve
+  c2  bench_opttransport.cpp-style           100 k Diracs, 512^2 PL mixture: damped-Newton solve
+  c3  image triangulation                    1 M Diracs, 2048^2 image: damped-Newton solve
+  c4  tests/test_lloyd.cpp:48-56             250 k points, 50 Lloyd iterations X <- centroids
+  c5  tests/test_zeldovich.cpp:101-120       4 M Diracs on uniform density: outer loop { ot_solve from w = 0;
+                                             barycentres of the Laguerre cells; X += 0.03 (X - bary) }
+    python scripts/run_configs.py c4 c5                                  # one GPU
+    python -m torch.distributed.run --nproc-per-node 8 ... scripts/run_configs.py c5    # NCCL inside the engine
+Prints one JSON object (rank 0)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mongeampere_b200 import capi
 from mongeampere_b200 import workloads as common
 
-out = {}
-only = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+dist = None
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("gloo")  # out-of-band channel for the NCCL id only
+only = [a for a in sys.argv[1:] if not a.startswith("-")] or ["c1", "c2", "c3", "c4", "c5"]
+outer = int(os.environ.get("ZELDOVICH_OUTER", "3"))
+scale = float(os.environ.get("SCALE", "1.0"))
+out = {"gpus": world}
 
 
-def total_mass(ctx, N):
-    tm = getattr(ctx, "total_mass", None)
-    return tm if tm else float(ctx.kantorovich(np.zeros(N), hessian=False)[1].sum())
+def context(case):
+    ctx = capi.Context(local)
+    common.load_engine(ctx, case)
+    if world > 1:
+        ids = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(rank, world, ids[0])
+    return ctx
 
 
-if "c1" in only:  # configs[0]: 10k Diracs, uniform density on the unit square, full damped-Newton solve
-    case = common.make_case("c1", 1.0, "zero")
-    ctx = capi.Context(0); common.load_engine(ctx, case)
-    tm = total_mass(ctx, case["N"])
-    t = time.perf_counter()
-    w, st, rc = ctx.ot_solve(np.full(case["N"], tm / case["N"]), eps_g=1e-7, maxiter=100)
-    out["c1_newton"] = dict(N=case["N"], seconds=time.perf_counter() - t, status=capi.STATUS_NAMES[rc], niter=st["niter"],
-                            neval=st["neval"], cg_iters=st["cg_iters"], final_norm=st["final_norm"])
-    ctx.close()
-if "c3" in only:  # configs[2]: 1M Diracs on the 2048^2 image triangulation: evaluation + the first Newton iterations
-    case = common.make_case("c3", 1.0, "zero")
-    ctx = capi.Context(0); common.load_engine(ctx, case)
+for name in ("c1", "c2", "c3"):
+    if name not in only:
+        continue
+    case = common.make_case(name, scale, "zero")
+    ctx = context(case)
     nu = np.full(case["N"], ctx.total_mass / case["N"])
     t = time.perf_counter()
-    w, st, rc = ctx.ot_solve(nu, eps_g=1e-7, maxiter=3)
-    dt = time.perf_counter() - t
-    f, g, H = ctx.kantorovich(w)
-    out["c3_newton_first_iterations"] = dict(N=case["N"], seconds=dt, status=capi.STATUS_NAMES[rc], niter=st["niter"],
-                                             neval=st["neval"], cg_iters=st["cg_iters"], norm=st["final_norm"],
-                                             mass_err=abs(g.sum() - ctx.total_mass) / ctx.total_mass, kmax=int(ctx.info("kmax")))
+    w, st, rc = ctx.ot_solve(nu, eps_g=1e-7, maxiter=3000)
+    out[name + "_newton"] = dict(N=case["N"], seconds=time.perf_counter() - t, status=capi.STATUS_NAMES[rc], niter=st["niter"],
+                                 neval=st["neval"], cg_iters=st["cg_iters"], final_norm=st["final_norm"])
     ctx.close()
-if "c4" in only:  # configs[3]: Lloyd quantization, 250k points, exact centroids (tests/test_lloyd.cpp:52-56), 10 of the 50 iterations
-    case = common.make_case("c4", 1.0, "zero")
-    ctx = capi.Context(0); common.load_engine(ctx, case)
+if "c4" in only:  # tests/test_lloyd.cpp:48-56
+    case = common.make_case("c4", scale, "zero")
+    ctx = context(case)
     X = case["X"].copy()
-    t = time.perf_counter()
     move = []
-    for it in range(10):
+    t = time.perf_counter()
+    for it in range(50):
         ctx.set_points(X)
         m, c = ctx.lloyd(np.zeros(len(X)))
         move.append(float(np.abs(c - X).max()))
         X = c
-    out["c4_lloyd_10_iterations"] = dict(N=len(X), seconds=time.perf_counter() - t, first_move=move[0], last_move=move[-1],
+    dt = time.perf_counter() - t
+    out["c4_lloyd_50_iterations"] = dict(N=len(X), seconds=dt, ms_per_iteration=1e3 * dt / 50, first_move=move[0], last_move=move[-1],
                                          mass_err=abs(m.sum() - ctx.total_mass) / ctx.total_mass)
     ctx.close()
-if "c5" in only:  # configs[4]: 4M Diracs, uniform density on 2 triangles: evaluation + first Newton iterations
-    case = common.make_case("c5", 1.0, "zero")
-    ctx = capi.Context(0); common.load_engine(ctx, case)
-    tm = total_mass(ctx, case["N"])
-    t = time.perf_counter()
-    w, st, rc = ctx.ot_solve(np.full(case["N"], tm / case["N"]), eps_g=1e-7, maxiter=1)
-    out["c5_newton_first_iterations"] = dict(N=case["N"], seconds=time.perf_counter() - t, status=capi.STATUS_NAMES[rc],
-                                             niter=st["niter"], neval=st["neval"], cg_iters=st["cg_iters"], norm=st["final_norm"])
+if "c5" in only:  # tests/test_zeldovich.cpp:101-120
+    case = common.make_case("c5", scale, "zero")
+    ctx = context(case)
+    X = case["X"].copy()
+    N = len(X)
+    nu = np.full(N, ctx.total_mass / N)
+    log = []
+    t0 = time.perf_counter()
+    for it in range(outer):
+        ctx.set_points(X)
+        t = time.perf_counter()
+        w, st, rc = ctx.ot_solve(nu, eps_g=1e-7, maxiter=100)           # weights start from zero every time (:103,106)
+        t_solve = time.perf_counter() - t
+        m, bary = ctx.lloyd(w)                                           # uniform density: rho-centroid = area centroid (:58-74)
+        X = X + 0.03 * (X - bary)                                        # :117-118
+        log.append(dict(outer=it, solve_seconds=t_solve, status=capi.STATUS_NAMES[rc], niter=st["niter"], neval=st["neval"],
+                        cg_iters=st["cg_iters"], final_norm=st["final_norm"], max_push=float(np.abs(0.03 * (X - bary)).max())))
+    out["c5_zeldovich"] = dict(N=N, outer_iterations=outer, seconds=time.perf_counter() - t0, log=log)
     ctx.close()
-print(json.dumps(out))
+if rank == 0:
+    print(json.dumps(out))
+if dist is not None:
+    dist.destroy_process_group()

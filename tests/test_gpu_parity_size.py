@@ -377,3 +377,26 @@ def test_rasterised_laguerre_diagram(gpu_ctx, oracle_mod):
     assert img.shape == (H, W)
     assert np.abs(img - ref).max() <= 1e-11 * np.abs(ref).max()
     assert (ref > 0).all()  # the pieces tile the domain: every pixel is covered
+
+
+def test_zeldovich_outer_loop_matches_oracle(gpu_ctx, oracle_mod):
+    """Config 5 in small (tests/test_zeldovich.cpp:101-120): outer loop of { ot_solve from zero weights, barycentres of
+    the Laguerre cells, X += 0.03 (X - bary) } on the uniform 2-triangle density; two outer iterations stay together."""
+    case = common.make_case("c5", 0.0005, "zero")  # 2000 Diracs
+    orc = common.oracle_for(oracle_mod, case)
+    common.load_engine(gpu_ctx, case)
+    N = case["N"]
+    nu = np.full(N, gpu_ctx.total_mass / N)
+    X0 = case["X"].copy()
+    X1 = case["X"].copy()
+    for it in range(2):
+        orc.set_points(X0)
+        w0, st0, _ = oracle_mod.ot_solve(orc, nu, eps_g=1e-9)
+        b0 = orc.lloyd(w0)[1]
+        X0 = X0 + 0.03 * (X0 - b0)
+        gpu_ctx.set_points(X1)
+        w1, st1, rc = gpu_ctx.ot_solve(nu, eps_g=1e-9)
+        assert rc == 0 and (st1["niter"], st1["neval"]) == (st0["niter"], st0["neval"])
+        b1 = gpu_ctx.lloyd(w1)[1]
+        X1 = X1 + 0.03 * (X1 - b1)
+        assert np.abs(X1 - X0).max() <= 1e-9
