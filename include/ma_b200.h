@@ -210,14 +210,22 @@ int ma_measure_fp64_peak(ma_ctx *ctx, double *flops_per_s);
  *   "bin_target" (1)       average Diracs per leaf bin (upper bound), takes effect at the next ma_set_points
  *   "rmax" (6)             rings of leaf bins K2 walks before it turns to the quadtree
  *   "rtree" (4)            rings it walks in any case, even when the ring certificate cannot succeed (weights with a gradient)
- *   "persist" (1)          K2 with persistent lanes (k_cells_persist) or one cell per lane (0)
+ *   "lean" (1)             K2 on weights within a few bin areas runs the lock-step block kernels (k_cells_block 5x5 -> 7x7 ->
+ *                          warp-per-cell 11x11 -> CellSearch for the rest); 0: CellSearch for every cell
+ *   "block_target" (1)     average Diracs per bin of the block grid, takes effect at the next ma_set_points
+ *   "persist" (1)          CellSearch with persistent lanes (k_cells_persist) or one cell per lane (0)
  *   "persist_waves", "persist_min_chunk", "clip_a", "clip_b", "refill_at"   scheduling of k_cells_persist
  *   "cg_rtol" (1e-12), "cg_maxit" (200000)   PCG stopping rule, relative to |g|
- *   "cg_single" (0), "pcg_persist" (0), "pcg_blocks_per_sm"   alternative CG kernels (measured no faster)
- *   "filter_tol" (1e-11)   relative threshold below which k_pieces re-decides a sign in double-double
+ *   "amg" (1), "amg_omega" (0.7), "amg_alpha" (1.5)   quadtree-aggregation multigrid preconditioner of the Newton solves
+ *                          (0: Jacobi), its smoother damping and the scaling of the coarse correction
+ *   "quick_reject" (1)     ma_ot_solve tests a trial point for an empty cell against the adjacency of the last accepted
+ *                          point before it evaluates it (same outcome, optimal_transport.hpp:167)
+ *   "filter_tol" (1e-11)   relative threshold below which a sign is re-decided in double-double (K2 and k_pieces);
+ *                          1e300 sends every decision through the exact stage
  *   "abort_on_empty" (0)   see ma_cells_build
  * Read-outs (ma_get_info): "N", "nF", "nnz", "kmax", "levels", "mesh_kind", "strategy", "sm_count", "fval", "mass_sum",
- *   "mass_min", "cg_iters", "launches", "cell_lo", "cell_hi", "aborted". */
+ *   "mass_min", "cg_iters", "launches", "cell_lo", "cell_hi", "aborted", "cell_fallbacks" (sign decisions of the last
+ *   evaluation's K2 that went through the exact stage). */
 int ma_set_option(ma_ctx *ctx, const char *name, double value);
 double ma_get_info(ma_ctx *ctx, const char *name);
 

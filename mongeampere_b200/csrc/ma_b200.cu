@@ -75,6 +75,9 @@ struct ma_ctx {
   int bG = 1;
   double bph = 1, binv = 1, block_target = 1.0;           // block grid: bG x bG bins of side bph, ~block_target Diracs each
   Buf hard1, hard2, hard_n;                               // cells the block kernels pass on (lists + 2 counters)
+  Buf nbr_prev, cnt_prev;                                 // adjacency at the last accepted Newton point (quick reject of trials)
+  int prev_stride = 0;
+  int quick_reject = 1;
   int lean = 1;                                           // K2: block kernels first (0: CellSearch for every cell)
   bool abort_on_empty = false, aborted = false;
   bool probe_empty = false;  // option "abort_on_empty": ma_cells_build stops at the first empty cell and reports it
@@ -301,7 +304,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
                   &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->rho_p, &c->bin_rm,
-                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard_n};
+                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->nbr_prev, &c->cnt_prev, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard_n};
     for (Buf *b : all) release(*b);
     for (int l = 0; l < AMG_MAX_LEVELS; ++l) {
       Buf *lv[] = {&c->amg.agg[l], &c->amg.cstart[l], &c->amg.code[l], &c->amg.rowptr[l], &c->amg.col[l], &c->amg.val[l],
@@ -350,6 +353,7 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "filter_tol") c->filter_tol = value;
   else if (n == "persist") c->persist = (int)value;
   else if (n == "lean") c->lean = (int)value;
+  else if (n == "quick_reject") c->quick_reject = (int)value;
   else if (n == "block_target") c->block_target = std::max(0.05, value);
   else if (n == "abort_on_empty") c->probe_empty = value != 0;
   else if (n == "rmax") c->rmax = std::min(MA_RING_TABLE_RMAX, std::max(1, (int)value));
@@ -1801,6 +1805,42 @@ extern "C" int ma_solve_laplacian(ma_ctx *c, int N, const int *rowptr, const int
   return rc;
 }
 
+namespace {
+// remembers the adjacency of the evaluation just done (an accepted Newton point)
+int save_adjacency(ma_ctx *c) {
+  const size_t N = c->N, K = c->kmax;
+  CKR(ensure(c, c->nbr_prev, N * K * 4));
+  CKR(ensure(c, c->cnt_prev, N * 4));
+  CK(cudaMemcpyAsync(c->nbr_prev.p, c->nbr.p, N * K * 4, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->cnt_prev.p, c->nbr_cnt.p, N * 4, cudaMemcpyDeviceToDevice, c->stream));
+  c->prev_stride = (int)K;
+  return MA_OK;
+}
+// true in *empty if, at the weights now in c->w, some cell is certainly empty (k_cells_quick_empty)
+int quick_empty(ma_ctx *c, bool *empty) {
+  *empty = false;
+  if (!c->quick_reject || c->prev_stride == 0) return MA_OK;
+  CKR(alloc_eval(c));
+  Params p;
+  fill_params(c, p);
+  CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
+  k_gather_w<<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->w.as<double>(), c->perm.as<int>(), c->s2rm.as<int>(), c->N,
+                                                    c->ws.as<double>(), c->wr.as<double>());
+  CKR(reduce4(c, c->ws.as<double>(), nullptr, c->N, c->wstat.as<double>()));  // (CellSearch::init reads the weight range)
+  constexpr int NT = 128;
+  const size_t sm = cells_smem_bytes<16, NT>();
+  CK(cudaFuncSetAttribute(k_cells_quick_empty<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_cells_quick_empty<NT><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p, c->nbr_prev.as<int>(), c->cnt_prev.as<int>(), c->prev_stride);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  CKR(dist_sync_flags(c));
+  CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *empty = c->hs->abort_ != 0;
+  return MA_OK;
+}
+}  // namespace
+
 extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_initial, double eps_g, size_t maxiter,
                            int verbose, ma_statistics *stats) {
   NEED_CTX();
@@ -1834,8 +1874,19 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
   auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double>(b - a).count();
   };
+  c->prev_stride = 0;  // no adjacency of an accepted point yet
   auto feval_inner = [&]() -> int {
     ++neval;
+    if (neval > 1) {  // a line-search trial: first the cheap "is some cell already empty?" test
+      bool empty = false;
+      CKR(quick_empty(c, &empty));
+      if (empty) {
+        if (c->trace) fprintf(stderr, "[ma] trial rejected by the quick empty-cell test\n");
+        mmin = 0.0;
+        gnorm = 1e300;
+        return MA_OK;
+      }
+    }
     c->abort_on_empty = neval > 1;  // every evaluation after the first is a line-search trial
     int rc_e = evaluate_mode<MODE_KANTOROVICH>(c, true);
     c->abort_on_empty = false;
@@ -1888,6 +1939,7 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
   };
 
   CKR(feval());  // :131
+  CKR(save_adjacency(c));
   const double eps0 = std::min(mmin, nu_min) / 2;  // :137-138
   if (!(eps0 > 0)) {                              // :139-148
     if (verbose) fprintf(stderr, "Error: computed minimum mass is non-positive\n");
@@ -1946,7 +1998,7 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
                                                                c->w.as<double>());
       c->launches += 2;
       CKR(feval());
-      if (mmin >= eps0 && gnorm <= (1 - alpha / 2) * n0) break;
+      if (mmin >= eps0 && gnorm <= (1 - alpha / 2) * n0) { CKR(save_adjacency(c)); break; }
       alpha *= .5;
       if (verbose) fprintf(stderr, "subit %zu.%zu: min(masses)=%g\n", niter, nls++, mmin);
       if (alpha < 1e-30) {

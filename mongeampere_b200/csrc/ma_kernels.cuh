@@ -691,6 +691,53 @@ __global__ void __launch_bounds__(NT, MA_K2B_MINBLOCKS) k_cells_block(Params p, 
   }
 }
 
+// Line-search trials (optimal_transport.hpp:163-170): most of them are rejected because some cell has become EMPTY.
+// Before a trial point is evaluated this kernel clips every cell against the neighbours it had at the last ACCEPTED
+// point only — a superset of the true cell — and raises the abort flag if one of those supersets is already empty:
+// then the true cell is empty too and the trial is rejected without the neighbour search (which, with the graded
+// weights of the Newton iterates, is the expensive quadtree walk: 20 ms per evaluation at 1 M Diracs against 0.3 ms here).
+template <int NT> __global__ void __launch_bounds__(NT, 4) k_cells_quick_empty(Params p, const int *__restrict__ prev_nbr,
+                                                                               const int *__restrict__ prev_cnt, int prev_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sx = reinterpret_cast<double *>(smem_raw);
+  double *sy = sx + 16 * NT;
+  int *st = reinterpret_cast<int *>(sy + 16 * NT);
+  typedef PolyRef<NT, true> Poly;
+  const int idx = blockIdx.x * NT + threadIdx.x;
+  const int ncell = p.cell_hi - p.cell_lo;
+  if ((idx & ~31) >= ncell) return;  // warp-uniform
+  const bool valid = idx < ncell;
+  const int i = p.cell_lo + (valid ? idx : ncell - 1);
+  Poly P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+  CellSearch<Poly> S;
+  S.init(p, i, P);
+  const int cnt = valid ? max(prev_cnt[i], 0) : 0;
+  const int cmax = __reduce_max_sync(0xffffffffu, cnt);
+  bool live = valid && cnt > 0;
+  for (int s = 0; s < cmax; ++s) {
+    const bool act = live && s < cnt;
+    const int j = act ? prev_nbr[(size_t)i * prev_stride + s] : i;
+    const double Dx = p.xs[j] - S.xi, Dy = p.ys[j] - S.yi, dw = S.wi - p.ws[j];
+    const double dd2 = Dx * Dx + Dy * Dy, c = 0.5 * (dd2 + dw);
+    bool cut = false;
+    if (act && dd2 > 0.0 && !(c >= 0.0 && c * c >= S.R2 * dd2 * (1.0 + 1e-9))) {
+      double r2;
+      const unsigned long long in = S.sign_mask(p, P, j, Dx, Dy, c, dd2, dw, r2);
+      S.R2 = r2;
+      if (in == 0ull) { p.flags[1] = 1; live = false; }
+      else if (in != lowmask64(S.n)) { S.jc = j; S.cDx = Dx; S.cDy = Dy; S.cc = c; S.cin = in; cut = true; }
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, cut)) {
+      if (cut) {
+        S.template clip<false>(p, P, 16);
+        if (S.phase != 0) live = false;  // more than 16 vertices on the way: no statement about this cell
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // K2, the tail: ONE WARP per cell for the few cells (0.4 % of a uniform point set) that even the 7 x 7 block cannot
 // certify.  Thread-per-cell kernels run them at the latency of a single lane walking 121 candidates; here the 32
 // lanes test 32 candidates of the block of radius R at once against the polygon (shared memory), the cutting ones are

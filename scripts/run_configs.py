@@ -25,6 +25,11 @@ scale = float(os.environ.get("SCALE", "1.0"))
 out = {"gpus": world}
 
 
+def progress(*a):
+    if rank == 0:
+        print("[run_configs]", *a, file=sys.stderr, flush=True)
+
+
 def context(case):
     ctx = capi.Context(local)
     common.load_engine(ctx, case)
@@ -38,13 +43,16 @@ def context(case):
 for name in ("c1", "c2", "c3"):
     if name not in only:
         continue
+    progress(name, "building the case")
     case = common.make_case(name, scale, "zero")
     ctx = context(case)
+    progress(name, "solving")
     nu = np.full(case["N"], ctx.total_mass / case["N"])
     t = time.perf_counter()
     w, st, rc = ctx.ot_solve(nu, eps_g=1e-7, maxiter=3000)
     out[name + "_newton"] = dict(N=case["N"], seconds=time.perf_counter() - t, status=capi.STATUS_NAMES[rc], niter=st["niter"],
                                  neval=st["neval"], cg_iters=st["cg_iters"], final_norm=st["final_norm"])
+    progress(name, out[name + "_newton"])
     ctx.close()
 if "c4" in only:  # tests/test_lloyd.cpp:48-56
     case = common.make_case("c4", scale, "zero")
@@ -56,6 +64,8 @@ if "c4" in only:  # tests/test_lloyd.cpp:48-56
         ctx.set_points(X)
         m, c = ctx.lloyd(np.zeros(len(X)))
         move.append(float(np.abs(c - X).max()))
+        if it % 10 == 0:
+            progress("c4 iteration", it, "move", move[-1], "t", time.perf_counter() - t)
         X = c
     dt = time.perf_counter() - t
     out["c4_lloyd_50_iterations"] = dict(N=len(X), seconds=dt, ms_per_iteration=1e3 * dt / 50, first_move=move[0], last_move=move[-1],
@@ -70,7 +80,9 @@ if "c5" in only:  # tests/test_zeldovich.cpp:101-120
     log = []
     t0 = time.perf_counter()
     for it in range(outer):
+        progress("c5 outer", it, "set_points")
         ctx.set_points(X)
+        progress("c5 outer", it, "ot_solve")
         t = time.perf_counter()
         w, st, rc = ctx.ot_solve(nu, eps_g=1e-7, maxiter=100)           # weights start from zero every time (:103,106)
         t_solve = time.perf_counter() - t
@@ -78,6 +90,7 @@ if "c5" in only:  # tests/test_zeldovich.cpp:101-120
         X = X + 0.03 * (X - bary)                                        # :117-118
         log.append(dict(outer=it, solve_seconds=t_solve, status=capi.STATUS_NAMES[rc], niter=st["niter"], neval=st["neval"],
                         cg_iters=st["cg_iters"], final_norm=st["final_norm"], max_push=float(np.abs(0.03 * (X - bary)).max())))
+        progress(log[-1])
     out["c5_zeldovich"] = dict(N=N, outer_iterations=outer, seconds=time.perf_counter() - t0, log=log)
     ctx.close()
 if rank == 0:
