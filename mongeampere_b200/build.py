@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libma_b200.so")
 SOURCES = ["ma_b200.cu"]
-HEADERS = ["ma_geom.cuh", "ma_cell.cuh", "ma_block.cuh", "ma_seg.cuh", "ma_kernels.cuh", "ma_pcg.cuh"]
+HEADERS = ["ma_geom.cuh", "ma_cell.cuh", "ma_block.cuh", "ma_warm.cuh", "ma_amg.cuh", "ma_seg.cuh", "ma_kernels.cuh", "ma_pcg.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

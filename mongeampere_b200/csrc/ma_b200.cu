@@ -34,6 +34,13 @@ struct ma_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // copy stream of ma_get_hessian_csr
+  cudaStream_t side = nullptr;      // evaluation: work that is off the critical path (supporting planes, scalar reductions)
+  cudaEvent_t ev_fork[4] = {};
+  bool planes_pending = false;      // the side stream is building the supporting planes: join before CellSearch runs
+  int use_graph = 1;                // evaluations are replayed as CUDA graphs (captured per distinct launch sequence)
+  struct EvalGraph { std::string key; cudaGraphExec_t exec = nullptr; int launches = 0; unsigned long long stamp = 0; };
+  std::vector<EvalGraph> graphs;
+  unsigned long long graph_clock = 0;
   cudaEvent_t ev_chunk[8] = {};
   std::string err;
   int sm_count = 148;
@@ -77,6 +84,15 @@ struct ma_ctx {
   Buf hard1, hard2, hard_n;                               // cells the block kernels pass on (lists + 2 counters)
   Buf nbr_prev, cnt_prev;                                 // adjacency at the last accepted Newton point (quick reject of trials)
   int prev_stride = 0;
+  double mesh_mass = 0.0;  // integral of the density over the mesh (the warm path's sheet count)
+  bool in_newton = false;
+  // warm path of K2 (ma_warm.cuh): cells from that adjacency + the ring-match certificate
+  Buf ring, ring_n, cstate;
+  int warm = 1;            // 0: off; 1: inside ma_ot_solve; 2: every evaluation seeds the next one
+  int warm_skip = 0;       // evaluations to run cold after a warm attempt that could not be certified
+  int warm_penalty = 4;
+  bool warm_now = false;   // the evaluation being enqueued uses the warm path
+  long long warm_evals = 0, warm_rebuilt = 0, warm_failed = 0;  // statistics: warm evaluations, cells CellSearch rebuilt in them, attempts redone cold
   int quick_reject = 1;
   int lean = 1;                                           // K2: block kernels first (0: CellSearch for every cell)
   bool abort_on_empty = false, aborted = false;
@@ -87,7 +103,7 @@ struct ma_ctx {
   // evaluation state
   Buf poly_x, poly_y, poly_t, poly_n;
   Buf w, ws, nbr, nbr_cnt, cell_bb, mass, fcell, hslot, touched, rowcnt, rowptr, col, val, mom;
-  Buf scan_tmp, red_partial, red_out, counters, flags, scratch_d, scratch_i;
+  Buf scan_tmp, red_partial, red_partial2, red_out, counters, flags, scratch_d, scratch_i;
   Buf cptr, ccol, cval, cg_out;  // caller-order copies
   int nnz = 0;
   bool have_eval = false, have_hessian = false;
@@ -118,7 +134,7 @@ struct ma_ctx {
   // L2 flush
   Buf flush;
   // pinned host staging for the scalars read back every evaluation (pageable copies are staged and slow)
-  struct HostScalars { int flags, abort_, cell_fallbacks, pad, nnz, pad2[3]; double red[8]; } *hs = nullptr;  // flags..pad mirror the device flags[4]
+  struct HostScalars { int flags, abort_, cell_fallbacks, pad, nnz, pad2[3]; double red[8]; int warm[8]; } *hs = nullptr;  // flags..pad mirror the device flags[4]
 
   // timing
   cudaEvent_t ev[MA_T_COUNT + 2] = {};
@@ -187,7 +203,7 @@ int scan_i32(ma_ctx *c, const int *in, int *out, int n) {
 
 // out (device, 4 doubles) = { sum a, sum a*b (a*a if b null), min a, max a }
 int reduce4(ma_ctx *c, const double *a, const double *b, int n, double *out_dev) {
-  CKR(ensure(c, c->red_partial, (size_t)RED_BLOCKS * 4 * sizeof(double)));
+  CKR(ensure(c, c->red_partial, (size_t)RED_BLOCKS * 8 * sizeof(double)));
   int nb = std::min(RED_BLOCKS, std::max(1, cdiv(n, RED_NT)));
   k_reduce_stage1<<<nb, RED_NT, 0, c->stream>>>(a, b, n, c->red_partial.as<double>());
   k_reduce_stage2<<<1, RED_NT, 0, c->stream>>>(c->red_partial.as<double>(), nb, out_dev);
@@ -195,17 +211,28 @@ int reduce4(ma_ctx *c, const double *a, const double *b, int n, double *out_dev)
   CK(cudaGetLastError());
   return MA_OK;
 }
+// the same for two arrays in one pair of launches: out[0..4) from a0, out[4..8) from a1 (same reduction trees as reduce4)
+int reduce4x2(ma_ctx *c, const double *a0, const double *a1, int n, double *out_dev, cudaStream_t st) {
+  CKR(ensure(c, c->red_partial2, (size_t)RED_BLOCKS * 8 * sizeof(double)));
+  int nb = std::min(RED_BLOCKS, std::max(1, cdiv(n, RED_NT)));
+  k_reduce2_stage1<<<dim3(nb, 2), RED_NT, 0, st>>>(a0, a1, n, c->red_partial2.as<double>());
+  k_reduce2_stage2<<<2, RED_NT, 0, st>>>(c->red_partial2.as<double>(), nb, out_dev);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  return MA_OK;
+}
 
 // prefix sums of the moment terms of SET over the Morton-sorted sites into out[K][n+1]
-template <int SET> int moment_scan(ma_ctx *c, double *out, PlaneGate gate = PlaneGate{nullptr, 0.0}) {
+template <int SET> int moment_scan(ma_ctx *c, double *out, PlaneGate gate = PlaneGate{nullptr, 0.0}, cudaStream_t st = nullptr) {
+  if (!st) st = c->stream;
   constexpr int K = MomentTerms<SET>::K;
   const int n = c->N, nt = std::max(1, cdiv(n, FS_TILE));
   CKR(ensure(c, c->fs_tiles, (size_t)K * nt * 8));
   const double cx = c->px0 + 0.5 * c->ph * (1 << c->L), cy = c->py0 + 0.5 * c->ph * (1 << c->L);
-  k_moment_scan_tiles<SET><<<nt, FS_NT, 0, c->stream>>>(c->xs.as<double>(), c->ys.as<double>(), c->ws.as<double>(), cx, cy,
-                                                        n, out, c->fs_tiles.as<double>(), gate);
-  k_moment_scan_sums<<<K, FS_NT, 0, c->stream>>>(c->fs_tiles.as<double>(), nt, n, out, gate);
-  k_moment_scan_add<<<nt, FS_NT, 0, c->stream>>>(out, c->fs_tiles.as<double>(), n, K, gate);
+  k_moment_scan_tiles<SET><<<nt, FS_NT, 0, st>>>(c->xs.as<double>(), c->ys.as<double>(), c->ws.as<double>(), cx, cy,
+                                                 n, out, c->fs_tiles.as<double>(), gate);
+  k_moment_scan_sums<<<K, FS_NT, 0, st>>>(c->fs_tiles.as<double>(), nt, n, out, gate);
+  k_moment_scan_add<<<nt, FS_NT, 0, st>>>(out, c->fs_tiles.as<double>(), n, K, gate);
   c->launches += 3;
   CK(cudaGetLastError());
   return MA_OK;
@@ -280,6 +307,8 @@ extern "C" int ma_create(ma_ctx **out, int device) {
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  for (auto &ev : c->ev_fork) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
@@ -298,13 +327,13 @@ extern "C" void ma_destroy(ma_ctx *c) {
     Buf *all[] = {&c->vx, &c->vy, &c->tri, &c->abc, &c->tbin_ptr, &c->tbin_face, &c->x, &c->y, &c->xs, &c->ys,
                   &c->perm, &c->pos, &c->code, &c->bin_count, &c->bin_start, &c->wmax, &c->w, &c->ws, &c->nbr,
                   &c->nbr_cnt, &c->cell_bb, &c->mass, &c->fcell, &c->hslot, &c->touched, &c->rowcnt, &c->rowptr,
-                  &c->col, &c->val, &c->mom, &c->scan_tmp, &c->red_partial, &c->red_out, &c->counters, &c->flags,
+                  &c->col, &c->val, &c->mom, &c->scan_tmp, &c->red_partial, &c->red_partial2, &c->red_out, &c->counters, &c->flags,
                   &c->scratch_d, &c->scratch_i, &c->cptr, &c->ccol, &c->cval, &c->cg_out, &c->pc_count, &c->pc_off,
                   &c->pc_cell, &c->pc_face, &c->pc_ptr, &c->pc_tag, &c->pc_xy, &c->dinv, &c->cgx, &c->cgr, &c->cgz,
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
                   &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->rho_p, &c->bin_rm,
-                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->nbr_prev, &c->cnt_prev, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard_n};
+                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->nbr_prev, &c->cnt_prev, &c->ring, &c->ring_n, &c->cstate, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard_n};
     for (Buf *b : all) release(*b);
     for (int l = 0; l < AMG_MAX_LEVELS; ++l) {
       Buf *lv[] = {&c->amg.agg[l], &c->amg.cstart[l], &c->amg.code[l], &c->amg.rowptr[l], &c->amg.col[l], &c->amg.val[l],
@@ -319,6 +348,11 @@ extern "C" void ma_destroy(ma_ctx *c) {
     for (auto &ev : c->ev_chunk)
       if (ev) cudaEventDestroy(ev);
     ma_comm_destroy(c);
+    for (auto &g : c->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto &ev : c->ev_fork)
+      if (ev) cudaEventDestroy(ev);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     if (c->hs) cudaFreeHost(c->hs);
@@ -353,6 +387,8 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "filter_tol") c->filter_tol = value;
   else if (n == "persist") c->persist = (int)value;
   else if (n == "lean") c->lean = (int)value;
+  else if (n == "graph") c->use_graph = (int)value;
+  else if (n == "warm") c->warm = (int)value;
   else if (n == "quick_reject") c->quick_reject = (int)value;
   else if (n == "block_target") c->block_target = std::max(0.05, value);
   else if (n == "abort_on_empty") c->probe_empty = value != 0;
@@ -390,6 +426,9 @@ extern "C" double ma_get_info(ma_ctx *c, const char *name) {
   if (n == "strategy") return c->strategy;
   if (n == "aborted") return c->aborted ? 1 : 0;
   if (n == "fval") return c->fval;
+  if (n == "warm_evals") return (double)c->warm_evals;      // evaluations certified by the warm path of K2 ...
+  if (n == "warm_rebuilt") return (double)c->warm_rebuilt;  // ... cells CellSearch rebuilt in them ...
+  if (n == "warm_failed") return (double)c->warm_failed;    // ... and attempts that had to be redone cold
   if (n == "cell_fallbacks") return (double)c->cell_fallbacks;  // K2 sign decisions that went to the exact stage (last evaluation)
   if (n == "cell_lo") return (double)((long long)c->N * c->part_rank / c->part_n);
   if (n == "cell_hi") return (double)((long long)c->N * (c->part_rank + 1) / c->part_n);
@@ -459,6 +498,7 @@ extern "C" int ma_set_mesh(ma_ctx *c, int nV, const double *vx, const double *vy
   CKR(upload(c, c->tbin_ptr, ptr.data(), ptr.size() * 4));
   CKR(upload(c, c->tbin_face, faces.data(), faces.size() * 4));
   CK(cudaStreamSynchronize(c->stream));
+  c->mesh_mass = host_total_mass(nF, tri, vx, vy, abc);
   invalidate_eval(c);
   return MA_OK;
 }
@@ -602,7 +642,7 @@ extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y)
     CKR(ensure(c, c->xr, (size_t)N * 8)); CKR(ensure(c, c->yr, (size_t)N * 8)); CKR(ensure(c, c->wr, (size_t)N * 8));
     CKR(ensure(c, c->rm2s, (size_t)N * 4)); CKR(ensure(c, c->s2rm, (size_t)N * 4));
     CKR(ensure(c, c->rm_start, (nbb + 1) * 4)); CKR(ensure(c, c->blk_cnt, nbb * 4)); CKR(ensure(c, c->scratch_i, (size_t)N * 4));
-    CKR(ensure(c, c->hard1, (size_t)N * 4)); CKR(ensure(c, c->hard2, (size_t)N * 4)); CKR(ensure(c, c->hard_n, 16));
+    CKR(ensure(c, c->hard1, (size_t)N * 4)); CKR(ensure(c, c->hard2, (size_t)N * 4)); CKR(ensure(c, c->hard_n, 64));
     CK(cudaMemsetAsync(c->blk_cnt.p, 0, nbb * 4, c->stream));
     k_blk_count<<<cdiv(N, 256), 256, 0, c->stream>>>(c->xs.as<double>(), c->ys.as<double>(), N, c->px0, c->py0, c->binv, bG,
                                                      c->scratch_i.as<int>(), c->blk_cnt.as<int>());
@@ -856,6 +896,7 @@ int fill_params(ma_ctx *c, Params &p) {
   p.nbr = c->nbr.as<int>(); p.nbr_cnt = c->nbr_cnt.as<int>(); p.cell_bb = c->cell_bb.as<double>();
   p.poly_x = c->poly_x.as<double>(); p.poly_y = c->poly_y.as<double>();
   p.poly_t = c->poly_t.as<int>(); p.poly_n = c->poly_n.as<int>();
+  p.ring = c->ring.as<int>(); p.ring_n = c->ring_n.as<int>(); p.cstate = c->cstate.as<int>();
   p.mass = c->mass.as<double>(); p.fcell = c->fcell.as<double>(); p.hslot = c->hslot.as<double>();
   p.touched = c->touched.as<unsigned long long>(); p.rowcnt = c->rowcnt.as<int>();
   p.mom = c->mom.as<double>();
@@ -863,6 +904,13 @@ int fill_params(ma_ctx *c, Params &p) {
   p.stats = c->stats;
   p.flags = c->flags.as<int>();
   p.filter_tol = c->filter_tol;
+  return MA_OK;
+}
+
+// CellSearch is about to run: the supporting planes must be complete
+int join_planes(ma_ctx *c) {
+  if (c->planes_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_fork[1], 0));
+  c->planes_pending = false;
   return MA_OK;
 }
 
@@ -875,19 +923,21 @@ template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
   const int ncells = p.cell_hi - p.cell_lo;
   int *cnt = c->hard_n.as<int>();
   CK(cudaMemsetAsync(cnt, 0, 16, c->stream));
-  CK(cudaFuncSetAttribute(k_cells_block<-1, 2, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  CK(cudaFuncSetAttribute(k_cells_block<2, 3, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const size_t smb = sm;
+  CK(cudaFuncSetAttribute(k_cells_block<-1, 2, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+  CK(cudaFuncSetAttribute(k_cells_block<2, 3, MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
   CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int nblk = std::max(1, cdiv(ncells, NT));
-  k_cells_block<-1, 2, MAXV, NT, POLY><<<nblk, NT, sm, c->stream>>>(p, nullptr, nullptr, c->hard1.as<int>(), cnt);
+  k_cells_block<-1, 2, MAXV, NT, POLY><<<nblk, NT, smb, c->stream>>>(p, nullptr, nullptr, c->hard1.as<int>(), cnt);
   // The later stages see a fraction of the cells (or, with graded weights, all of them: k_cells_persist then ignores the
   // list): the ~15 % the 5 x 5 block cannot certify continue from their polygon with the ring of bins around it, the
   // ~0.4 % left after that get a warp each and the block of radius 5 (one by one through CellSearch those few cells
   // cost 0.6 ms of pure latency, profiles/r02b), CellSearch takes whatever remains.
   const int nblk2 = std::max(1, std::min(nblk, c->sm_count * 8));
-  k_cells_block<2, 3, MAXV, NT, POLY><<<nblk2, NT, sm, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
+  k_cells_block<2, 3, MAXV, NT, POLY><<<nblk2, NT, smb, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
   k_cells_warp<5, POLY><<<c->sm_count * 16, 128, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, c->hard1.as<int>(), cnt + 2);
   // CellSearch: a small grid for the leftovers of the list (a handful of cells, if any) ...
+  CKR(join_planes(c));
   k_cells_persist<MAXV, NT, POLY><<<c->sm_count * 2, NT, sm, c->stream>>>(p, 1, c->hard1.as<int>(), cnt + 2);
   // ... and a grid sized for the whole tile that only works when the weights are graded (the regime of the Newton iterates)
   int per_sm = 1;
@@ -901,12 +951,39 @@ template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
   return MA_OK;
 }
 
+// K2 warm path (ma_warm.cuh): seed every cell from the saved adjacency, certify by ring matching, let CellSearch rebuild
+// the cells around every failing vertex, twice; the count of the last match goes to the host with the other scalars.
+template <int NT, bool POLY> int launch_cells_warm(ma_ctx *c, const Params &p) {
+  constexpr int MAXV = 16;
+  const size_t sm = cells_smem_bytes<MAXV, NT>();
+  const int ncells = p.cell_hi - p.cell_lo;
+  int *cnt = c->hard_n.as<int>();  // [0], [1]: lengths of the two rebuild lists, [5]: of the last match's; [2..4]: failing cells per match
+  CK(cudaMemsetAsync(cnt, 0, 32, c->stream));
+  CK(cudaFuncSetAttribute(k_cells_seed<NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const int nblk = std::max(1, cdiv(ncells, NT)), nblk_m = std::max(1, cdiv(ncells, 256));
+  k_cells_seed<NT, POLY><<<nblk, NT, sm, c->stream>>>(p, c->nbr_prev.as<int>(), c->cnt_prev.as<int>(), c->hard1.as<int>(), cnt);
+  k_cells_match<<<nblk_m, 256, 0, c->stream>>>(p, c->hard1.as<int>(), cnt, cnt + 2);
+  CKR(join_planes(c));
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cells_persist<MAXV, NT, POLY>, NT, sm));
+  k_cells_persist<MAXV, NT, POLY><<<c->sm_count * std::max(per_sm, 1), NT, sm, c->stream>>>(p, 1, c->hard1.as<int>(), cnt, true);
+  k_cells_match<<<nblk_m, 256, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, cnt + 3);
+  k_cells_persist<MAXV, NT, POLY><<<c->sm_count * 2, NT, sm, c->stream>>>(p, 1, c->hard2.as<int>(), cnt + 1, true);
+  k_cells_match<<<nblk_m, 256, 0, c->stream>>>(p, c->hard1.as<int>(), cnt + 5, cnt + 4);
+  c->launches += 6;
+  CK(cudaGetLastError());
+  return MA_OK;
+}
+
 template <int MAXV, int NT, bool POLY> int launch_cells(ma_ctx *c, const Params &p) {
   size_t sm = cells_smem_bytes<MAXV, NT>();
   const int ncells = p.cell_hi - p.cell_lo;
   if constexpr (MAXV == 16) {
+    if (c->warm_now) return launch_cells_warm<NT, POLY>(c, p);
     if (c->lean && c->persist) return launch_cells_lean<NT, POLY>(c, p);
   }
+  CKR(join_planes(c));
   if (c->persist) {
     // persistent lanes: each warp owns `chunk` consecutive cells; about 3 waves of resident blocks
     CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -982,10 +1059,18 @@ int alloc_eval(ma_ctx *c) {
   CKR(ensure(c, c->flags, 16));
   CKR(ensure(c, c->red_out, 16 * sizeof(double)));
   CKR(ensure(c, c->wstat, 4 * sizeof(double)));
+  // scratch of the scans / reductions (no allocation may happen while an evaluation is being captured into a graph)
+  CKR(ensure(c, c->scan_tmp, (size_t)(cdiv((int)N, SCAN_TILE) + 2) * sizeof(int)));
+  CKR(ensure(c, c->red_partial, (size_t)RED_BLOCKS * 8 * sizeof(double)));
+  CKR(ensure(c, c->red_partial2, (size_t)RED_BLOCKS * 8 * sizeof(double)));
+  CKR(ensure(c, c->fs_tiles, (size_t)8 * std::max(1, cdiv((int)N, FS_TILE)) * 8));
   // cell polygons: what k_seg integrates, and what the block kernels hand from one pass to the next
   const size_t slots = (size_t)(c->kmax == 16 ? 16 : (c->kmax == 32 ? 36 : 64)) * N;
   CKR(ensure(c, c->poly_x, slots * 8)); CKR(ensure(c, c->poly_y, slots * 8));
   CKR(ensure(c, c->poly_t, slots * 4)); CKR(ensure(c, c->poly_n, N * 4));
+  if (c->warm && c->prev_stride == RING_STRIDE) {
+    CKR(ensure(c, c->ring, N * RING_STRIDE * 4)); CKR(ensure(c, c->ring_n, N * 4)); CKR(ensure(c, c->cstate, N * 4));
+  }
   return MA_OK;
 }
 
@@ -1000,22 +1085,40 @@ template <bool POLY = false> int run_cells(ma_ctx *c, Params &p) {
   if (c->L >= 5) k_wmax_top<<<1, 1024, 0, c->stream>>>(c->L, c->wmax.as<double>());
   CKR(reduce4(c, c->ws.as<double>(), nullptr, N, c->wstat.as<double>()));  // weight range (K2's choice of pruning disk)
   c->launches += 2 + (c->L >= 5);
+  // The supporting planes are read by CellSearch only (graded weights, or the few cells the block kernels leave over):
+  // they are built on the side stream while the block kernels run.
   const PlaneGate gate{c->wstat.as<double>(), 0.25 * c->ph * c->ph};
-  CKR(moment_scan<1>(c, c->pre1.as<double>(), gate));
+  CK(cudaEventRecord(c->ev_fork[0], c->stream));
+  CK(cudaStreamWaitEvent(c->side, c->ev_fork[0], 0));
+  CKR(moment_scan<1>(c, c->pre1.as<double>(), gate, c->side));
   {
     const size_t nnodes = (4 * nb - 1) / 3;
-    k_node_fit<<<cdiv((long long)nnodes, 256), 256, 0, c->stream>>>(c->L, c->bin_start.as<int>(), N, c->pre0.as<double>(),
-                                                                    c->pre1.as<double>(), c->nodeG.as<double>(),
-                                                                    c->nodeA.as<unsigned long long>(), gate);
-    k_node_alpha<<<cdiv(N, 256), 256, 0, c->stream>>>(N, c->L, c->xs.as<double>(), c->ys.as<double>(), c->ws.as<double>(),
-                                                      c->code_s.as<unsigned>(), c->px0, c->py0, c->ph, c->nodeG.as<double>(),
-                                                      c->nodeA.as<unsigned long long>(), gate);
+    k_node_fit<<<cdiv((long long)nnodes, 256), 256, 0, c->side>>>(c->L, c->bin_start.as<int>(), N, c->pre0.as<double>(),
+                                                                  c->pre1.as<double>(), c->nodeG.as<double>(),
+                                                                  c->nodeA.as<unsigned long long>(), gate);
+    k_node_alpha<<<cdiv(N, 256), 256, 0, c->side>>>(N, c->L, c->xs.as<double>(), c->ys.as<double>(), c->ws.as<double>(),
+                                                    c->code_s.as<unsigned>(), c->px0, c->py0, c->ph, c->nodeG.as<double>(),
+                                                    c->nodeA.as<unsigned long long>(), gate);
     c->launches += 2;
   }
   CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev_fork[1], c->side));
+  c->planes_pending = true;
   if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PREP + 1], c->stream));
   CKR(launch_cells_kmax<POLY>(c, p));
   if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CELLS + 1], c->stream));
+  return MA_OK;
+}
+
+// remembers the adjacency of the evaluation just done (an accepted Newton point): the seeds of the warm
+// path and of the quick empty-cell test
+int save_adjacency(ma_ctx *c) {
+  const size_t N = c->N, K = c->kmax;
+  CKR(ensure(c, c->nbr_prev, N * K * 4));
+  CKR(ensure(c, c->cnt_prev, N * 4));
+  CK(cudaMemcpyAsync(c->nbr_prev.p, c->nbr.p, N * K * 4, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->cnt_prev.p, c->nbr_cnt.p, N * 4, cudaMemcpyDeviceToDevice, c->stream));
+  c->prev_stride = (int)K;
   return MA_OK;
 }
 
@@ -1025,7 +1128,14 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
   if (c->N < 1) return fail(c, MA_INVALID, "no points set");
   c->capacity_hit = false;
   c->kmax = c->kmax_base;
-  for (int attempt = 0; attempt < 3; ++attempt) {
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    // warm path of K2: the adjacency of an earlier evaluation of these points seeds this one (ma_warm.cuh)
+    c->warm_now = false;
+    if (c->warm && (c->warm == 2 || c->in_newton) && c->kmax == 16 && c->part_n == 1 && c->prev_stride == RING_STRIDE && c->persist &&
+        (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2)) {
+      if (c->warm_skip > 0) --c->warm_skip;
+      else c->warm_now = true;
+    }
     CKR(alloc_eval(c));
     if (MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) CKR(ensure(c, c->mom, (size_t)c->N * 48));
     if (use_seg<MODE>(c)) {
@@ -1035,38 +1145,10 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     }
     Params p;
     fill_params(c, p);
-    CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
-    if (c->stats) CK(cudaMemsetAsync(c->counters.p, 0, CNT_N * 8, c->stream));
-    if (c->profiling) CK(cudaEventRecord(c->ev[0], c->stream));
     const int lo = p.cell_lo, nloc = p.cell_hi - p.cell_lo;
-    if (MODE == MODE_KANTOROVICH && c->part_n > 1) {
-      // rows outside this context's Morton tile are empty here (another GPU owns them)
-      const size_t N = c->N, hi = p.cell_hi;
-      auto zero = [&](Buf &b, size_t esz) {
-        if (lo) cudaMemsetAsync(b.p, 0, (size_t)lo * esz, c->stream);
-        if (hi < N) cudaMemsetAsync((char *)b.p + hi * esz, 0, (N - hi) * esz, c->stream);
-      };
-      zero(c->mass, 8); zero(c->fcell, 8); zero(c->touched, 8); zero(c->rowcnt, 4);
-    }
     constexpr int SEG_MODE = (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) ? MODE : 0;
     const bool seg = use_seg<MODE>(c);
-    if (seg) CKR(run_cells<true>(c, p));
-    else CKR(run_cells<false>(c, p));
-    c->aborted = false;
-    // (line-search trials: once K2 has found an empty cell the point is rejected whatever the rest says,
-    // optimal_transport.hpp:167 — K3 / K4 then return at once on the device-side flag, the host learns it at the one
-    // synchronisation below)
-    if (seg) CKR(launch_seg_kmax<SEG_MODE>(c, p));
-    else CKR(launch_pieces_mode<MODE>(c, p));
-    if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
     const bool hess = (MODE == MODE_KANTOROVICH) && with_hessian;
-    if (MODE == MODE_KANTOROVICH) {
-      // row pointers of this context's rows only (rowptr[lo] = 0 ... rowptr[hi] = nnz); rows of other tiles have none
-      if (hess) CKR(scan_i32(c, c->rowcnt.as<int>() + lo, c->rowptr.as<int>() + lo, nloc));
-      CKR(reduce4(c, c->fcell.as<double>() + lo, nullptr, nloc, c->red_out.as<double>()));
-      CKR(reduce4(c, c->mass.as<double>() + lo, nullptr, nloc, c->red_out.as<double>() + 4));
-    }
-    if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
     auto csr_fill = [&]() -> int {
       const int cap = (int)std::min<size_t>(c->col.cap / 4, c->val.cap / 8);
       const int *skip = c->abort_on_empty ? c->flags.as<int>() + 1 : nullptr;
@@ -1085,13 +1167,96 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       // does not fit and the fill is repeated in the rare case that it did not
       const size_t want = std::max<size_t>((size_t)8 * nloc, 1024);
       if (c->col.cap / 4 < want || c->val.cap / 8 < want) { CKR(ensure(c, c->col, want * 4)); CKR(ensure(c, c->val, want * 8)); }
-      CKR(csr_fill());
-      if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CSR + 1], c->stream));
+    }
+    // Everything the evaluation launches, in stream order (no allocation, no synchronisation in here: the sequence is
+    // captured once per distinct configuration and replayed as a CUDA graph — ~30 launches of which ~20 are tiny).
+    auto enqueue = [&]() -> int {
+      CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
+      if (c->stats) CK(cudaMemsetAsync(c->counters.p, 0, CNT_N * 8, c->stream));
+      if (c->profiling) CK(cudaEventRecord(c->ev[0], c->stream));
+      if (MODE == MODE_KANTOROVICH && c->part_n > 1) {
+        // rows outside this context's Morton tile are empty here (another GPU owns them)
+        const size_t N = c->N, hi = p.cell_hi;
+        auto zero = [&](Buf &b, size_t esz) {
+          if (lo) cudaMemsetAsync(b.p, 0, (size_t)lo * esz, c->stream);
+          if (hi < N) cudaMemsetAsync((char *)b.p + hi * esz, 0, (N - hi) * esz, c->stream);
+        };
+        zero(c->mass, 8); zero(c->fcell, 8); zero(c->touched, 8); zero(c->rowcnt, 4);
+      }
+      if (seg) CKR(run_cells<true>(c, p));
+      else CKR(run_cells<false>(c, p));
+      // (line-search trials: once K2 has found an empty cell the point is rejected whatever the rest says,
+      // optimal_transport.hpp:167 — K3 / K4 then return at once on the device-side flag, the host learns it at the one
+      // synchronisation below)
+      if (seg) CKR(launch_seg_kmax<SEG_MODE>(c, p));
+      else CKR(launch_pieces_mode<MODE>(c, p));
+      if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
+      if (MODE == MODE_KANTOROVICH) {
+        // f, sum m, min m on the side stream while the main stream assembles the Hessian
+        CK(cudaEventRecord(c->ev_fork[2], c->stream));
+        CK(cudaStreamWaitEvent(c->side, c->ev_fork[2], 0));
+        CKR(reduce4x2(c, c->fcell.as<double>() + lo, c->mass.as<double>() + lo, nloc, c->red_out.as<double>(), c->side));
+        CK(cudaEventRecord(c->ev_fork[3], c->side));
+        // row pointers of this context's rows only (rowptr[lo] = 0 ... rowptr[hi] = nnz); rows of other tiles have none
+        if (hess) CKR(scan_i32(c, c->rowcnt.as<int>() + lo, c->rowptr.as<int>() + lo, nloc));
+      }
+      if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_REDUCE + 1], c->stream));
+      if (hess) {
+        CKR(csr_fill());
+        if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CSR + 1], c->stream));
+      }
+      if (MODE == MODE_KANTOROVICH) CK(cudaStreamWaitEvent(c->stream, c->ev_fork[3], 0));
+      return MA_OK;
+    };
+    c->aborted = false;
+    if (c->use_graph && !c->profiling && !c->stats) {
+      // key: every launch argument and dimension is a function of these bytes
+      std::string key((const char *)&p, sizeof p);
+      const void *ptrs[] = {c->w.p, c->perm.p, c->s2rm.p, c->pre0.p, c->pre1.p, c->code_s.p, c->fs_tiles.p, c->hard1.p, c->hard2.p,
+                            c->hard_n.p, c->rowptr.p, c->col.p, c->val.p, c->scan_tmp.p, c->red_partial.p, c->red_partial2.p,
+                            c->red_out.p, c->mom.p};
+      const long long ints[] = {c->warm_now, (long long)(size_t)c->nbr_prev.p, (long long)(size_t)c->cnt_prev.p, MODE, hess, seg, c->lean, c->persist, c->persist_waves, c->persist_min_chunk, c->L, c->sm_count,
+                                (long long)c->col.cap, (long long)c->val.cap, c->part_rank, c->part_n, c->abort_on_empty};
+      key.append((const char *)ptrs, sizeof ptrs);
+      key.append((const char *)ints, sizeof ints);
+      ma_ctx::EvalGraph *g = nullptr;
+      for (auto &e : c->graphs)
+        if (e.key == key) g = &e;
+      if (!g) {
+        const long long l0 = c->launches;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        const int rc_q = enqueue();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e_end = cudaStreamEndCapture(c->stream, &graph);
+        c->planes_pending = false;
+        if (rc_q != MA_OK) { if (graph) cudaGraphDestroy(graph); return rc_q; }
+        if (e_end != cudaSuccess) return fail(c, MA_CUDA_ERROR, "graph capture of the evaluation failed: %s", cudaGetErrorString(e_end));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e_inst != cudaSuccess) return fail(c, MA_CUDA_ERROR, "cudaGraphInstantiate: %s", cudaGetErrorString(e_inst));
+        if (c->graphs.size() >= 8) {  // evict the least recently used
+          size_t o = 0;
+          for (size_t k = 1; k < c->graphs.size(); ++k)
+            if (c->graphs[k].stamp < c->graphs[o].stamp) o = k;
+          cudaGraphExecDestroy(c->graphs[o].exec);
+          c->graphs.erase(c->graphs.begin() + o);
+        }
+        c->graphs.push_back(ma_ctx::EvalGraph{key, exec, (int)(c->launches - l0), 0});
+        c->launches = l0;
+        g = &c->graphs.back();
+      }
+      g->stamp = ++c->graph_clock;
+      CK(cudaGraphLaunch(g->exec, c->stream));
+      c->launches += g->launches;
+    } else {
+      CKR(enqueue());
     }
     CKR(dist_sync_flags(c));  // multi-GPU: every rank learns about an overflow / an empty cell of ANY tile
     if (MODE == MODE_KANTOROVICH) CKR(dist_reduce_eval(c));  // f, sum m, min m over all tiles
     c->hs->flags = 0; c->hs->nnz = 0;
     CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 12, cudaMemcpyDeviceToHost, c->stream));  // flags, abort, K2 exact-stage count
+    if (c->warm_now) CK(cudaMemcpyAsync(c->hs->warm, c->hard_n.p, 32, cudaMemcpyDeviceToHost, c->stream));
     if (MODE == MODE_KANTOROVICH) {
       CK(cudaMemcpyAsync(c->hs->red, c->red_out.p, sizeof c->hs->red, cudaMemcpyDeviceToHost, c->stream));
       if (hess) CK(cudaMemcpyAsync(&c->hs->nnz, c->rowptr.as<int>() + p.cell_hi, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1118,6 +1283,22 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       invalidate_eval(c);
       if (c->trace) fprintf(stderr, "[ma] eval aborted after K2: a cell is empty\n");
       return MA_OK;
+    }
+    if (c->warm_now) {
+      // certified iff the last ring match found nothing and the cells are ONE sheet over the mesh (ma_warm.cuh)
+      const int *wn = c->hs->warm;
+      bool ok = wn[4] == 0;
+      if (ok && MODE == MODE_KANTOROVICH && c->mesh_mass > 0) ok = std::fabs(red[4] - c->mesh_mass) <= 1e-6 * c->mesh_mass;
+      if (c->trace) fprintf(stderr, "[ma] warm K2: rebuilt %d + %d cells, failing cells per match %d %d %d%s\n", wn[0], wn[1], wn[2], wn[3], wn[4], ok ? "" : "  -> redone cold");
+      if (!ok) {
+        c->warm_failed++;
+        c->warm_skip = c->warm_penalty;
+        c->warm_penalty = std::min(c->warm_penalty * 2, 1024);
+        continue;
+      }
+      c->warm_evals++;
+      c->warm_rebuilt += wn[0] + wn[1];
+      c->warm_penalty = 4;
     }
     if (MODE == MODE_KANTOROVICH) {
       c->fval = red[0];
@@ -1151,6 +1332,7 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     }
     c->have_eval = true;
     c->have_hessian = (MODE == MODE_KANTOROVICH) && with_hessian;
+    if (c->warm == 2 && c->kmax == 16 && c->part_n == 1) CKR(save_adjacency(c));
     if (c->trace)
       fprintf(stderr, "[ma] eval kmax=%d attempt=%d total=%.3f prep=%.3f cells=%.3f pieces=%.3f reduce=%.3f csr=%.3f ms  mass_min=%g nnz=%d\n",
               c->kmax, attempt, c->t_ms[MA_T_TOTAL], c->t_ms[MA_T_PREP], c->t_ms[MA_T_CELLS], c->t_ms[MA_T_PIECES],
@@ -1806,16 +1988,6 @@ extern "C" int ma_solve_laplacian(ma_ctx *c, int N, const int *rowptr, const int
 }
 
 namespace {
-// remembers the adjacency of the evaluation just done (an accepted Newton point)
-int save_adjacency(ma_ctx *c) {
-  const size_t N = c->N, K = c->kmax;
-  CKR(ensure(c, c->nbr_prev, N * K * 4));
-  CKR(ensure(c, c->cnt_prev, N * 4));
-  CK(cudaMemcpyAsync(c->nbr_prev.p, c->nbr.p, N * K * 4, cudaMemcpyDeviceToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->cnt_prev.p, c->nbr_cnt.p, N * 4, cudaMemcpyDeviceToDevice, c->stream));
-  c->prev_stride = (int)K;
-  return MA_OK;
-}
 // true in *empty if, at the weights now in c->w, some cell is certainly empty (k_cells_quick_empty)
 int quick_empty(ma_ctx *c, bool *empty) {
   *empty = false;
@@ -1852,6 +2024,11 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
   auto t0 = std::chrono::steady_clock::now();
   const int N = c->N;
   size_t neval = 0, niter = 0, cg_total = 0;
+  struct NewtonScope {  // evaluations inside this call may take the warm path of K2
+    ma_ctx *c;
+    explicit NewtonScope(ma_ctx *c_) : c(c_) { c->in_newton = true; c->warm_skip = 0; c->warm_penalty = 4; }
+    ~NewtonScope() { c->in_newton = false; }
+  } newton_scope(c);
   CKR(ensure(c, c->nu_s, (size_t)N * 8)); CKR(ensure(c, c->x0_s, (size_t)N * 8));
   CKR(ensure(c, c->d_s, (size_t)N * 8)); CKR(ensure(c, c->g_s, (size_t)N * 8));
   CKR(ensure(c, c->scratch_d, (size_t)N * 8));

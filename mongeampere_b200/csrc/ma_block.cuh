@@ -130,7 +130,10 @@ MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv
   // All lanes step through their lists together, candidate t of every lane in iteration t.  (Per-lane cursors with
   // vote-scheduled clips — the CellSearch scheme — were measured on this kernel: 7 % fewer instructions, 15 of 32 lanes
   // instead of 14, but 18 % SLOWER: the candidate loads then issue lane by lane behind data-dependent branches and the
-  // kernel is bound by their latency at 20 warps per SM, profiles/r02g.)
+  // kernel is bound by their latency at 20 warps per SM, profiles/r02g.  Queueing the candidates that pass the disk test
+  // and clipping them in batches, all lanes busy, was measured too: 1.9x SLOWER (2.73 against 1.43 ms of K2 at c3,
+  // profiles/r02k) — a polygon that is clipped late stays large, so far more candidates pass the test and are clipped
+  // at all; clipping the moment a candidate is met is what keeps the work per cell at ~8 clips.)
   const int Tmax = MA_WARP_MAX_INT(T);
   // (the next candidate's coordinates are fetched one iteration ahead: the loads then fly while this one is tested / clipped)
   int npos = (active && 0 < T) ? runs.position(0) : 0;

@@ -78,6 +78,8 @@ struct Params {
   // local coordinates, tag = site index or < 0 for a side of the mesh box; poly_n[i] vertices
   double *poly_x, *poly_y;
   int *poly_t, *poly_n;
+  // warm path (ma_warm.cuh): cyclic edge tags of cell i at ring[16 i ..], ring_n[i] of them; cstate[i] = WARM_*
+  int *ring, *ring_n, *cstate;
   // K3 outputs
   double *mass;     // N
   double *fcell;    // N: m_i w_i - cost_i

@@ -144,6 +144,30 @@ __global__ void __launch_bounds__(RED_NT) k_reduce_stage2(const double *__restri
   block_reduce4(s, q, mn, mx, out);
 }
 
+// two arrays at once (blockIdx.y / blockIdx.x of stage 2 picks the array); same trees as the kernels above
+__global__ void __launch_bounds__(RED_NT) k_reduce2_stage1(const double *__restrict__ a0, const double *__restrict__ a1, int n,
+                                                            double *__restrict__ partial) {
+  const double *__restrict__ a = blockIdx.y ? a1 : a0;
+  double s = 0, q = 0, mn = 1e300, mx = -1e300;
+  for (int i = blockIdx.x * RED_NT + threadIdx.x; i < n; i += gridDim.x * RED_NT) {
+    double v = a[i];
+    s += v;
+    q += v * v;
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+  }
+  block_reduce4(s, q, mn, mx, partial + 4 * (blockIdx.y * RED_BLOCKS + blockIdx.x));
+}
+__global__ void __launch_bounds__(RED_NT) k_reduce2_stage2(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+  partial += 4 * RED_BLOCKS * blockIdx.x;
+  double s = 0, q = 0, mn = 1e300, mx = -1e300;
+  for (int i = threadIdx.x; i < nb; i += RED_NT) {
+    s += partial[4 * i]; q += partial[4 * i + 1];
+    mn = fmin(mn, partial[4 * i + 2]); mx = fmax(mx, partial[4 * i + 3]);
+  }
+  block_reduce4(s, q, mn, mx, out + 4 * blockIdx.x);
+}
+
 // ================================================================================================
 // K1: Morton-ordered uniform bins of the Diracs (once per point set) + per-eval max-weight pyramid
 // ================================================================================================
@@ -546,7 +570,7 @@ template <int MAXV, int NT> constexpr size_t cells_smem_bytes() { return (size_t
 // sizes its chunks itself from the device-side count (the host never reads it); it returns at once when the weights are
 // graded.  list == null with list_n != null is the complementary launch: the whole tile, but only when the weights are
 // graded (the block kernels then did nothing).
-template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K2_MINBLOCKS : 1)) k_cells_persist(Params p, int chunk, const int *__restrict__ list, const int *__restrict__ list_n) {
+template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K2_MINBLOCKS : 1)) k_cells_persist(Params p, int chunk, const int *__restrict__ list, const int *__restrict__ list_n, bool warm = false) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
   double *sy = sx + MAXV * NT;
@@ -559,7 +583,8 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
   if (list) {
     // the cells the block kernels left over; with graded weights those kernels did nothing and the launch with
     // list == null && list_n != null (a full grid, sized for the whole tile) does the work instead
-    if (weights_graded(p)) return;
+    // (warm: the cells the ring match sent back, whatever the weights look like)
+    if (!warm && weights_graded(p)) return;
     lo = 0; hi = *list_n;
     const long long nwarps = (long long)gridDim.x * (NT / 32);
     chunk = (int)max(1ll, ((long long)(hi - lo) + nwarps - 1) / nwarps);
@@ -602,6 +627,10 @@ template <int MAXV, int NT, bool POLY> __global__ void __launch_bounds__(NT, (MA
               const size_t o = (size_t)k * p.N + i;
               p.poly_x[o] = P.X(k); p.poly_y[o] = P.Y(k); p.poly_t[o] = P.T(k);
             }
+          }
+          if (warm) {  // an exact cell from now on
+            ring_store(p.ring, p.ring_n, i, P, n);
+            p.cstate[i] = WARM_EXACT;
           }
         }
         const int idx = next + __popc(finmask & lt_mask);
@@ -689,6 +718,67 @@ __global__ void __launch_bounds__(NT, MA_K2B_MINBLOCKS) k_cells_block(Params p, 
     }
     __syncwarp();
   }
+}
+
+// K2, warm path (ma_warm.cuh), step 1: every cell from the neighbours it had in the seed evaluation.  Cells that cannot
+// be seeded (no seed row, more than 16 vertices on the way) go straight to the list of cells CellSearch rebuilds.
+template <int NT, bool POLY>
+__global__ void __launch_bounds__(NT, 4) k_cells_seed(Params p, const int *__restrict__ seed_nbr, const int *__restrict__ seed_cnt,
+                                                      int *__restrict__ out_list, int *__restrict__ out_n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sx = reinterpret_cast<double *>(smem_raw);
+  double *sy = sx + 16 * NT;
+  int *st = reinterpret_cast<int *>(sy + 16 * NT);
+  typedef PolyRef<NT, true> Poly;
+  const unsigned lane = threadIdx.x & 31u;
+  const int idx = blockIdx.x * NT + threadIdx.x;
+  const int ncell = p.cell_hi - p.cell_lo;
+  if ((idx & ~31) >= ncell) return;  // warp-uniform
+  const bool valid = idx < ncell;
+  const int i = p.cell_lo + (valid ? idx : ncell - 1);
+  Poly P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
+  CellSearch<Poly> S;
+  S.init(p, i, P);
+  const int cnt = valid ? seed_cnt[i] : 0;
+  seed_build(p, S, P, 16, valid && cnt > 0, seed_nbr + (size_t)i * RING_STRIDE, cnt);
+  __syncwarp();
+  // seeded: a polygon (or a proven-empty cell); hard: nothing usable
+  const bool hard = valid && (cnt <= 0 || S.status != 0);
+  if (valid && !hard) {
+    const int n = S.n;
+    if (n == 0 && p.abort_on_empty) p.flags[1] = 1;  // a hidden Dirac: the line search rejects this trial point
+    cell_emit(p, i, P, n);
+    ring_store(p.ring, p.ring_n, i, P, n);
+    p.cstate[i] = n == 0 ? WARM_EXACT : WARM_SEEDED;
+    if (POLY) {
+      p.poly_n[i] = n;
+      for (int k = 0; k < n; ++k) {
+        const size_t o = (size_t)k * p.N + i;
+        p.poly_x[o] = P.X(k); p.poly_y[o] = P.Y(k); p.poly_t[o] = P.T(k);
+      }
+    }
+  }
+  if (hard) { p.ring_n[i] = -1; p.cstate[i] = WARM_QUEUED; }
+  const unsigned hm = __ballot_sync(0xffffffffu, hard);
+  if (hm) {
+    int b = 0;
+    if (lane == (unsigned)(__ffs(hm) - 1)) b = atomicAdd(out_n, __popc(hm));
+    b = __shfl_sync(0xffffffffu, b, __ffs(hm) - 1);
+    if (hard) out_list[b + __popc(hm & ((1u << lane) - 1u))] = i;
+  }
+}
+
+// Step 2: the combinatorial certificate.  The cells of every failing vertex that are not exact yet are appended to
+// out_list (once: the state flips SEEDED -> QUEUED under an atomic); *n_fail counts the cells with a failing vertex.
+__global__ void __launch_bounds__(256) k_cells_match(Params p, int *__restrict__ out_list, int *__restrict__ out_n, int *__restrict__ n_fail) {
+  const int i = p.cell_lo + blockIdx.x * 256 + threadIdx.x;
+  if (i >= p.cell_hi) return;
+  if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return;
+  int *state = p.cstate;
+  const bool ok = ring_match(p.ring, p.ring_n, i, [&](int c) {
+    if (atomicCAS(state + c, (int)WARM_SEEDED, (int)WARM_QUEUED) == WARM_SEEDED) out_list[atomicAdd(out_n, 1)] = c;
+  });
+  if (!ok) atomicAdd(n_fail, 1);
 }
 
 // Line-search trials (optimal_transport.hpp:163-170): most of them are rejected because some cell has become EMPTY.

@@ -29,6 +29,7 @@
 // on the input.  One THREAD handles one cell.  SURVEY.md §7.2 "two regimes", DESIGN.md §3.
 #pragma once
 #include "ma_block.cuh"
+#include "ma_warm.cuh"
 
 namespace ma {
 

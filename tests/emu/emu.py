@@ -16,7 +16,7 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_HERE, "emu_harness.cu")
-    deps = [src] + [os.path.join(_ROOT, "mongeampere_b200", "csrc", f) for f in ("ma_cell.cuh", "ma_geom.cuh", "ma_seg.cuh", "ma_block.cuh")]
+    deps = [src] + [os.path.join(_ROOT, "mongeampere_b200", "csrc", f) for f in ("ma_cell.cuh", "ma_geom.cuh", "ma_seg.cuh", "ma_block.cuh", "ma_warm.cuh")]
     if not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(d) for d in deps):
         return _LIB
     os.makedirs(os.path.dirname(_LIB), exist_ok=True)
@@ -45,9 +45,17 @@ def lean_counts():
     return tuple(out[1:4])
 
 
-def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_target=2, nlanes=32, seg=False):
+def warm_counts():
+    """Warm path of K2 in the last evaluation: (certified, cells rebuilt in round 0, in round 1, failing cells per match x 3)."""
+    out = (C.c_int * 6)()
+    lib().emu_get_warm(out)
+    return tuple(out)
+
+
+def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_target=2, nlanes=32, seg=False, seeds=None):
     """mesh: dict(kind='grid', n, m, x0, y0, x1, y1, abc) or dict(kind='mesh', vx, vy, tri, abc).
-    Returns dict(f, g, H, mom, counters, flags, adjacency)."""
+    seeds: the `seeds` entry of an earlier result for the same X (K2 then takes the warm path, ma_warm.cuh).
+    Returns dict(f, g, H, mom, counters, flags, adjacency, seeds)."""
     X = np.asarray(X, np.float64)
     N = len(X)
     x = np.ascontiguousarray(X[:, 0]); y = np.ascontiguousarray(X[:, 1])
@@ -72,10 +80,18 @@ def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_t
     rho = np.ascontiguousarray(mesh["rho"], np.float64).reshape(-1) if mesh.get("rho") is not None else None
     if seg and mesh["kind"] == "grid":
         assert rho is not None, "the segment path reads the vertex densities"
+    if seeds is not None:
+        assert kmax == 16
+        snbr = np.ascontiguousarray(seeds[0], np.int32); scnt = np.ascontiguousarray(seeds[1], np.int32)
+        lib().emu_set_seeds(p(snbr), p(scnt))
+    else:
+        lib().emu_set_seeds(None, None)
     rc = lib().emu_eval(*gargs, p(abc), p(rho) if rho is not None else None, N, p(x), p(y), p(w), kmax, maxv_piece, mode, C.c_double(filter_tol),
                         bin_target, nlanes, (int(seg) if mesh["kind"] == "grid" else 0), p(perm), p(mass), p(fcell), p(nbr_cnt), p(nbr), p(hslot), p(touched),
                         p(mom), p(counters), C.byref(flags))
     assert rc == 0
+    lib().emu_set_seeds(None, None)
+    raw = dict(mass=mass.copy(), nbr=nbr.copy(), nbr_cnt=nbr_cnt.copy(), hslot=hslot.copy(), fcell=fcell.copy())
     g = np.zeros(N); g[perm] = mass
     momc = np.zeros((N, 6)); momc[perm] = mom.reshape(N, 6)
     # CSR from slots (what k_csr_fill does)
@@ -96,4 +112,4 @@ def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_t
     H = sp.csr_matrix((vals, (rows, cols)), shape=(N, N))
     names = ("pieces", "piece_vertices", "new_vertices", "laguerre_edges", "sum_k", "sum_k_np", "fallbacks", "candidates")
     return dict(f=float(fcell.sum()), g=g, H=H, mom=momc, counters=dict(zip(names, map(int, counters))),
-                flags=flags.value, adjacency=adj)
+                flags=flags.value, adjacency=adj, seeds=(raw["nbr"].reshape(N, kmax), raw["nbr_cnt"]), raw=raw)

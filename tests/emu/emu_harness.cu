@@ -26,6 +26,12 @@ using namespace ma;
 // [0] on/off, [1..3] cells finished by radius 2 / radius 3 / CellSearch in the last evaluation
 static int emu_lean[4] = {0, 0, 0, 0};
 extern "C" void emu_set_lean(int on) { emu_lean[0] = on; }
+// K2 warm path (ma_warm.cuh): seeds = adjacency of an earlier evaluation of the same points, internal order, 16 per cell;
+// emu_warm: [0] used (certified), [1] cells rebuilt in round 0, [2] in round 1, [3..5] failing cells per match
+static const int *emu_seed_nbr = nullptr, *emu_seed_cnt = nullptr;
+static int emu_warm[6] = {0, 0, 0, 0, 0, 0};
+extern "C" void emu_set_seeds(const int *nbr, const int *cnt) { emu_seed_nbr = nbr; emu_seed_cnt = cnt; }
+extern "C" void emu_get_warm(int *out) { for (int k = 0; k < 6; ++k) out[k] = emu_warm[k]; }
 extern "C" void emu_get_lean(int *out) { for (int k = 0; k < 4; ++k) out[k] = emu_lean[k]; }
 
 extern "C" int emu_eval(int mesh_kind,
@@ -223,6 +229,53 @@ extern "C" int emu_eval(int mesh_kind,
   emu_lean[1] = emu_lean[2] = emu_lean[3] = 0;
   // ---- K2 ----
   const int maxv_cell = kmax + 4;
+  // warm path first, as launch_cells_warm does: seed every cell, match, rebuild, match, rebuild, match
+  std::vector<int> ring, ring_n, cstate, WT, WN;
+  std::vector<double> WX, WY;
+  bool warm_ok = false;
+  for (int k = 0; k < 6; ++k) emu_warm[k] = 0;
+  if (emu_seed_nbr && kmax == 16) {
+    ring.assign((size_t)N * RING_STRIDE, -9); ring_n.assign(N, -1); cstate.assign(N, WARM_SEEDED);
+    WX.assign((size_t)N * 16, 0.0); WY.assign((size_t)N * 16, 0.0); WT.assign((size_t)N * 16, 0); WN.assign(N, -2);
+    p.ring = ring.data(); p.ring_n = ring_n.data(); p.cstate = cstate.data();
+    std::vector<double> px(16), py(16);
+    std::vector<int> pt(16);
+    PolyRef<1, true> PP{px.data(), py.data(), pt.data()};
+    std::vector<int> list;
+    auto keep = [&](int i, int n) {
+      WN[i] = n;
+      for (int k = 0; k < n; ++k) { WX[(size_t)i * 16 + k] = PP.X(k); WY[(size_t)i * 16 + k] = PP.Y(k); WT[(size_t)i * 16 + k] = PP.T(k); }
+      ring_store(p.ring, p.ring_n, i, PP, n);
+    };
+    for (int i = 0; i < N; ++i) {
+      CellSearch<PolyRef<1, true>> S;
+      S.init(p, i, PP);
+      const int cnt = emu_seed_cnt[i];
+      seed_build(p, S, PP, 16, cnt > 0, emu_seed_nbr + (size_t)i * RING_STRIDE, cnt);
+      if (cnt <= 0 || S.status != 0) { ring_n[i] = -1; cstate[i] = WARM_QUEUED; list.push_back(i); }
+      else { keep(i, S.n); cstate[i] = S.n == 0 ? WARM_EXACT : WARM_SEEDED; }
+    }
+    for (int round = 0; round < 3; ++round) {
+      int nfail = 0;
+      for (int i = 0; i < N; ++i)
+        if (!ring_match(p.ring, p.ring_n, i, [&](int c) { if (cstate[c] == WARM_SEEDED) { cstate[c] = WARM_QUEUED; list.push_back(c); } })) ++nfail;
+      emu_warm[3 + round] = nfail;
+      if (round == 2) break;
+      emu_warm[1 + round] = (int)list.size();
+      for (int i : list) {
+        int fl = 0;
+        int n = cell_build(p, i, PP, 16, &fl);
+        flags |= fl;
+        if (n < 0) n = 0;
+        keep(i, n);
+        cstate[i] = WARM_EXACT;
+      }
+      list.clear();
+    }
+    warm_ok = emu_warm[5] == 0 && !(flags & (FLAG_CELL_OVERFLOW | FLAG_KMAX_OVERFLOW));
+    emu_warm[0] = warm_ok;
+    if (!warm_ok) flags = 0;  // redone cold below
+  }
   {
     std::vector<double> px(maxv_cell), py(maxv_cell);
     std::vector<int> pt(maxv_cell);
@@ -232,7 +285,13 @@ extern "C" int emu_eval(int mesh_kind,
       PolyRef<1, true> PP{px.data(), py.data(), pt.data()};
       PolyRef<1, false> PA{px.data(), py.data(), pt.data()};
       int n = -2;
-      if (kmax == 16 && emu_lean[0] && !graded) {
+      if (warm_ok) {  // the polygon the warm path certified
+        n = WN[i];
+        for (int k = 0; k < n; ++k) { PP.SX(k) = WX[(size_t)i * 16 + k]; PP.SY(k) = WY[(size_t)i * 16 + k]; PP.ST(k) = WT[(size_t)i * 16 + k]; }
+        PP.ord = 0xfedcba9876543210ull;
+        PP.used = (1u << n) - 1u;
+      }
+      if (n == -2 && kmax == 16 && emu_lean[0] && !graded) {
         {  // pass 1: block of radius 2; pass 2 continues from its polygon with the ring around it; pass 3: radius 5 from scratch
           CellSearch<PolyRef<1, true>> S;
           S.init(p, i, PP);

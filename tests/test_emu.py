@@ -280,3 +280,101 @@ def test_segment_path_many_boundary_cells(oracle_mod, emu_mod):
         assert np.abs(r["g"] - g0).max() <= 1e-11 * np.abs(g0).max()
         assert common.same_pattern(H0, r["H"])
         assert abs(H0 - r["H"]).max() <= 1e-11 * np.abs(H0.diagonal()).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 warm path (ma_warm.cuh): cells from the adjacency of an earlier evaluation + the ring-match certificate
+# ------------------------------------------------------------------------------------------------
+def _graded(case, amp, seed):
+    """Smooth weights with a large gradient (cells displaced from their Diracs) plus noise, the Newton-iterate regime."""
+    X = case["X"]
+    ext = X.max(0) - X.min(0)
+    u = (X - X.min(0)) / ext
+    cell = ext.prod() / len(X)
+    rng = np.random.default_rng(seed)
+    return amp * ext.prod() * (0.3 * np.sin(2.1 * u[:, 0] + 0.3) * np.cos(1.7 * u[:, 1]) + 0.1 * u[:, 0] * u[:, 1]) + 0.03 * cell * rng.normal(size=len(X))
+
+
+def _same_raw(a, b):
+    """Same cells: identical neighbour sets (the polygons may start at another vertex, so slot order and the last bits of
+    the sums may differ), values equal to rounding."""
+    assert a["flags"] == b["flags"] == 0
+    assert a["adjacency"] == b["adjacency"]
+    assert np.array_equal(a["raw"]["nbr_cnt"], b["raw"]["nbr_cnt"])
+    assert np.abs(a["g"] - b["g"]).max() <= 1e-14 * np.abs(a["g"]).max()
+    assert abs(a["f"] - b["f"]) <= 1e-13 * abs(a["f"])
+    assert common.same_pattern(a["H"], b["H"])
+    assert abs(a["H"] - b["H"]).max() <= 1e-13 * np.abs(a["H"].diagonal()).max()
+
+
+@pytest.mark.parametrize("name,scale,seg", [("c3", 0.002, True), ("c2", 0.02, True), ("c1", 0.2, False)])
+@pytest.mark.parametrize("step", [0.02, 0.3])
+def test_warm_path_gives_the_cells_of_the_cold_one(emu_mod, name, scale, seg, step):
+    """Seeds from an evaluation at w1; the evaluation at w2 = w1 + step * (another graded field) through the warm path must
+    give the same cells as without seeds: identical adjacency, masses and Hessian equal to rounding.  A small step rebuilds a few cells,
+    a large one a good part of them — the certificate decides, never the answer."""
+    case = common.make_case(name, scale, "zero")
+    w1 = _graded(case, 0.05, 1)
+    w2 = w1 + step * _graded(case, 0.05, 2)
+    first = emu_mod.evaluate(case["emu_mesh"], case["X"], w1, seg=seg)
+    cold = emu_mod.evaluate(case["emu_mesh"], case["X"], w2, seg=seg)
+    warm = emu_mod.evaluate(case["emu_mesh"], case["X"], w2, seg=seg, seeds=first["seeds"])
+    used, r0, r1, f0, f1, f2 = emu_mod.warm_counts()
+    assert used == 1 and f2 == 0
+    N = case["N"]
+    assert r0 + r1 < (0.25 if step < 0.1 else 0.95) * N, (r0, r1, N)
+    _same_raw(cold, warm)
+
+
+def test_warm_path_with_identical_weights_rebuilds_nothing(emu_mod):
+    case = common.make_case("c3", 0.002, "zero")
+    w = _graded(case, 0.05, 3)
+    first = emu_mod.evaluate(case["emu_mesh"], case["X"], w, seg=True)
+    warm = emu_mod.evaluate(case["emu_mesh"], case["X"], w, seg=True, seeds=first["seeds"])
+    hidden = int((first["raw"]["nbr_cnt"] < 0).sum())  # no seed row: CellSearch has to look (the cell may have come back)
+    assert emu_mod.warm_counts() == (1, hidden, 0, hidden, 0, 0)
+    _same_raw(first, warm)
+
+
+def test_ring_match_holds_on_every_cold_diagram(emu_mod):
+    """The certificate itself: with seeds = the TRUE adjacency the match must pass at every vertex — interior vertices
+    (three cells), vertices on the sides of the box (two cells) and the corners — on uniform and on graded weights."""
+    for name, scale, weights in (("c2", 0.01, "zero"), ("c1", 0.1, "0.4"), ("c5", 0.0003, "0.2")):
+        case = common.make_case(name, scale, weights)
+        first = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"])
+        again = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], seeds=first["seeds"])
+        hidden = int((first["raw"]["nbr_cnt"] < 0).sum())
+        assert emu_mod.warm_counts() == (1, hidden, 0, hidden, 0, 0), (name, emu_mod.warm_counts())
+        _same_raw(first, again)
+
+
+def test_warm_path_with_hidden_and_emptied_cells(emu_mod):
+    """A Dirac that is hidden in the seed evaluation has no seed row (rebuilt by CellSearch); one that becomes hidden at
+    the new weights is found empty on its superset.  Either way the answer is the cold one."""
+    case = common.make_case("c2", 0.01, "zero")
+    N = case["N"]
+    w1 = np.zeros(N)
+    w1[5] = -1.0  # hidden in the seed evaluation
+    first = emu_mod.evaluate(case["emu_mesh"], case["X"], w1, seg=True)
+    w2 = np.zeros(N)
+    w2[7] = -1.0  # hidden now
+    cold = emu_mod.evaluate(case["emu_mesh"], case["X"], w2, seg=True)
+    warm = emu_mod.evaluate(case["emu_mesh"], case["X"], w2, seg=True, seeds=first["seeds"])
+    assert emu_mod.warm_counts()[0] == 1
+    assert cold["g"][7] == 0.0 and cold["g"][5] > 0.0
+    _same_raw(cold, warm)
+
+
+def test_warm_path_gives_up_on_degenerate_lattices(emu_mod):
+    """Co-circular quadruples everywhere: with ties outside the rings of the four cells round a vertex do not pair up, the
+    last match still reports failures and the evaluation is redone without seeds — same answer, no certificate claimed."""
+    n = 12
+    g = (np.arange(n) + 0.5) / n * 2 - 1
+    X = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    case = common.make_case("c2", 0.004, "zero")
+    w = np.zeros(len(X))
+    first = emu_mod.evaluate(case["emu_mesh"], X, w, seg=True)
+    warm = emu_mod.evaluate(case["emu_mesh"], X, w, seg=True, seeds=first["seeds"])
+    used = emu_mod.warm_counts()[0]
+    _same_raw(first, warm)
+    assert used in (0, 1)

@@ -100,6 +100,18 @@ def test_newton_trajectory_matches_oracle(gpu_ctx, oracle_mod, name, scale):
     assert np.abs((x1 - x1[-1]) - (x0 - x0[-1])).max() <= 1e-8
     f0 = orc.kantorovich(x0, mode=oracle_mod.MODE_PER_CELL)[0] - nu.dot(x0)
     assert abs(st1["fval"] - f0) <= 1e-8 * abs(f0)
+    # the solve above went through the warm path of K2 (cells seeded from the last accepted point + ring match); without
+    # it — every evaluation a full neighbour search — the trajectory and the weights are the same
+    warm_evals = gpu_ctx.info("warm_evals")
+    assert warm_evals > 0.5 * st1["niter"], (warm_evals, gpu_ctx.info("warm_failed"), st1)
+    gpu_ctx.set_option("warm", 0)
+    try:
+        x2, st2, rc2 = gpu_ctx.ot_solve(nu, eps_g=1e-7, maxiter=1000)
+    finally:
+        gpu_ctx.set_option("warm", 1)
+    assert rc2 == 0 and gpu_ctx.info("warm_evals") == warm_evals
+    assert (st2["niter"], st2["neval"], st2["cg_iters"]) == (st1["niter"], st1["neval"], st1["cg_iters"])
+    assert np.abs(x2 - x1).max() <= 1e-13 * max(1.0, np.abs(x1).max())
 
 
 def test_c4_moments_at_a_tenth(gpu_ctx, oracle_mod):
