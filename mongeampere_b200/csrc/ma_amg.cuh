@@ -23,7 +23,11 @@
 namespace ma {
 
 constexpr int AMG_MAX_LEVELS = 16;
-constexpr int AMG_DENSE_MAX = 320;   // the last level is solved with an explicit dense inverse
+constexpr int AMG_DENSE_MAX = 80;    // the last level (64 rows: quadtree level 3) is solved with an explicit dense inverse;
+                                     // at 256 rows the one-block Gauss-Jordan cost 6.5 ms per solve and the apply 35 us per
+                                     // PCG iteration (profiles/r02n), a fifth of the Newton solve at 1 M Diracs
+constexpr int AMG_TAIL_ROWS = 4096;  // levels with at most this many rows run inside ONE block (k_amg_tail)
+constexpr int AMG_TAIL_MAX = 8;
 constexpr int AMG_ROW_CAP = 96;      // distinct columns one coarse row may have while it is merged
 
 struct AmgLevel {
@@ -171,18 +175,83 @@ __global__ void __launch_bounds__(256) k_amg_restrict(int nc, const int *__restr
     rc[c] = s;
   }
 }
-// last level: e = Ainv r, one block
-__global__ void __launch_bounds__(AMG_DENSE_MAX) k_amg_dense_apply(int n, const double *__restrict__ Ainv,
-                                                                  const double *__restrict__ r, double *__restrict__ e) {
-  __shared__ double sr[AMG_DENSE_MAX];
-  if ((int)threadIdx.x < n) sr[threadIdx.x] = r[threadIdx.x];
-  __syncthreads();
-  if ((int)threadIdx.x >= n) return;
-  const double *row = Ainv + (size_t)threadIdx.x;  // symmetric: column threadIdx.x, coalesced across the block
-  double s = 0.0;
-  for (int k = 0; k < n; ++k) s += row[(size_t)k * n] * sr[k];
-  e[threadIdx.x] = s;
+// The coarse end of the V-cycle in ONE launch.  Levels of a few thousand rows are pure launch latency as separate
+// kernels (3 per level, ~7 us each against ~1 us of work: 120 of the 280 us of a PCG iteration at 1 M rows,
+// profiles/r02n); here one block of 1024 threads walks down from the first level with <= AMG_TAIL_ROWS rows to the
+// dense level and back up, a __syncthreads between the phases.  Same arithmetic in the same order as the kernels below.
+struct AmgTail {
+  int nlev;                    // lev[0] = first level of the tail ... lev[nlev - 1] = the dense level
+  AmgLevel lev[AMG_TAIL_MAX];
+  const double *Ainv;
+};
+__global__ void __launch_bounds__(1024) k_amg_tail(AmgTail T, double omega, double alpha) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int l = 0; l + 1 < T.nlev; ++l) {
+    const AmgLevel &L = T.lev[l];
+    for (int i = tid; i < L.n; i += nt) {  // k_amg_down
+      const double ri = L.r[i];
+      double acc = 0.0;
+      const int k1 = L.rowptr[i + 1];
+      for (int k = L.rowptr[i]; k < k1; k += 4) {
+        int j[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool in = k + u < k1;
+          j[u] = in ? L.col[k + u] : i;
+          v[u] = in ? L.val[k + u] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += v[u] * (L.dinv[j[u]] * L.r[j[u]]);
+      }
+      L.x[i] = omega * L.dinv[i] * ri;
+      L.t[i] = ri - omega * acc;
+    }
+    __syncthreads();
+    const AmgLevel &C = T.lev[l + 1];
+    for (int c = tid; c < C.n; c += nt) {  // k_amg_restrict
+      double s = 0.0;
+      for (int i = L.cstart[c]; i < L.cstart[c + 1]; ++i) s += L.t[i];
+      C.r[c] = s;
+    }
+    __syncthreads();
+  }
+  {  // k_amg_dense_apply
+    const AmgLevel &D = T.lev[T.nlev - 1];
+    for (int i = tid; i < D.n; i += nt) {
+      const double *row = T.Ainv + (size_t)i;
+      double s = 0.0;
+      for (int k = 0; k < D.n; ++k) s += row[(size_t)k * D.n] * D.r[k];
+      D.x2[i] = s;
+    }
+    __syncthreads();
+  }
+  for (int l = T.nlev - 2; l >= 0; --l) {  // k_amg_up<false>
+    const AmgLevel &L = T.lev[l];
+    const double *ec = T.lev[l + 1].x2;
+    for (int i = tid; i < L.n; i += nt) {
+      const double ri = L.r[i];
+      const double xi = L.x[i] + alpha * ec[L.agg[i]];
+      double acc = 0.0;
+      const int k1 = L.rowptr[i + 1];
+      for (int k = L.rowptr[i]; k < k1; k += 4) {
+        int j[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool in = k + u < k1;
+          j[u] = in ? L.col[k + u] : i;
+          v[u] = in ? L.val[k + u] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += v[u] * (L.x[j[u]] + alpha * ec[L.agg[j[u]]]);
+      }
+      L.x2[i] = xi + omega * L.dinv[i] * (ri - acc);
+    }
+    __syncthreads();
+  }
 }
+
 // up (one thread per row): x' = x + alpha e_coarse[agg], then one Jacobi sweep x2 = x' + omega D^-1 (r - A x').
 // On the finest level x2 is z = M^-1 r and the kernel also leaves the partial sums of r.z in part_rz (fixed grid).
 template <bool FINE>

@@ -984,7 +984,11 @@ template <int MAXV, int NT, bool POLY> int launch_cells(ma_ctx *c, const Params 
     if (c->lean && c->persist) return launch_cells_lean<NT, POLY>(c, p);
   }
   CKR(join_planes(c));
-  if (c->persist) {
+  // The larger capacity classes (array polygons) run one cell per lane: k_cells_persist<36 / 64> does not finish on graded
+  // weights at 1 M Diracs (seen at c5 x 4 M and c3 x 1 M with kmax = 32, profiles/r02q: > 30 s against 47 ms for k_cells on
+  // the same input, whatever the scheduling knobs; the 16-vertex instantiation is not affected).  Not understood yet; these
+  // classes are the rare fallback (P(n >= 17) ~ 5e-10 per cell on random points), so they take the slower, proven kernel.
+  if (c->persist && MAXV == 16) {
     // persistent lanes: each warp owns `chunk` consecutive cells; about 3 waves of resident blocks
     CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int per_sm = 1;
@@ -1170,6 +1174,13 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     }
     // Everything the evaluation launches, in stream order (no allocation, no synchronisation in here: the sequence is
     // captured once per distinct configuration and replayed as a CUDA graph — ~30 launches of which ~20 are tiny).
+    auto stage = [&](const char *what) {  // MA_TRACE=2: synchronise after every stage and say which one just ended
+      if (c->trace < 2) return;
+      const cudaError_t e = cudaStreamSynchronize(c->stream);
+      static auto t_first = std::chrono::steady_clock::now();
+      const double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_first).count();
+      fprintf(stderr, "[ma]   %9.3f s  stage %s done (kmax=%d, abort_on_empty=%d)%s%s\n", t, what, c->kmax, (int)c->abort_on_empty, e == cudaSuccess ? "" : ": ", e == cudaSuccess ? "" : cudaGetErrorString(e));
+    };
     auto enqueue = [&]() -> int {
       CK(cudaMemsetAsync(c->flags.p, 0, 16, c->stream));
       if (c->stats) CK(cudaMemsetAsync(c->counters.p, 0, CNT_N * 8, c->stream));
@@ -1185,12 +1196,14 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       }
       if (seg) CKR(run_cells<true>(c, p));
       else CKR(run_cells<false>(c, p));
+      stage("K1+K2");
       // (line-search trials: once K2 has found an empty cell the point is rejected whatever the rest says,
       // optimal_transport.hpp:167 — K3 / K4 then return at once on the device-side flag, the host learns it at the one
       // synchronisation below)
       if (seg) CKR(launch_seg_kmax<SEG_MODE>(c, p));
       else CKR(launch_pieces_mode<MODE>(c, p));
       if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_PIECES + 1], c->stream));
+      stage("K3");
       if (MODE == MODE_KANTOROVICH) {
         // f, sum m, min m on the side stream while the main stream assembles the Hessian
         CK(cudaEventRecord(c->ev_fork[2], c->stream));
@@ -1206,6 +1219,7 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
         if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_CSR + 1], c->stream));
       }
       if (MODE == MODE_KANTOROVICH) CK(cudaStreamWaitEvent(c->stream, c->ev_fork[3], 0));
+      stage("scan + K4 + reductions");
       return MA_OK;
     };
     c->aborted = false;
@@ -1252,11 +1266,13 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     } else {
       CKR(enqueue());
     }
+    const bool was_warm = c->warm_now;
+    c->warm_now = false;  // (ma_cells_build / ma_pieces_build share launch_cells: they never take the warm path)
     CKR(dist_sync_flags(c));  // multi-GPU: every rank learns about an overflow / an empty cell of ANY tile
     if (MODE == MODE_KANTOROVICH) CKR(dist_reduce_eval(c));  // f, sum m, min m over all tiles
     c->hs->flags = 0; c->hs->nnz = 0;
     CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 12, cudaMemcpyDeviceToHost, c->stream));  // flags, abort, K2 exact-stage count
-    if (c->warm_now) CK(cudaMemcpyAsync(c->hs->warm, c->hard_n.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    if (was_warm) CK(cudaMemcpyAsync(c->hs->warm, c->hard_n.p, 32, cudaMemcpyDeviceToHost, c->stream));
     if (MODE == MODE_KANTOROVICH) {
       CK(cudaMemcpyAsync(c->hs->red, c->red_out.p, sizeof c->hs->red, cudaMemcpyDeviceToHost, c->stream));
       if (hess) CK(cudaMemcpyAsync(&c->hs->nnz, c->rowptr.as<int>() + p.cell_hi, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1284,7 +1300,7 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       if (c->trace) fprintf(stderr, "[ma] eval aborted after K2: a cell is empty\n");
       return MA_OK;
     }
-    if (c->warm_now) {
+    if (was_warm) {
       // certified iff the last ring match found nothing and the cells are ONE sheet over the mesh (ma_warm.cuh)
       const int *wn = c->hs->warm;
       bool ok = wn[4] == 0;
@@ -1815,14 +1831,23 @@ int amg_vcycle(ma_ctx *c, const double *r, double *z, double *part_rz, int nbloc
   const double omega = c->amg_omega, alpha = c->amg_alpha;
   auto grid = [&](int n) { return std::max(1, std::min(cdiv(n, 256), c->sm_count * 8)); };
   const int last = A.nlev - 1;
-  for (int l = 0; l < last; ++l) {
+  // the levels from `tail` on run in one block (k_amg_tail); tail == last: only the dense level is left for it
+  int tail = last;
+  while (tail > 1 && A.n[tail - 1] <= AMG_TAIL_ROWS && last - (tail - 1) < AMG_TAIL_MAX) --tail;
+  for (int l = 0; l < tail; ++l) {
     const AmgLevel &L = A.lev[l];
     const double *rl = l == 0 ? r : L.r;
     k_amg_down<<<grid(L.n), 256, 0, c->stream>>>(L.n, L.rowptr, L.col, L.val, L.dinv, rl, omega, l == 0 ? ground : -1, L.x, L.t);
     k_amg_restrict<<<grid(A.n[l + 1]), 256, 0, c->stream>>>(A.n[l + 1], L.cstart, L.t, A.lev[l + 1].r);
   }
-  k_amg_dense_apply<<<1, AMG_DENSE_MAX, 0, c->stream>>>(A.lev[last].n, A.Ainv.as<double>(), A.lev[last].r, A.lev[last].x2);
-  for (int l = last - 1; l >= 0; --l) {
+  {
+    AmgTail T;
+    T.nlev = last - tail + 1;
+    for (int l = tail; l <= last; ++l) T.lev[l - tail] = A.lev[l];
+    T.Ainv = A.Ainv.as<double>();
+    k_amg_tail<<<1, 1024, 0, c->stream>>>(T, omega, alpha);
+  }
+  for (int l = tail - 1; l >= 0; --l) {
     const AmgLevel &L = A.lev[l];
     const double *ec = A.lev[l + 1].x2;
     if (l == 0)
@@ -1830,7 +1855,7 @@ int amg_vcycle(ma_ctx *c, const double *r, double *z, double *part_rz, int nbloc
     else
       k_amg_up<false><<<grid(L.n), 256, 0, c->stream>>>(L.n, L.rowptr, L.col, L.val, L.dinv, L.r, L.x, L.agg, ec, alpha, omega, -1, L.x2, nullptr);
   }
-  c->launches += 3 * last + 1;
+  c->launches += 3 * tail + 1;
   CK(cudaGetLastError());
   return MA_OK;
 }
