@@ -86,6 +86,8 @@ struct ma_ctx {
   int prev_stride = 0;
   double mesh_mass = 0.0;  // integral of the density over the mesh (the warm path's sheet count)
   bool in_newton = false;
+  bool seeds_global = false;  // multi-GPU: nbr_prev holds the rows of ALL tiles (gathered, or left by a warm evaluation)
+  bool k2_all = false;        // the last evaluation's K2 covered all cells (warm path on a partitioned context)
   // warm path of K2 (ma_warm.cuh): cells from that adjacency + the ring-match certificate
   Buf ring, ring_n, cstate;
   int warm = 1;            // 0: off; 1: inside ma_ot_solve; 2: every evaluation seeds the next one
@@ -134,7 +136,7 @@ struct ma_ctx {
   // L2 flush
   Buf flush;
   // pinned host staging for the scalars read back every evaluation (pageable copies are staged and slow)
-  struct HostScalars { int flags, abort_, cell_fallbacks, pad, nnz, pad2[3]; double red[8]; int warm[8]; } *hs = nullptr;  // flags..pad mirror the device flags[4]
+  struct HostScalars { int flags, abort_, cell_fallbacks, warm_fail, nnz, pad2[3]; double red[8]; int warm[8]; } *hs = nullptr;  // flags..pad mirror the device flags[4]
 
   // timing
   cudaEvent_t ev[MA_T_COUNT + 2] = {};
@@ -732,12 +734,14 @@ __global__ void k_flags_unpack(const int *__restrict__ flags, int *__restrict__ 
   if (threadIdx.x < 4) out[threadIdx.x] = (flags[0] >> threadIdx.x) & 1;
   if (threadIdx.x == 4) out[4] = flags[1] != 0;
   if (threadIdx.x == 5) out[5] = flags[2] > 0;
+  if (threadIdx.x == 6) out[6] = flags[3] != 0;  // warm path: a vertex still failed the last ring match
 }
 __global__ void k_flags_pack(const int *__restrict__ in, int *__restrict__ flags) {
   if (threadIdx.x == 0) {
     flags[0] = (in[0] ? 1 : 0) | (in[1] ? 2 : 0) | (in[2] ? 4 : 0) | (in[3] ? 8 : 0);
     flags[1] = in[4];
     flags[2] = max(flags[2], in[5]);
+    flags[3] = in[6];
   }
 }
 // every rank leaves with the union of all ranks' flags (they then take the same branch: escalate / abort / go on)
@@ -746,7 +750,7 @@ int dist_sync_flags(ma_ctx *c) {
   CKR(ensure(c, c->dist_buf, 256));
   int *b = c->dist_buf.as<int>();
   k_flags_unpack<<<1, 32, 0, c->stream>>>(c->flags.as<int>(), b);
-  NCK(nccl_api().AllReduce(b, b, 6, ncclInt32, ncclMax, (ncclComm_t)c->comm, c->stream));
+  NCK(nccl_api().AllReduce(b, b, 7, ncclInt32, ncclMax, (ncclComm_t)c->comm, c->stream));
   k_flags_pack<<<1, 32, 0, c->stream>>>(b, c->flags.as<int>());
   c->launches += 2;
   return MA_OK;
@@ -953,11 +957,16 @@ template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
 
 // K2 warm path (ma_warm.cuh): seed every cell from the saved adjacency, certify by ring matching, let CellSearch rebuild
 // the cells around every failing vertex, twice; the count of the last match goes to the host with the other scalars.
-template <int NT, bool POLY> int launch_cells_warm(ma_ctx *c, const Params &p) {
+template <int NT, bool POLY> int launch_cells_warm(ma_ctx *c, const Params &tile) {
   constexpr int MAXV = 16;
   const size_t sm = cells_smem_bytes<MAXV, NT>();
-  const int ncells = p.cell_hi - p.cell_lo;
-  int *cnt = c->hard_n.as<int>();  // [0], [1]: lengths of the two rebuild lists, [5]: of the last match's; [2..4]: failing cells per match
+  // The certificate is global (every vertex of every cell): with the Diracs partitioned over several GPUs each rank runs
+  // this stage on ALL cells — a couple of ms at 1 M Diracs, what the sharded quadtree walk costs on 8 GPUs — and K3 / K4
+  // on its own tile; every rank reaches the same verdict from the same inputs.
+  Params p = tile;
+  p.cell_lo = 0; p.cell_hi = p.N;
+  const int ncells = p.N;
+  int *cnt = c->hard_n.as<int>();  // [0], [1]: lengths of the two rebuild lists, [5]: of the last match's; [2], [3]: failing cells per match
   CK(cudaMemsetAsync(cnt, 0, 32, c->stream));
   CK(cudaFuncSetAttribute(k_cells_seed<NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -970,7 +979,7 @@ template <int NT, bool POLY> int launch_cells_warm(ma_ctx *c, const Params &p) {
   k_cells_persist<MAXV, NT, POLY><<<c->sm_count * std::max(per_sm, 1), NT, sm, c->stream>>>(p, 1, c->hard1.as<int>(), cnt, true);
   k_cells_match<<<nblk_m, 256, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, cnt + 3);
   k_cells_persist<MAXV, NT, POLY><<<c->sm_count * 2, NT, sm, c->stream>>>(p, 1, c->hard2.as<int>(), cnt + 1, true);
-  k_cells_match<<<nblk_m, 256, 0, c->stream>>>(p, c->hard1.as<int>(), cnt + 5, cnt + 4);
+  k_cells_match<<<nblk_m, 256, 0, c->stream>>>(p, c->hard1.as<int>(), cnt + 5, p.flags + 3);  // the verdict: flags[3] failing cells
   c->launches += 6;
   CK(cudaGetLastError());
   return MA_OK;
@@ -1123,6 +1132,13 @@ int save_adjacency(ma_ctx *c) {
   CK(cudaMemcpyAsync(c->nbr_prev.p, c->nbr.p, N * K * 4, cudaMemcpyDeviceToDevice, c->stream));
   CK(cudaMemcpyAsync(c->cnt_prev.p, c->nbr_cnt.p, N * 4, cudaMemcpyDeviceToDevice, c->stream));
   c->prev_stride = (int)K;
+  c->seeds_global = c->part_n == 1 || c->k2_all;
+  if (c->comm && c->part_n > 1 && !c->k2_all && c->warm && K == RING_STRIDE) {
+    // a cold evaluation knows its own tile only: the warm path wants the rows of all tiles on every rank
+    CKR(dist_gather_slices(c, c->nbr_prev.p, K * 4));
+    CKR(dist_gather_slices(c, c->cnt_prev.p, 4));
+    c->seeds_global = true;
+  }
   return MA_OK;
 }
 
@@ -1135,7 +1151,7 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
   for (int attempt = 0; attempt < 4; ++attempt) {
     // warm path of K2: the adjacency of an earlier evaluation of these points seeds this one (ma_warm.cuh)
     c->warm_now = false;
-    if (c->warm && (c->warm == 2 || c->in_newton) && c->kmax == 16 && c->part_n == 1 && c->prev_stride == RING_STRIDE && c->persist &&
+    if (c->warm && (c->warm == 2 || c->in_newton) && c->kmax == 16 && (c->part_n == 1 || (c->comm && c->seeds_global)) && c->prev_stride == RING_STRIDE && c->persist &&
         (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2)) {
       if (c->warm_skip > 0) --c->warm_skip;
       else c->warm_now = true;
@@ -1267,11 +1283,12 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       CKR(enqueue());
     }
     const bool was_warm = c->warm_now;
+    c->k2_all = was_warm || c->part_n == 1;
     c->warm_now = false;  // (ma_cells_build / ma_pieces_build share launch_cells: they never take the warm path)
     CKR(dist_sync_flags(c));  // multi-GPU: every rank learns about an overflow / an empty cell of ANY tile
     if (MODE == MODE_KANTOROVICH) CKR(dist_reduce_eval(c));  // f, sum m, min m over all tiles
     c->hs->flags = 0; c->hs->nnz = 0;
-    CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 12, cudaMemcpyDeviceToHost, c->stream));  // flags, abort, K2 exact-stage count
+    CK(cudaMemcpyAsync(&c->hs->flags, c->flags.p, 16, cudaMemcpyDeviceToHost, c->stream));  // flags, abort, K2 exact-stage count, warm-path failures
     if (was_warm) CK(cudaMemcpyAsync(c->hs->warm, c->hard_n.p, 32, cudaMemcpyDeviceToHost, c->stream));
     if (MODE == MODE_KANTOROVICH) {
       CK(cudaMemcpyAsync(c->hs->red, c->red_out.p, sizeof c->hs->red, cudaMemcpyDeviceToHost, c->stream));
@@ -1303,9 +1320,9 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     if (was_warm) {
       // certified iff the last ring match found nothing and the cells are ONE sheet over the mesh (ma_warm.cuh)
       const int *wn = c->hs->warm;
-      bool ok = wn[4] == 0;
+      bool ok = c->hs->warm_fail == 0;
       if (ok && MODE == MODE_KANTOROVICH && c->mesh_mass > 0) ok = std::fabs(red[4] - c->mesh_mass) <= 1e-6 * c->mesh_mass;
-      if (c->trace) fprintf(stderr, "[ma] warm K2: rebuilt %d + %d cells, failing cells per match %d %d %d%s\n", wn[0], wn[1], wn[2], wn[3], wn[4], ok ? "" : "  -> redone cold");
+      if (c->trace) fprintf(stderr, "[ma] warm K2: rebuilt %d + %d cells, failing cells per match %d %d %d%s\n", wn[0], wn[1], wn[2], wn[3], c->hs->warm_fail, ok ? "" : "  -> redone cold");
       if (!ok) {
         c->warm_failed++;
         c->warm_skip = c->warm_penalty;
@@ -2077,6 +2094,7 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
     return std::chrono::duration<double>(b - a).count();
   };
   c->prev_stride = 0;  // no adjacency of an accepted point yet
+  c->seeds_global = false;
   auto feval_inner = [&]() -> int {
     ++neval;
     if (neval > 1) {  // a line-search trial: first the cheap "is some cell already empty?" test
