@@ -383,7 +383,7 @@ def main_b200(args, rank, world, local_rank):
                   "status": capi.STATUS_NAMES[rc], "niter": st["niter"], "neval": st["neval"],
                   "cg_iters": st["cg_iters"], "final_norm": st["final_norm"], "eps_g": 1e-7,
                   "maxiter": args.newton_maxiter, "gpus": world,
-                  "linear_solver": "PCG, quadtree-aggregation multigrid V(1,1) preconditioner, rtol 1e-12"}
+                  "linear_solver": "PCG, quadtree-aggregation multigrid V(1,1) preconditioner, rtol %g" % nctx.info("cg_rtol")}
         nctx.close()
 
     cpu = None

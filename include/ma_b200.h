@@ -215,17 +215,24 @@ int ma_measure_fp64_peak(ma_ctx *ctx, double *flops_per_s);
  *   "block_target" (1)     average Diracs per bin of the block grid, takes effect at the next ma_set_points
  *   "persist" (1)          CellSearch with persistent lanes (k_cells_persist) or one cell per lane (0)
  *   "persist_waves", "persist_min_chunk", "clip_a", "clip_b", "refill_at"   scheduling of k_cells_persist
- *   "cg_rtol" (1e-12), "cg_maxit" (200000)   PCG stopping rule, relative to |g|
+ *   "cg_rtol" (1e-10), "cg_maxit" (200000)   PCG stopping rule, relative to |g|
  *   "amg" (1), "amg_omega" (0.7), "amg_alpha" (1.5)   quadtree-aggregation multigrid preconditioner of the Newton solves
  *                          (0: Jacobi), its smoother damping and the scaling of the coarse correction
  *   "quick_reject" (1)     ma_ot_solve tests a trial point for an empty cell against the adjacency of the last accepted
  *                          point before it evaluates it (same outcome, optimal_transport.hpp:167)
+ *   "warm" (1)             K2 inside ma_ot_solve starts from the adjacency of the last accepted point and certifies the cells by
+ *                          ring matching (ma_warm.cuh); 2: every evaluation seeds the next one of the same point set; 0: off
+ *   "newton_sharded" (0)   ma_ot_solve on a communicator: 1 = evaluations sharded over the ranks (collectives per trial),
+ *                          0 = every rank runs the whole loop (faster at <= a few million Diracs; same bits either way)
+ *   "graph" (1)            evaluations are replayed as CUDA graphs;  "k3_overlap" (0)  K3 of the cells the first block kernel
+ *                          certifies runs on a side stream under the tail of K2 (measured: no gain)
  *   "filter_tol" (1e-11)   relative threshold below which a sign is re-decided in double-double (K2 and k_pieces);
  *                          1e300 sends every decision through the exact stage
  *   "abort_on_empty" (0)   see ma_cells_build
  * Read-outs (ma_get_info): "N", "nF", "nnz", "kmax", "levels", "mesh_kind", "strategy", "sm_count", "fval", "mass_sum",
  *   "mass_min", "cg_iters", "launches", "cell_lo", "cell_hi", "aborted", "cell_fallbacks" (sign decisions of the last
- *   evaluation's K2 that went through the exact stage). */
+ *   evaluation's K2 that went through the exact stage), "warm_evals" / "warm_rebuilt" / "warm_failed" (evaluations certified
+ *   by the warm path, cells CellSearch rebuilt in them, attempts that had to be redone without seeds), "cg_rtol". */
 int ma_set_option(ma_ctx *ctx, const char *name, double value);
 double ma_get_info(ma_ctx *ctx, const char *name);
 

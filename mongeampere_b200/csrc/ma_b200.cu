@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -35,8 +36,13 @@ struct ma_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // copy stream of ma_get_hessian_csr
   cudaStream_t side = nullptr;      // evaluation: work that is off the critical path (supporting planes, scalar reductions)
-  cudaEvent_t ev_fork[4] = {};
+  cudaEvent_t ev_fork[6] = {};
+  std::function<int()> k3_early;  // set by the evaluation: launches k_seg's first pass (launch_cells_lean calls it after the first block kernel)
+  bool k3_split = false;          // ... and it did: K3 proper then only takes the rest
   bool planes_pending = false;      // the side stream is building the supporting planes: join before CellSearch runs
+  int k3_overlap = 0;               // 1: K3 of the cells the first block kernel certifies runs on the side stream under K2's tail.
+                                    // Measured (profiles/r02y): K2 + K3 2.18 ms against 2.23 ms in sequence, and slower when replayed
+                                    // as a graph (stream priorities are not captured) — the tail is not idle time, so off by default.
   int use_graph = 1;                // evaluations are replayed as CUDA graphs (captured per distinct launch sequence)
   struct EvalGraph { std::string key; cudaGraphExec_t exec = nullptr; int launches = 0; unsigned long long stamp = 0; };
   std::vector<EvalGraph> graphs;
@@ -50,7 +56,8 @@ struct ma_ctx {
   int kmax_base = 16;  // class every evaluation starts from
   bool capacity_hit = false;  // last evaluation failed because a cell exceeded the largest class
   int bin_target = 1;  // average Diracs per leaf bin (upper bound); ~1 per bin + rings 0..6 measured best (profiles/r01m)
-  double cg_rtol = 1e-12;
+  double cg_rtol = 1e-10;  // relative residual of the Newton solves: below what a sparse Cholesky leaves (cond * eps ~ 1e-10 on these
+                           // Hessians); 1e-12, 1e-10 and 1e-9 give the same Newton trajectories on c2 / c3 (profiles/r02w)
   int cg_maxit = 200000;
   double filter_tol = 1e-11;
   int profiling = 0, stats = 0, trace = 0;
@@ -81,11 +88,12 @@ struct ma_ctx {
   Buf xr, yr, wr, rm2s, s2rm, rm_start, blk_cnt;          // the sites in row-major bin order (ma_block.cuh)
   int bG = 1;
   double bph = 1, binv = 1, block_target = 1.0;           // block grid: bG x bG bins of side bph, ~block_target Diracs each
-  Buf hard1, hard2, hard_n;                               // cells the block kernels pass on (lists + 2 counters)
+  Buf hard1, hard2, hard3, hard_n;                               // cells the block kernels pass on (lists + 2 counters)
   Buf nbr_prev, cnt_prev;                                 // adjacency at the last accepted Newton point (quick reject of trials)
   int prev_stride = 0;
   double mesh_mass = 0.0;  // integral of the density over the mesh (the warm path's sheet count)
   bool in_newton = false;
+  int newton_sharded = 0;     // ma_ot_solve on a communicator: 1 = shard the evaluations (collectives per trial), 0 = every rank runs the whole loop
   bool seeds_global = false;  // multi-GPU: nbr_prev holds the rows of ALL tiles (gathered, or left by a warm evaluation)
   bool k2_all = false;        // the last evaluation's K2 covered all cells (warm path on a partitioned context)
   // warm path of K2 (ma_warm.cuh): cells from that adjacency + the ring-match certificate
@@ -307,9 +315,15 @@ extern "C" int ma_create(ma_ctx **out, int device) {
   }
   *out = c;
   CK(cudaSetDevice(device));
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  {
+    // the side stream carries work that only fills idle SMs (K3 under the tail of K2, the planes, the scalar reductions):
+    // lowest priority, so that blocks of the main stream's kernels are scheduled first whenever a slot frees up
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest));
+    CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, least));
+  }
   for (auto &ev : c->ev_fork) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   cudaDeviceProp prop;
@@ -335,7 +349,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
                   &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->rho_p, &c->bin_rm,
-                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->nbr_prev, &c->cnt_prev, &c->ring, &c->ring_n, &c->cstate, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard_n};
+                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->nbr_prev, &c->cnt_prev, &c->ring, &c->ring_n, &c->cstate, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard3, &c->hard_n};
     for (Buf *b : all) release(*b);
     for (int l = 0; l < AMG_MAX_LEVELS; ++l) {
       Buf *lv[] = {&c->amg.agg[l], &c->amg.cstart[l], &c->amg.code[l], &c->amg.rowptr[l], &c->amg.col[l], &c->amg.val[l],
@@ -390,7 +404,9 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "persist") c->persist = (int)value;
   else if (n == "lean") c->lean = (int)value;
   else if (n == "graph") c->use_graph = (int)value;
+  else if (n == "k3_overlap") c->k3_overlap = (int)value;
   else if (n == "warm") c->warm = (int)value;
+  else if (n == "newton_sharded") c->newton_sharded = (int)value;
   else if (n == "quick_reject") c->quick_reject = (int)value;
   else if (n == "block_target") c->block_target = std::max(0.05, value);
   else if (n == "abort_on_empty") c->probe_empty = value != 0;
@@ -431,6 +447,7 @@ extern "C" double ma_get_info(ma_ctx *c, const char *name) {
   if (n == "warm_evals") return (double)c->warm_evals;      // evaluations certified by the warm path of K2 ...
   if (n == "warm_rebuilt") return (double)c->warm_rebuilt;  // ... cells CellSearch rebuilt in them ...
   if (n == "warm_failed") return (double)c->warm_failed;    // ... and attempts that had to be redone cold
+  if (n == "cg_rtol") return c->cg_rtol;
   if (n == "cell_fallbacks") return (double)c->cell_fallbacks;  // K2 sign decisions that went to the exact stage (last evaluation)
   if (n == "cell_lo") return (double)((long long)c->N * c->part_rank / c->part_n);
   if (n == "cell_hi") return (double)((long long)c->N * (c->part_rank + 1) / c->part_n);
@@ -644,7 +661,7 @@ extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y)
     CKR(ensure(c, c->xr, (size_t)N * 8)); CKR(ensure(c, c->yr, (size_t)N * 8)); CKR(ensure(c, c->wr, (size_t)N * 8));
     CKR(ensure(c, c->rm2s, (size_t)N * 4)); CKR(ensure(c, c->s2rm, (size_t)N * 4));
     CKR(ensure(c, c->rm_start, (nbb + 1) * 4)); CKR(ensure(c, c->blk_cnt, nbb * 4)); CKR(ensure(c, c->scratch_i, (size_t)N * 4));
-    CKR(ensure(c, c->hard1, (size_t)N * 4)); CKR(ensure(c, c->hard2, (size_t)N * 4)); CKR(ensure(c, c->hard_n, 64));
+    CKR(ensure(c, c->hard1, (size_t)N * 4)); CKR(ensure(c, c->hard2, (size_t)N * 4)); CKR(ensure(c, c->hard3, (size_t)N * 4)); CKR(ensure(c, c->hard_n, 64));
     CK(cudaMemsetAsync(c->blk_cnt.p, 0, nbb * 4, c->stream));
     k_blk_count<<<cdiv(N, 256), 256, 0, c->stream>>>(c->xs.as<double>(), c->ys.as<double>(), N, c->px0, c->py0, c->binv, bG,
                                                      c->scratch_i.as<int>(), c->blk_cnt.as<int>());
@@ -933,16 +950,26 @@ template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
   CK(cudaFuncSetAttribute(k_cells_persist<MAXV, NT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int nblk = std::max(1, cdiv(ncells, NT));
   k_cells_block<-1, 2, MAXV, NT, POLY><<<nblk, NT, smb, c->stream>>>(p, nullptr, nullptr, c->hard1.as<int>(), cnt);
+  c->k3_split = false;
+  if (c->k3_early) {
+    // K3 of the cells this kernel certified starts now, on the side stream, under the tail of K2 below
+    CK(cudaEventRecord(c->ev_fork[4], c->stream));
+    CK(cudaStreamWaitEvent(c->side, c->ev_fork[4], 0));
+    CKR(c->k3_early());
+    CK(cudaEventRecord(c->ev_fork[5], c->side));
+    c->k3_split = true;
+  }
   // The later stages see a fraction of the cells (or, with graded weights, all of them: k_cells_persist then ignores the
   // list): the ~15 % the 5 x 5 block cannot certify continue from their polygon with the ring of bins around it, the
   // ~0.4 % left after that get a warp each and the block of radius 5 (one by one through CellSearch those few cells
-  // cost 0.6 ms of pure latency, profiles/r02b), CellSearch takes whatever remains.
+  // cost 0.6 ms of pure latency, profiles/r02b), CellSearch takes whatever remains.  (hard1 keeps the list of the first
+  // kernel: it is K3's second pass.)
   const int nblk2 = std::max(1, std::min(nblk, c->sm_count * 8));
   k_cells_block<2, 3, MAXV, NT, POLY><<<nblk2, NT, smb, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
-  k_cells_warp<5, POLY><<<c->sm_count * 16, 128, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, c->hard1.as<int>(), cnt + 2);
+  k_cells_warp<5, POLY><<<c->sm_count * 16, 128, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, c->hard3.as<int>(), cnt + 2);
   // CellSearch: a small grid for the leftovers of the list (a handful of cells, if any) ...
   CKR(join_planes(c));
-  k_cells_persist<MAXV, NT, POLY><<<c->sm_count * 2, NT, sm, c->stream>>>(p, 1, c->hard1.as<int>(), cnt + 2);
+  k_cells_persist<MAXV, NT, POLY><<<c->sm_count * 2, NT, sm, c->stream>>>(p, 1, c->hard3.as<int>(), cnt + 2);
   // ... and a grid sized for the whole tile that only works when the weights are graded (the regime of the Newton iterates)
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cells_persist<MAXV, NT, POLY>, NT, sm));
@@ -1036,17 +1063,24 @@ template <bool POLY> int launch_cells_kmax(ma_ctx *c, const Params &p) {
     default: return launch_cells<64, 32, POLY>(c, p);
   }
 }
-template <int MAXV, int NT, int MODE> int launch_seg(ma_ctx *c, const Params &p) {
+template <int MAXV, int NT, int MODE> int launch_seg(ma_ctx *c, const Params &p, int sel = SEG_ALL, cudaStream_t st = nullptr) {
   size_t sm = seg_smem_bytes<MAXV, NT, MODE>();
   CK(cudaFuncSetAttribute(k_seg<MAXV, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_seg<MAXV, NT, MODE><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, c->stream>>>(p);
+  k_seg<MAXV, NT, MODE><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, st ? st : c->stream>>>(p, sel, c->hard1.as<int>(), c->hard_n.as<int>());
   c->launches++;
   CK(cudaGetLastError());
   return MA_OK;
 }
 template <int MODE> int launch_seg_kmax(ma_ctx *c, const Params &p) {
   switch (c->kmax) {
-    case 16: return launch_seg<16, 128, MODE>(c, p);
+    case 16: {
+      if (!c->k3_split) return launch_seg<16, 128, MODE>(c, p);
+      // the second pass (launch_cells_lean started the first one): the cells the first block kernel left to K2's later stages
+      CKR((launch_seg<16, 128, MODE>(c, p, SEG_REST)));
+      CK(cudaStreamWaitEvent(c->stream, c->ev_fork[5], 0));
+      c->k3_split = false;
+      return MA_OK;
+    }
     case 32: return launch_seg<36, 64, MODE>(c, p);
     default: return launch_seg<64, 32, MODE>(c, p);
   }
@@ -1081,9 +1115,8 @@ int alloc_eval(ma_ctx *c) {
   const size_t slots = (size_t)(c->kmax == 16 ? 16 : (c->kmax == 32 ? 36 : 64)) * N;
   CKR(ensure(c, c->poly_x, slots * 8)); CKR(ensure(c, c->poly_y, slots * 8));
   CKR(ensure(c, c->poly_t, slots * 4)); CKR(ensure(c, c->poly_n, N * 4));
-  if (c->warm && c->prev_stride == RING_STRIDE) {
-    CKR(ensure(c, c->ring, N * RING_STRIDE * 4)); CKR(ensure(c, c->ring_n, N * 4)); CKR(ensure(c, c->cstate, N * 4));
-  }
+  CKR(ensure(c, c->cstate, N * 4));
+  if (c->warm && c->prev_stride == RING_STRIDE) { CKR(ensure(c, c->ring, N * RING_STRIDE * 4)); CKR(ensure(c, c->ring_n, N * 4)); }
   return MA_OK;
 }
 
@@ -1093,16 +1126,16 @@ template <bool POLY = false> int run_cells(ma_ctx *c, Params &p) {
   k_gather_w<<<cdiv(N, 256), 256, 0, c->stream>>>(c->w.as<double>(), c->perm.as<int>(), c->s2rm.as<int>(), N,
                                                   c->ws.as<double>(), c->wr.as<double>());
   const size_t nb = (size_t)1 << (2 * c->L);
-  k_wmax_leaf<<<cdiv((long long)nb, 256), 256, 0, c->stream>>>(c->ws.as<double>(), c->bin_start.as<int>(), c->L,
-                                                               c->wmax.as<double>());
-  if (c->L >= 5) k_wmax_top<<<1, 1024, 0, c->stream>>>(c->L, c->wmax.as<double>());
-  CKR(reduce4(c, c->ws.as<double>(), nullptr, N, c->wstat.as<double>()));  // weight range (K2's choice of pruning disk)
-  c->launches += 2 + (c->L >= 5);
-  // The supporting planes are read by CellSearch only (graded weights, or the few cells the block kernels leave over):
-  // they are built on the side stream while the block kernels run.
+  CKR(reduce4(c, c->ws.as<double>(), nullptr, N, c->wstat.as<double>()));  // weight range and maximum (the certificates' w_max)
+  c->launches += 1;
+  // The max-weight pyramid and the supporting planes are read by CellSearch's tree walk only (graded weights, or the few
+  // cells the block kernels leave over): they are built on the side stream while the block kernels run.
   const PlaneGate gate{c->wstat.as<double>(), 0.25 * c->ph * c->ph};
   CK(cudaEventRecord(c->ev_fork[0], c->stream));
   CK(cudaStreamWaitEvent(c->side, c->ev_fork[0], 0));
+  k_wmax_leaf<<<cdiv((long long)nb, 256), 256, 0, c->side>>>(c->ws.as<double>(), c->bin_start.as<int>(), c->L, c->wmax.as<double>());
+  if (c->L >= 5) k_wmax_top<<<1, 1024, 0, c->side>>>(c->L, c->wmax.as<double>());
+  c->launches += 1 + (c->L >= 5);
   CKR(moment_scan<1>(c, c->pre1.as<double>(), gate, c->side));
   {
     const size_t nnodes = (4 * nb - 1) / 3;
@@ -1210,8 +1243,16 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
         };
         zero(c->mass, 8); zero(c->fcell, 8); zero(c->touched, 8); zero(c->rowcnt, 4);
       }
-      if (seg) CKR(run_cells<true>(c, p));
-      else CKR(run_cells<false>(c, p));
+      c->k3_early = nullptr;
+      c->k3_split = false;
+      if (seg && c->kmax == 16 && c->lean && c->persist && !c->warm_now && c->k3_overlap)
+        c->k3_early = [c, &p]() -> int {
+          constexpr int SM = (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2) ? MODE : 0;
+          return launch_seg<16, 128, SM>(c, p, SEG_CERTIFIED, c->side);
+        };
+      const int rc_cells = seg ? run_cells<true>(c, p) : run_cells<false>(c, p);
+      c->k3_early = nullptr;
+      CKR(rc_cells);
       stage("K1+K2");
       // (line-search trials: once K2 has found an empty cell the point is rejected whatever the rest says,
       // optimal_transport.hpp:167 — K3 / K4 then return at once on the device-side flag, the host learns it at the one
@@ -1242,10 +1283,10 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
     if (c->use_graph && !c->profiling && !c->stats) {
       // key: every launch argument and dimension is a function of these bytes
       std::string key((const char *)&p, sizeof p);
-      const void *ptrs[] = {c->w.p, c->perm.p, c->s2rm.p, c->pre0.p, c->pre1.p, c->code_s.p, c->fs_tiles.p, c->hard1.p, c->hard2.p,
+      const void *ptrs[] = {c->w.p, c->perm.p, c->s2rm.p, c->pre0.p, c->pre1.p, c->code_s.p, c->fs_tiles.p, c->hard1.p, c->hard2.p, c->hard3.p, c->cstate.p,
                             c->hard_n.p, c->rowptr.p, c->col.p, c->val.p, c->scan_tmp.p, c->red_partial.p, c->red_partial2.p,
                             c->red_out.p, c->mom.p};
-      const long long ints[] = {c->warm_now, (long long)(size_t)c->nbr_prev.p, (long long)(size_t)c->cnt_prev.p, MODE, hess, seg, c->lean, c->persist, c->persist_waves, c->persist_min_chunk, c->L, c->sm_count,
+      const long long ints[] = {c->k3_overlap, c->warm_now, (long long)(size_t)c->nbr_prev.p, (long long)(size_t)c->cnt_prev.p, MODE, hess, seg, c->lean, c->persist, c->persist_waves, c->persist_min_chunk, c->L, c->sm_count,
                                 (long long)c->col.cap, (long long)c->val.cap, c->part_rank, c->part_n, c->abort_on_empty};
       key.append((const char *)ptrs, sizeof ptrs);
       key.append((const char *)ints, sizeof ints);
@@ -2068,8 +2109,17 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
   size_t neval = 0, niter = 0, cg_total = 0;
   struct NewtonScope {  // evaluations inside this call may take the warm path of K2
     ma_ctx *c;
-    explicit NewtonScope(ma_ctx *c_) : c(c_) { c->in_newton = true; c->warm_skip = 0; c->warm_penalty = 4; }
-    ~NewtonScope() { c->in_newton = false; }
+    int rank, n;
+    explicit NewtonScope(ma_ctx *c_) : c(c_), rank(c_->part_rank), n(c_->part_n) {
+      c->in_newton = true; c->warm_skip = 0; c->warm_penalty = 4;
+      // With a communicator the loop runs REPLICATED on every rank unless "newton_sharded" is set: after the first
+      // evaluation K2 takes the warm path (whose certificate covers all cells on every rank anyway) and most trials end at
+      // the quick empty-cell test, so what sharding saves is K3 on a few dozen accepted points (~0.1 s at 1 M Diracs) while
+      // it adds 4 small collectives per trial and the gather of gradient / Hessian per accepted point (~0.4 s on 2 GPUs,
+      // ~1 s on 8, profiles/r02v).  The solve is replicated in both variants; all ranks return the same bits.
+      if (c->comm && c->part_n > 1 && !c->newton_sharded) { c->part_rank = 0; c->part_n = 1; }
+    }
+    ~NewtonScope() { c->in_newton = false; c->part_rank = rank; c->part_n = n; invalidate_eval(c); }
   } newton_scope(c);
   CKR(ensure(c, c->nu_s, (size_t)N * 8)); CKR(ensure(c, c->x0_s, (size_t)N * 8));
   CKR(ensure(c, c->d_s, (size_t)N * 8)); CKR(ensure(c, c->g_s, (size_t)N * 8));

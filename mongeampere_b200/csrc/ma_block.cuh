@@ -83,7 +83,7 @@ MA_DEV bool block_certified(const Params &p, const CellSearch<Poly> &S, const Po
   const double br = (cbx + R < G - 1) ? p.px0 + (double)(cbx + R + 1) * p.bph - S.xi : INF;
   const double bb = (cby - R > 0) ? p.py0 + (double)(cby - R) * p.bph - S.yi : -INF;
   const double bt = (cby + R < G - 1) ? p.py0 + (double)(cby + R + 1) * p.bph - S.yi : INF;
-  const double dwg = p.wmax[0] - S.wi;  // >= 0
+  const double dwg = p.wstat[3] - S.wi;  // >= 0 (wstat[3] = the largest weight of this evaluation)
   const double slack = 1e-9 * p.bph;    // a site sits in its bin up to the rounding of the bin index
   bool ok = true;
   for (int k = 0; k < S.n; ++k) {

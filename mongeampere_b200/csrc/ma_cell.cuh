@@ -258,7 +258,7 @@ template <class Poly> struct CellSearch {
     const double pinv = 1.0 / p.ph;
     bx = min(max((int)((xi - p.px0) * pinv), 0), G - 1);
     by = min(max((int)((yi - p.py0) * pinv), 0), G - 1);
-    dw_glob = wi - p.wmax[0];
+    dw_glob = wi - p.wstat[3];  // (the global maximum weight; the pyramid p.wmax may still be under construction, it is read by the tree walk only)
     status = 0;
     phase = 0;
     if (p.abort_on_empty && *(volatile const int *)p.abort_flag) { n = 0; phase = 2; }

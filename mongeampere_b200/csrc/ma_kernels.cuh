@@ -709,6 +709,7 @@ __global__ void __launch_bounds__(NT, MA_K2B_MINBLOCKS) k_cells_block(Params p, 
       }
     }
     const bool hard = valid && !cert;
+    if (R0 < 0 && valid) p.cstate[i] = hard ? 1 : 0;  // k_seg's first pass integrates the certified cells while the later passes of K2 run
     const unsigned hm = __ballot_sync(0xffffffffu, hard);
     if (hm) {
       int b = 0;
@@ -928,12 +929,29 @@ __global__ void __launch_bounds__(128) k_cells_warp(Params p, const int *__restr
 #ifndef MA_K3_MINBLOCKS
 #define MA_K3_MINBLOCKS 5
 #endif
-template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K3_MINBLOCKS : 1)) k_seg(Params p) {
+// sel = 0: every cell of the tile.  With K2's block kernels the work is split so that it overlaps K2's tail (the passes
+// over the ~15 % of the cells the 5 x 5 block cannot certify are latency-bound and leave the GPU mostly idle):
+// sel = 1, launched on a side stream right after the first block kernel: the cells that kernel certified (cstate == 0);
+// sel = 2, after K2 is complete: the rest (list[0 .. *list_n)).  With graded weights the block kernels did nothing:
+// sel = 1 returns at once and sel = 2 takes every cell.
+enum { SEG_ALL = 0, SEG_CERTIFIED = 1, SEG_REST = 2 };
+template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K3_MINBLOCKS : 1))
+k_seg(Params p, int sel, const int *__restrict__ list, const int *__restrict__ list_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
   double *sy = sx + MAXV * NT;
   double *se = sy + MAXV * NT;  // per-edge accumulators of the Hessian's edge integrals (kantorovich mode)
-  const int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
+  int i = p.cell_lo + blockIdx.x * NT + threadIdx.x;
+  if (sel != SEG_ALL) {
+    const bool graded = weights_graded(p);
+    if (sel == SEG_CERTIFIED) {
+      if (graded || i >= p.cell_hi || p.cstate[i] != 0) return;
+    } else if (!graded) {
+      const int idx = blockIdx.x * NT + threadIdx.x;
+      if (idx >= *list_n) return;
+      i = list[idx];
+    }
+  }
   if (i >= p.cell_hi) return;
   if (p.abort_on_empty && *p.abort_flag) return;  // line-search trial already rejected by K2 (an empty cell)
   PolyRef<NT, false> P{sx + threadIdx.x, sy + threadIdx.x, nullptr};  // the tags stay in global memory

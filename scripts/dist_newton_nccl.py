@@ -32,6 +32,8 @@ dist.broadcast_object_list(ids, src=0)
 ctx = capi.Context(local)
 common.load_engine(ctx, case)
 ctx.comm_init(rank, world, ids[0])
+sharded = int(os.environ.get("NEWTON_SHARDED", "0"))
+ctx.set_option("newton_sharded", sharded)  # 1: evaluations sharded, collectives per trial; 0 (default): the loop replicated
 nu = np.full(N, ctx.total_mass / N)
 dist.barrier()
 t = time.perf_counter()
@@ -42,7 +44,7 @@ allw = [None] * world
 dist.all_gather_object(allw, w.tobytes())
 same = all(b == allw[0] for b in allw)
 if rank == 0:
-    out = dict(workload=name, scale=scale, N=N, gpus=world,
+    out = dict(workload=name, scale=scale, N=N, gpus=world, newton_sharded=sharded,
                distributed=dict(seconds=dt, rc=rc, niter=st["niter"], neval=st["neval"], cg_iters=st["cg_iters"], final_norm=st["final_norm"]),
                single_gpu=ref, max_weight_diff=float(np.abs((w - w[-1]) - (w0 - w0[-1])).max()), identical_on_all_ranks=same,
                g_diff=float(np.abs(g - g0).max() / np.abs(g0).max()), H_nnz=(int(H.nnz), int(H0.nnz)),
