@@ -118,12 +118,9 @@ template <class Poly> MA_DEV bool block_reload(const Params &p, CellSearch<Poly>
 // polygon in P is what the block of radius R0 left (a previous pass), only the bins beyond it are looked at.
 // `active` = false lanes only keep the warp's votes company.  On return S.phase == 0: polygon of S.n vertices in P,
 // certified says whether it is final; S.phase == 2: S.n == 0 and S.status tells an empty cell (0) from a capacity overflow.
+// One lock-step walk over the candidates of the bins of block R that are not in block R0 (see BlockRuns).
 template <int R0, int R, class Poly>
-MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv, bool active, bool &certified) {
-  const int G = p.bG;
-  // the Dirac's bin of the block grid (same expression as k_blk_count, so a site is in the bin it was filed under)
-  const int cbx = min(max((int)((S.xi - p.px0) * p.binv), 0), G - 1);
-  const int cby = min(max((int)((S.yi - p.py0) * p.binv), 0), G - 1);
+MA_DEV void block_walk(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv, bool active, int cbx, int cby) {
   BlockRuns<R0, R> runs;
   runs.build(p, cbx, cby, active);
   const int T = runs.total();
@@ -172,6 +169,27 @@ MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv
         MA_WARP_SYNC();
       }
     }
+  }
+}
+
+// Builds the cell of S.i from the block of radius R.  R0 < 0: from scratch (S.init() already done); R0 >= 0: the
+// polygon in P is what the block of radius R0 left (a previous pass), only the bins beyond it are looked at.
+// `active` = false lanes only keep the warp's votes company.  On return S.phase == 0: polygon of S.n vertices in P,
+// certified says whether it is final; S.phase == 2: S.n == 0 and S.status tells an empty cell (0) from a capacity overflow.
+#ifndef MA_K2B_INNER_FIRST
+#define MA_K2B_INNER_FIRST 0  // 1: the 3 x 3 block first, then the ring around it (nearest candidates first)
+#endif
+template <int R0, int R, class Poly>
+MA_DEV void block_search(const Params &p, CellSearch<Poly> &S, Poly &P, int maxv, bool active, bool &certified) {
+  const int G = p.bG;
+  // the Dirac's bin of the block grid (same expression as k_blk_count, so a site is in the bin it was filed under)
+  const int cbx = min(max((int)((S.xi - p.px0) * p.binv), 0), G - 1);
+  const int cby = min(max((int)((S.yi - p.py0) * p.binv), 0), G - 1);
+  if constexpr (MA_K2B_INNER_FIRST && R0 < 0 && R == 2) {
+    block_walk<-1, 1>(p, S, P, maxv, active, cbx, cby);
+    block_walk<1, 2>(p, S, P, maxv, active, cbx, cby);
+  } else {
+    block_walk<R0, R>(p, S, P, maxv, active, cbx, cby);
   }
   // ---- certificate ----
   if (S.phase == 0) certified = block_certified<R>(p, S, P, cbx, cby);
