@@ -43,8 +43,8 @@ METRIC = "laguerre_cell_evals_per_s"
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, one launch each) of the roofline kernels at c3 / w = 0, from the
 # ncu --set full capture named in TRAFFIC_SOURCE; bench.py cannot measure DRAM traffic itself, so the figure is only quoted
 # for exactly that workload and is refreshed with every capture under profiles/
-NCU_TRAFFIC_BYTES = (149.4e6 + 197.5e6) + (120.8e6 + 74.1e6) + (258.1e6 + 72.3e6)  # k_cells_block<2> + k_cells_block<3> + k_seg
-TRAFFIC_SOURCE = "profiles/r02b_summary.md"
+NCU_TRAFFIC_BYTES = (113.0e6 + 194.7e6) + (258.2e6 + 71.5e6)  # k_cells_block<-1,2> (first pass of K2, all cells) + k_seg
+TRAFFIC_SOURCE = "profiles/r03b_summary.md"
 UNIT = "cell-evals/s"
 
 
@@ -411,8 +411,9 @@ def main_b200(args, rank, world, local_rank):
                          "frac": (flops_local / (kern_ms * 1e-3)) / fp64_peak if kern_ms > 0 else None,
                          "traffic": NCU_TRAFFIC_BYTES if (seg and world == 1 and args.workload == "c3" and args.scale == 1.0
                                                           and args.weights == "zero") else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the K2 block kernels + k_seg, one "
-                                           "launch each, ncu --set full capture of this workload (" + TRAFFIC_SOURCE + ")",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of K2's first block kernel (all cells) + k_seg, one "
+                                           "launch each, ncu --set full capture of this workload (" + TRAFFIC_SOURCE + "); the later "
+                                           "passes of K2 (15 % of the cells) were not captured",
                          "peak_source": "DFMA probe in this run (MEASURED_PEAKS.json has no fp64 figure)",
                          "algorithmic_flops_per_launch": flops_local,
                          "flops_per_cell": flops_total / N},

@@ -18,6 +18,8 @@
 // the finest level; coarse levels see it as +1 on the diagonal of its aggregate.
 // All reductions run in a fixed order (no atomics): the solve stays bit-reproducible.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ma_kernels.cuh"
 
 namespace ma {
@@ -26,7 +28,10 @@ constexpr int AMG_MAX_LEVELS = 16;
 constexpr int AMG_DENSE_MAX = 80;    // the last level (64 rows: quadtree level 3) is solved with an explicit dense inverse;
                                      // at 256 rows the one-block Gauss-Jordan cost 6.5 ms per solve and the apply 35 us per
                                      // PCG iteration (profiles/r02n), a fifth of the Newton solve at 1 M Diracs
-constexpr int AMG_TAIL_ROWS = 4096;  // levels with at most this many rows run inside ONE block (k_amg_tail)
+#ifndef MA_AMG_TAIL_ROWS
+#define MA_AMG_TAIL_ROWS 4096
+#endif
+constexpr int AMG_TAIL_ROWS = MA_AMG_TAIL_ROWS;  // levels with at most this many rows run inside ONE block (k_amg_tail)
 constexpr int AMG_TAIL_MAX = 8;
 constexpr int AMG_ROW_CAP = 96;      // distinct columns one coarse row may have while it is merged
 
@@ -177,19 +182,27 @@ __global__ void __launch_bounds__(256) k_amg_restrict(int nc, const int *__restr
 }
 // The coarse end of the V-cycle in ONE launch.  Levels of a few thousand rows are pure launch latency as separate
 // kernels (3 per level, ~7 us each against ~1 us of work: 120 of the 280 us of a PCG iteration at 1 M rows,
-// profiles/r02n); here one block of 1024 threads walks down from the first level with <= AMG_TAIL_ROWS rows to the
-// dense level and back up, a __syncthreads between the phases.  Same arithmetic in the same order as the kernels below.
+// profiles/r02n); here one launch walks down from the first level with <= AMG_TAIL_ROWS rows to the dense level and
+// back up, a barrier between the phases.  Same arithmetic in the same order as the kernels below.
 struct AmgTail {
   int nlev;                    // lev[0] = first level of the tail ... lev[nlev - 1] = the dense level
   AmgLevel lev[AMG_TAIL_MAX];
   const double *Ainv;
 };
-__global__ void __launch_bounds__(1024) k_amg_tail(AmgTail T, double omega, double alpha) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+// One thread-block CLUSTER of AMG_TAIL_CTAS blocks (8 x 1024 threads: a row or two per thread on the largest level of the
+// tail, so a phase is about one dependent chain rowptr -> (col, val) -> gather long) with the hardware cluster barrier
+// between the phases; one block with __syncthreads measured 60 us per cycle at 1 M Diracs, a quarter of a PCG iteration
+// (profiles/r03b).  The vectors the phases hand to each other go through L2 (__ldcg / plain stores: the barrier orders
+// them at cluster scope, L1 is bypassed on the reading side); the matrices are read-only.
+constexpr int AMG_TAIL_CTAS = 8;
+__global__ void __cluster_dims__(AMG_TAIL_CTAS, 1, 1) __launch_bounds__(1024) k_amg_tail(AmgTail T, double omega, double alpha) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = (int)cluster.block_rank() * (int)blockDim.x + (int)threadIdx.x, nt = AMG_TAIL_CTAS * (int)blockDim.x;
   for (int l = 0; l + 1 < T.nlev; ++l) {
     const AmgLevel &L = T.lev[l];
     for (int i = tid; i < L.n; i += nt) {  // k_amg_down
-      const double ri = L.r[i];
+      const double ri = __ldcg(L.r + i);
       double acc = 0.0;
       const int k1 = L.rowptr[i + 1];
       for (int k = L.rowptr[i]; k < k1; k += 4) {
@@ -202,36 +215,36 @@ __global__ void __launch_bounds__(1024) k_amg_tail(AmgTail T, double omega, doub
           v[u] = in ? L.val[k + u] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc += v[u] * (L.dinv[j[u]] * L.r[j[u]]);
+        for (int u = 0; u < 4; ++u) acc += v[u] * (L.dinv[j[u]] * __ldcg(L.r + j[u]));
       }
       L.x[i] = omega * L.dinv[i] * ri;
       L.t[i] = ri - omega * acc;
     }
-    __syncthreads();
+    cluster.sync();
     const AmgLevel &C = T.lev[l + 1];
     for (int c = tid; c < C.n; c += nt) {  // k_amg_restrict
       double s = 0.0;
-      for (int i = L.cstart[c]; i < L.cstart[c + 1]; ++i) s += L.t[i];
+      for (int i = L.cstart[c]; i < L.cstart[c + 1]; ++i) s += __ldcg(L.t + i);
       C.r[c] = s;
     }
-    __syncthreads();
+    cluster.sync();
   }
-  {  // k_amg_dense_apply
+  {  // the dense level: e = Ainv r
     const AmgLevel &D = T.lev[T.nlev - 1];
     for (int i = tid; i < D.n; i += nt) {
       const double *row = T.Ainv + (size_t)i;
       double s = 0.0;
-      for (int k = 0; k < D.n; ++k) s += row[(size_t)k * D.n] * D.r[k];
+      for (int k = 0; k < D.n; ++k) s += row[(size_t)k * D.n] * __ldcg(D.r + k);
       D.x2[i] = s;
     }
-    __syncthreads();
+    cluster.sync();
   }
   for (int l = T.nlev - 2; l >= 0; --l) {  // k_amg_up<false>
     const AmgLevel &L = T.lev[l];
     const double *ec = T.lev[l + 1].x2;
     for (int i = tid; i < L.n; i += nt) {
-      const double ri = L.r[i];
-      const double xi = L.x[i] + alpha * ec[L.agg[i]];
+      const double ri = __ldcg(L.r + i);
+      const double xi = __ldcg(L.x + i) + alpha * __ldcg(ec + L.agg[i]);
       double acc = 0.0;
       const int k1 = L.rowptr[i + 1];
       for (int k = L.rowptr[i]; k < k1; k += 4) {
@@ -244,11 +257,11 @@ __global__ void __launch_bounds__(1024) k_amg_tail(AmgTail T, double omega, doub
           v[u] = in ? L.val[k + u] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc += v[u] * (L.x[j[u]] + alpha * ec[L.agg[j[u]]]);
+        for (int u = 0; u < 4; ++u) acc += v[u] * (__ldcg(L.x + j[u]) + alpha * __ldcg(ec + L.agg[j[u]]));
       }
       L.x2[i] = xi + omega * L.dinv[i] * (ri - acc);
     }
-    __syncthreads();
+    cluster.sync();
   }
 }
 

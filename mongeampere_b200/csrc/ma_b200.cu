@@ -1903,7 +1903,7 @@ int amg_vcycle(ma_ctx *c, const double *r, double *z, double *part_rz, int nbloc
     T.nlev = last - tail + 1;
     for (int l = tail; l <= last; ++l) T.lev[l - tail] = A.lev[l];
     T.Ainv = A.Ainv.as<double>();
-    k_amg_tail<<<1, 1024, 0, c->stream>>>(T, omega, alpha);
+    k_amg_tail<<<AMG_TAIL_CTAS, 1024, 0, c->stream>>>(T, omega, alpha);  // one cluster
   }
   for (int l = tail - 1; l >= 0; --l) {
     const AmgLevel &L = A.lev[l];

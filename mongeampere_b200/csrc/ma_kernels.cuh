@@ -735,6 +735,7 @@ __global__ void __launch_bounds__(NT, 4) k_cells_seed(Params p, const int *__res
   const int idx = blockIdx.x * NT + threadIdx.x;
   const int ncell = p.cell_hi - p.cell_lo;
   if ((idx & ~31) >= ncell) return;  // warp-uniform
+  if (p.abort_on_empty && *(volatile const int *)p.abort_flag) return;  // line-search trial: an empty cell has already been found
   const bool valid = idx < ncell;
   const int i = p.cell_lo + (valid ? idx : ncell - 1);
   Poly P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
@@ -797,6 +798,9 @@ template <int NT> __global__ void __launch_bounds__(NT, 4) k_cells_quick_empty(P
   const int idx = blockIdx.x * NT + threadIdx.x;
   const int ncell = p.cell_hi - p.cell_lo;
   if ((idx & ~31) >= ncell) return;  // warp-uniform
+  // one empty cell is all the caller wants to know: blocks that start after the flag went up leave at once (a rejected
+  // trial usually has thousands of empty cells, so the first wave of blocks settles it)
+  if (*(volatile const int *)(p.flags + 1)) return;
   const bool valid = idx < ncell;
   const int i = p.cell_lo + (valid ? idx : ncell - 1);
   Poly P{sx + threadIdx.x, sy + threadIdx.x, st + threadIdx.x};
