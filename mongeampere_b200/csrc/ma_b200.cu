@@ -966,7 +966,7 @@ template <int NT, bool POLY> int launch_cells_lean(ma_ctx *c, const Params &p) {
   // kernel: it is K3's second pass.)
   const int nblk2 = std::max(1, std::min(nblk, c->sm_count * 8));
   k_cells_block<2, 3, MAXV, NT, POLY><<<nblk2, NT, smb, c->stream>>>(p, c->hard1.as<int>(), cnt, c->hard2.as<int>(), cnt + 1);
-  k_cells_warp<5, POLY><<<c->sm_count * 16, 128, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, c->hard3.as<int>(), cnt + 2);
+  k_cells_warp<3, 5, POLY><<<c->sm_count * 16, 128, 0, c->stream>>>(p, c->hard2.as<int>(), cnt + 1, c->hard3.as<int>(), cnt + 2);
   // CellSearch: a small grid for the leftovers of the list (a handful of cells, if any) ...
   CKR(join_planes(c));
   k_cells_persist<MAXV, NT, POLY><<<c->sm_count * 2, NT, sm, c->stream>>>(p, 1, c->hard3.as<int>(), cnt + 2);

@@ -837,7 +837,9 @@ template <int NT> __global__ void __launch_bounds__(NT, 4) k_cells_quick_empty(P
 // certify.  Thread-per-cell kernels run them at the latency of a single lane walking 121 candidates; here the 32
 // lanes test 32 candidates of the block of radius R at once against the polygon (shared memory), the cutting ones are
 // clipped one after the other by their own lane and the survivors re-tested — the mapping of north_star (2).
-template <int R, bool POLY>
+// R0 >= 0: continues from the polygon the pass of radius R0 stored (only the bins beyond that block are looked at: the polygon
+// is tight already, so most candidates fail the disk test and few clips are left to do one after the other).
+template <int R0, int R, bool POLY>
 __global__ void __launch_bounds__(128) k_cells_warp(Params p, const int *__restrict__ in_list, const int *__restrict__ in_n,
                                                     int *__restrict__ out_list, int *__restrict__ out_n) {
   __shared__ double sx[4][16], sy[4][16];
@@ -851,11 +853,16 @@ __global__ void __launch_bounds__(128) k_cells_warp(Params p, const int *__restr
     Poly P{sx[wib], sy[wib], st[wib]};
     CellSearch<Poly> S;
     S.init(p, i, P);  // every lane writes the same box into the warp's polygon
+    if (R0 >= 0 && !block_reload(p, S, P)) {  // (every lane reloads the same polygon) nothing usable: CellSearch takes the cell
+      if (lane == 0) out_list[atomicAdd(out_n, 1)] = i;
+      __syncwarp();
+      continue;
+    }
     __syncwarp();
     const int G = p.bG;
     const int cbx = min(max((int)((S.xi - p.px0) * p.binv), 0), G - 1);
     const int cby = min(max((int)((S.yi - p.py0) * p.binv), 0), G - 1);
-    BlockRuns<-1, R> runs;
+    BlockRuns<R0, R> runs;
     runs.build(p, cbx, cby, true);
     const int T = runs.total();
     for (int t0 = 0; t0 < T && S.phase == 0; t0 += 32) {
