@@ -91,6 +91,9 @@ struct ma_ctx {
   Buf hard1, hard2, hard3, hard_n;                               // cells the block kernels pass on (lists + 2 counters)
   Buf nbr_prev, cnt_prev;                                 // adjacency at the last accepted Newton point (quick reject of trials)
   int prev_stride = 0;
+  Buf diag;                   // general mesh that IS a regular grid (either diagonal per square): the bits k_seg<VD> reads
+  bool grid_overlay = false;  // ... found by ma_set_mesh: the integrating modes then run on the grid path
+  int detect_grid = 1;
   double mesh_mass = 0.0;  // integral of the density over the mesh (the warm path's sheet count)
   bool in_newton = false;
   int newton_sharded = 0;     // ma_ot_solve on a communicator: 1 = shard the evaluations (collectives per trial), 0 = every rank runs the whole loop
@@ -349,7 +352,7 @@ extern "C" void ma_destroy(ma_ctx *c) {
                   &c->cgp0, &c->cgp1, &c->cgq, &c->part_pq, &c->part_rz, &c->part_rr, &c->scal, &c->cgflag,
                   &c->nu_s, &c->x0_s, &c->d_s, &c->g_s, &c->flush, &c->code_s, &c->pre0, &c->pre1, &c->fs_tiles,
                   &c->nodeG, &c->nodeA, &c->poly_x, &c->poly_y, &c->poly_t, &c->poly_n, &c->wstat, &c->rho_v, &c->rho_p, &c->bin_rm,
-                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->nbr_prev, &c->cnt_prev, &c->ring, &c->ring_n, &c->cstate, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard3, &c->hard_n};
+                  &c->xr, &c->yr, &c->wr, &c->rm2s, &c->s2rm, &c->rm_start, &c->blk_cnt, &c->diag, &c->nbr_prev, &c->cnt_prev, &c->ring, &c->ring_n, &c->cstate, &c->dist_buf, &c->rowptr_g, &c->col_g, &c->val_g, &c->hard1, &c->hard2, &c->hard3, &c->hard_n};
     for (Buf *b : all) release(*b);
     for (int l = 0; l < AMG_MAX_LEVELS; ++l) {
       Buf *lv[] = {&c->amg.agg[l], &c->amg.cstart[l], &c->amg.code[l], &c->amg.rowptr[l], &c->amg.col[l], &c->amg.val[l],
@@ -406,6 +409,7 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
   else if (n == "graph") c->use_graph = (int)value;
   else if (n == "k3_overlap") c->k3_overlap = (int)value;
   else if (n == "warm") c->warm = (int)value;
+  else if (n == "detect_grid") c->detect_grid = (int)value;
   else if (n == "newton_sharded") c->newton_sharded = (int)value;
   else if (n == "quick_reject") c->quick_reject = (int)value;
   else if (n == "block_target") c->block_target = std::max(0.05, value);
@@ -448,6 +452,7 @@ extern "C" double ma_get_info(ma_ctx *c, const char *name) {
   if (n == "warm_rebuilt") return (double)c->warm_rebuilt;  // ... cells CellSearch rebuilt in them ...
   if (n == "warm_failed") return (double)c->warm_failed;    // ... and attempts that had to be redone cold
   if (n == "cg_rtol") return c->cg_rtol;
+  if (n == "grid_overlay") return c->grid_overlay ? 1.0 : 0.0;  // ma_set_mesh recognised a regular grid: K3 runs on k_seg
   if (n == "cell_fallbacks") return (double)c->cell_fallbacks;  // K2 sign decisions that went to the exact stage (last evaluation)
   if (n == "cell_lo") return (double)((long long)c->N * c->part_rank / c->part_n);
   if (n == "cell_hi") return (double)((long long)c->N * (c->part_rank + 1) / c->part_n);
@@ -457,6 +462,87 @@ extern "C" double ma_get_info(ma_ctx *c, const char *name) {
 // =============================================================================================
 // mesh
 // =============================================================================================
+namespace {
+// Is this explicit triangulation a regular n x m grid whose squares are each split along one of their diagonals, with a
+// density that is continuous across the faces (the values the face functions take at a shared vertex agree)?  That is what
+// image_to_pl_function + a Delaunay triangulation give (functions.hpp:82-120; the diagonal of a square is CGAL's to choose,
+// SURVEY App. B T1).  Then: rho[i * m + j] = the vertex densities, bits = one bit per PADDED square (ma_seg.cuh).
+bool detect_regular_grid(int nV, const double *vx, const double *vy, int nF, const int *tri, const double *abc, int &n, int &m,
+                         double box[4], std::vector<double> &rho, std::vector<unsigned> &bits) {
+  double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+  for (int v = 0; v < nV; ++v) {
+    x0 = std::min(x0, vx[v]); x1 = std::max(x1, vx[v]);
+    y0 = std::min(y0, vy[v]); y1 = std::max(y1, vy[v]);
+  }
+  if (!(x1 > x0) || !(y1 > y0)) return false;
+  const double tolx = 1e-9 * (x1 - x0), toly = 1e-9 * (y1 - y0);
+  long long mcount = 0;
+  for (int v = 0; v < nV; ++v) mcount += std::fabs(vx[v] - x0) <= tolx;  // vertices of the first column
+  if (mcount < 2 || nV % mcount) return false;
+  m = (int)mcount;
+  n = nV / m;
+  if (n < 2 || (long long)nF != 2ll * (n - 1) * (m - 1)) return false;
+  const double dx = (x1 - x0) / (n - 1), dy = (y1 - y0) / (m - 1);
+  std::vector<int> vi(nV), vj(nV);
+  std::vector<char> seen((size_t)n * m, 0);
+  for (int v = 0; v < nV; ++v) {
+    const double fi = (vx[v] - x0) / dx, fj = (vy[v] - y0) / dy;
+    const long long i = std::llround(fi), j = std::llround(fj);
+    if (std::fabs(fi - (double)i) > 1e-7 || std::fabs(fj - (double)j) > 1e-7 || i < 0 || i >= n || j < 0 || j >= m) return false;
+    if (seen[(size_t)i * m + j]) return false;
+    seen[(size_t)i * m + j] = 1;
+    vi[v] = (int)i; vj[v] = (int)j;
+  }
+  rho.assign((size_t)n * m, 0.0);
+  std::vector<char> have((size_t)n * m, 0);
+  std::vector<unsigned char> sq((size_t)(n - 1) * (m - 1), 0);  // bits 0-1: halves seen, bit 2: kind, bit 3: kind known
+  double scale = 0.0;
+  for (int f = 0; f < nF; ++f) {
+    const int *t = tri + 3 * f;
+    const int i0 = std::min(vi[t[0]], std::min(vi[t[1]], vi[t[2]])), j0 = std::min(vj[t[0]], std::min(vj[t[1]], vj[t[2]]));
+    int mask = 0;
+    for (int k = 0; k < 3; ++k) {
+      const int di = vi[t[k]] - i0, dj = vj[t[k]] - j0;
+      if (di > 1 || dj > 1) return false;
+      mask |= 1 << (di + 2 * dj);  // corners 00, 10, 01, 11
+    }
+    if (i0 >= n - 1 || j0 >= m - 1) return false;
+    int kind, half;
+    switch (mask) {
+      case 0b1011: kind = 0; half = 0; break;  // 00 10 11: below the "+" diagonal
+      case 0b1101: kind = 0; half = 1; break;  // 00 01 11: above it
+      case 0b0111: kind = 1; half = 0; break;  // 00 10 01: below the "-" diagonal
+      case 0b1110: kind = 1; half = 1; break;  // 10 01 11: above it
+      default: return false;
+    }
+    unsigned char &q = sq[(size_t)i0 * (m - 1) + j0];
+    if ((q & 8) && ((q >> 2) & 1) != kind) return false;
+    if (q & (1 << half)) return false;
+    q |= (unsigned char)(8 | (kind << 2) | (1 << half));
+    for (int k = 0; k < 3; ++k) {  // continuity of the density at the shared vertices
+      const int v = t[k];
+      const double val = abc[3 * f] * vx[v] + abc[3 * f + 1] * vy[v] + abc[3 * f + 2];
+      const size_t id = (size_t)vi[v] * m + vj[v];
+      scale = std::max(scale, std::fabs(val));
+      if (!have[id]) { have[id] = 1; rho[id] = val; }
+      else if (std::fabs(val - rho[id]) > 1e-10 * std::max(scale, 1e-300)) return false;
+    }
+  }
+  for (unsigned char q : sq)
+    if ((q & 3) != 3) return false;
+  const size_t npad = (size_t)(n + 1) * (m + 1);
+  bits.assign((npad + 31) / 32, 0u);
+  for (int i = 0; i < n - 1; ++i)
+    for (int j = 0; j < m - 1; ++j)
+      if ((sq[(size_t)i * (m - 1) + j] >> 2) & 1) {
+        const size_t q = (size_t)(i + 1) * (m + 1) + (j + 1);
+        bits[q >> 5] |= 1u << (q & 31);
+      }
+  box[0] = x0; box[1] = y0; box[2] = x1; box[3] = y1;
+  return true;
+}
+}  // namespace
+
 extern "C" int ma_set_mesh(ma_ctx *c, int nV, const double *vx, const double *vy, int nF, const int *tri,
                            const double *abc) {
   NEED_CTX();
@@ -518,6 +604,28 @@ extern "C" int ma_set_mesh(ma_ctx *c, int nV, const double *vx, const double *vy
   CKR(upload(c, c->tbin_face, faces.data(), faces.size() * 4));
   CK(cudaStreamSynchronize(c->stream));
   c->mesh_mass = host_total_mass(nF, tri, vx, vy, abc);
+  // A regular grid in disguise (the triangulation of an image, whichever diagonals it has)?  Then the integrating modes run
+  // on the boundary-segment kernel; the face arrays above stay what the pieces / raster / counter paths use.
+  c->grid_overlay = false;
+  if (c->detect_grid) {
+    int n = 0, m = 0;
+    double box[4];
+    std::vector<double> rho;
+    std::vector<unsigned> bits;
+    if (detect_regular_grid(nV, vx, vy, nF, tri, abc, n, m, box, rho, bits)) {
+      c->gn = n; c->gm = m;
+      c->gx0 = box[0]; c->gy0 = box[1];
+      c->gdx = (box[2] - box[0]) / (n - 1); c->gdy = (box[3] - box[1]) / (m - 1);
+      std::vector<double> pad((size_t)(n + 2) * (m + 2));
+      for (int a = -1; a <= n; ++a)
+        for (int b = -1; b <= m; ++b)
+          pad[(size_t)(a + 1) * (m + 2) + (b + 1)] = rho[(size_t)std::min(std::max(a, 0), n - 1) * m + std::min(std::max(b, 0), m - 1)];
+      CKR(upload(c, c->rho_p, pad.data(), pad.size() * 8));
+      CKR(upload(c, c->diag, bits.data(), bits.size() * 4));
+      CK(cudaStreamSynchronize(c->stream));
+      c->grid_overlay = true;
+    }
+  }
   invalidate_eval(c);
   return MA_OK;
 }
@@ -566,6 +674,7 @@ extern "C" int ma_set_grid(ma_ctx *c, int n, int m, double x0, double y0, double
     }
   if (total_mass) *total_mass = tot;
   c->mesh_kind = MESH_GRID;
+  c->grid_overlay = false;
   c->gn = n; c->gm = m;
   c->gx0 = x0; c->gy0 = y0; c->gdx = dx; c->gdy = dy;
   c->nV = n * m;
@@ -909,6 +1018,7 @@ int fill_params(ma_ctx *c, Params &p) {
   p.abc = c->abc.as<double>();
   p.rho_v = c->rho_v.as<double>();
   p.rho_p = c->rho_p.as<double>();
+  p.diag = c->grid_overlay ? c->diag.as<unsigned>() : nullptr;
   p.gn = c->gn; p.gm = c->gm; p.gx0 = c->gx0; p.gy0 = c->gy0; p.gdx = c->gdx; p.gdy = c->gdy;
   p.vx = c->vx.as<double>(); p.vy = c->vy.as<double>(); p.tri = c->tri.as<int>();
   p.tg = c->tg; p.tinvx = c->tinvx; p.tinvy = c->tinvy;
@@ -1065,8 +1175,14 @@ template <bool POLY> int launch_cells_kmax(ma_ctx *c, const Params &p) {
 }
 template <int MAXV, int NT, int MODE> int launch_seg(ma_ctx *c, const Params &p, int sel = SEG_ALL, cudaStream_t st = nullptr) {
   size_t sm = seg_smem_bytes<MAXV, NT, MODE>();
-  CK(cudaFuncSetAttribute(k_seg<MAXV, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_seg<MAXV, NT, MODE><<<std::max(1, cdiv(p.cell_hi - p.cell_lo, NT)), NT, sm, st ? st : c->stream>>>(p, sel, c->hard1.as<int>(), c->hard_n.as<int>());
+  const int nblk = std::max(1, cdiv(p.cell_hi - p.cell_lo, NT));
+  if (p.diag) {  // an explicit triangulation recognised as a grid: either diagonal per square
+    CK(cudaFuncSetAttribute(k_seg<MAXV, NT, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_seg<MAXV, NT, MODE, true><<<nblk, NT, sm, st ? st : c->stream>>>(p, sel, c->hard1.as<int>(), c->hard_n.as<int>());
+  } else {
+    CK(cudaFuncSetAttribute(k_seg<MAXV, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_seg<MAXV, NT, MODE><<<nblk, NT, sm, st ? st : c->stream>>>(p, sel, c->hard1.as<int>(), c->hard_n.as<int>());
+  }
   c->launches++;
   CK(cudaGetLastError());
   return MA_OK;
@@ -1087,7 +1203,7 @@ template <int MODE> int launch_seg_kmax(ma_ctx *c, const Params &p) {
 }
 // the boundary-segment kernel handles grid meshes in the integrating modes
 template <int MODE> bool use_seg(const ma_ctx *c) {
-  return c->mesh_kind == MESH_GRID && c->strategy == 0 && !c->stats &&
+  return (c->mesh_kind == MESH_GRID || c->grid_overlay) && c->strategy == 0 && !c->stats &&
          (MODE == MODE_KANTOROVICH || MODE == MODE_MOMENTS1 || MODE == MODE_MOMENTS2);
 }
 

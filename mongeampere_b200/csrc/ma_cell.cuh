@@ -59,6 +59,7 @@ struct Params {
   int nF;
   const double *abc;
   const double *rho_v;  // grid mesh: density at vertex (i, j) = rho_v[i * gm + j] (L2-resident: 8 B/vertex vs 24 B/face)
+  const unsigned *diag; // grid meshes with per-square diagonals: one bit per padded square (ma_seg.cuh), else null
   const double *rho_p;  // the same padded by one replicated layer: vertex (i, j), -1 <= i <= gn, at [(i+1)*(gm+2) + j+1]
   // grid mesh
   int gn, gm;

@@ -946,7 +946,8 @@ __global__ void __launch_bounds__(128) k_cells_warp(Params p, const int *__restr
 // sel = 2, after K2 is complete: the rest (list[0 .. *list_n)).  With graded weights the block kernels did nothing:
 // sel = 1 returns at once and sel = 2 takes every cell.
 enum { SEG_ALL = 0, SEG_CERTIFIED = 1, SEG_REST = 2 };
-template <int MAXV, int NT, int MODE> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K3_MINBLOCKS : 1))
+// VD: the squares of the grid are split along either diagonal (p.diag; ma_seg.cuh) — explicit triangulations of an image.
+template <int MAXV, int NT, int MODE, bool VD = false> __global__ void __launch_bounds__(NT, (MAXV <= 16 ? MA_K3_MINBLOCKS : 1))
 k_seg(Params p, int sel, const int *__restrict__ list, const int *__restrict__ list_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sx = reinterpret_cast<double *>(smem_raw);
@@ -972,7 +973,7 @@ k_seg(Params p, int sel, const int *__restrict__ list, const int *__restrict__ l
     P.X(k) = p.poly_x[o]; P.Y(k) = p.poly_y[o];
   }
   SegAcc acc;
-  unsigned long long touched = cell_integrate_lines<MODE, NT>(p, i, P, n, acc, p.hslot + (size_t)i * p.kmax, se + threadIdx.x,
+  unsigned long long touched = cell_integrate_lines<MODE, NT, VD>(p, i, P, n, acc, p.hslot + (size_t)i * p.kmax, se + threadIdx.x,
                                                               [&](int k) { return p.poly_t[(size_t)k * p.N + i]; });
   if (MODE == MODE_KANTOROVICH) {
     p.mass[i] = acc.mass;

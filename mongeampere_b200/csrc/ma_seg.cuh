@@ -24,7 +24,7 @@
 //   g runs over {1, |u|^2} for kantorovich (mass, cost) and {1, ux, uy [, ux², uy², ux uy]} for the
 //   moments.  All line integrals are of degree <= 3 and are taken with Simpson's rule (exact).
 //
-// On a grid the three families of mesh lines (x = const, y = const, diagonals) are enumerated directly:
+// On a grid the families of mesh lines (x = const, y = const, the diagonals of either direction) are enumerated directly:
 // no polygon is clipped and no orientation predicate decides anything, so the result depends continuously
 // on the input.  One THREAD handles one cell.  SURVEY.md §7.2 "two regimes", DESIGN.md §3.
 #pragma once
@@ -142,24 +142,48 @@ MA_DEV void seg_jump_item(double cx, double cy, double bx, double by, double tau
 // and the boundary line's chord supplies the difference, exactly as for an interior mesh line.
 MA_DEV const double *seg_rv(const Params &p, int i, int j) { return p.rho_p + (size_t)(i + 1) * (p.gm + 2) + (j + 1); }
 
-// kappa of the unit mesh edge mm of line (fam, k): n.(grad rho_T1 - grad rho_T2), n the outward normal of T1
+// Variable diagonals (VD): square (i, j) of the padded grid is split along (i,j)-(i+1,j+1) ("+", bit 0 — the only kind
+// ma_set_grid makes) or along (i+1,j)-(i,j+1) ("-", bit 1): what a Delaunay triangulation of the pixel grid gives, every
+// square being co-circular.  One bit per square, i in [-1, gn-1], j in [-1, gm-1], fictitious layer "+".
+MA_DEV bool seg_diag(const Params &p, int i, int j) {
+  const size_t q = (size_t)(i + 1) * (p.gm + 1) + (j + 1);
+  return (p.diag[q >> 5] >> (q & 31)) & 1u;
+}
+
+// kappa of the unit mesh edge mm of line (fam, k): n.(grad rho_low - grad rho_high), n the direction in which the line's
+// level function grows.  Families: 0 x = k, 1 y = k, 2 "+" diagonals fx - fy = k, 3 (VD only) "-" diagonals fx + fy = k;
+// a diagonal's unit edge exists only in a square of its own kind (kappa = 0 otherwise: rho is smooth across it).
+template <bool VD>
 MA_DEV double seg_kappa(const Params &p, int fam, int k, int mm, double inv_dx, double inv_dy, double dcoef) {
   const int gs = p.gm + 2;
-  if (fam == 0) {  // vertical edge (k,mm)-(k,mm+1): left = face 0 of square (k-1,mm), right = face 1 of (k,mm)
+  if (fam == 0) {  // vertical edge (k,mm)-(k,mm+1): left = square (k-1,mm), right = square (k,mm)
     const double *rv = seg_rv(p, k, mm);
-    return ((rv[0] - rv[-gs]) - (rv[gs + 1] - rv[1])) * inv_dx;
+    const bool dl = VD && seg_diag(p, k - 1, mm), dr = VD && seg_diag(p, k, mm);
+    const double left = dl ? (rv[1] - rv[1 - gs]) : (rv[0] - rv[-gs]);
+    const double right = dr ? (rv[gs] - rv[0]) : (rv[gs + 1] - rv[1]);
+    return (left - right) * inv_dx;
   }
-  if (fam == 1) {  // horizontal edge (mm,k)-(mm+1,k): below = face 1 of square (mm,k-1), above = face 0 of (mm,k)
+  if (fam == 1) {  // horizontal edge (mm,k)-(mm+1,k): below = square (mm,k-1), above = square (mm,k)
     const double *rv = seg_rv(p, mm, k);
-    return ((rv[0] - rv[-1]) - (rv[gs + 1] - rv[gs])) * inv_dy;
+    const bool db = VD && seg_diag(p, mm, k - 1), da = VD && seg_diag(p, mm, k);
+    const double below = db ? (rv[gs] - rv[gs - 1]) : (rv[0] - rv[-1]);
+    const double above = da ? (rv[1] - rv[0]) : (rv[gs + 1] - rv[gs]);
+    return (below - above) * inv_dy;
   }
-  const double *rv = seg_rv(p, mm, mm - k);  // diagonal of square (mm, mm-k)
-  return ((rv[0] + rv[gs + 1]) - (rv[1] + rv[gs])) * dcoef;
+  if (fam == 2) {  // "+" diagonal of square (mm, mm-k)
+    if (VD && seg_diag(p, mm, mm - k)) return 0.0;
+    const double *rv = seg_rv(p, mm, mm - k);
+    return ((rv[0] + rv[gs + 1]) - (rv[1] + rv[gs])) * dcoef;
+  }
+  // "-" diagonal of square (mm, k-mm-1)
+  if (!seg_diag(p, mm, k - mm - 1)) return 0.0;
+  const double *rv = seg_rv(p, mm, k - mm - 1);
+  return ((rv[1] + rv[gs]) - (rv[0] + rv[gs + 1])) * dcoef;
 }
 
 // E: per-edge accumulator of ∫_0^1 rho(u(t)) dt, element k at E[k * ES] (shared memory column of the thread)
 // tagof(k): the tag of edge k (only the Hessian slots at the very end need it, so it need not be staged with the vertices)
-template <int MODE, int ES, class Poly, class TagOf>
+template <int MODE, int ES, bool VD = false, class Poly, class TagOf>
 MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Poly &P, int n, SegAcc &acc,
                                                double *hslot_row, double *E, TagOf tagof) {
   const double xi = p.xs[i], yi = p.ys[i];
@@ -196,7 +220,7 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
     }
   }
   // ---------------- per edge: the term of the face at its start ----------------
-  double fxmin = 1e300, fxmax = -1e300, fymin = 1e300, fymax = -1e300, fdmin = 1e300, fdmax = -1e300;
+  double fxmin = 1e300, fxmax = -1e300, fymin = 1e300, fymax = -1e300, fdmin = 1e300, fdmax = -1e300, fsmin = 1e300, fsmax = -1e300;
   {
     double Ax = P.X(0), Ay = P.Y(0);
     for (int k = 0; k < n; ++k) {
@@ -208,13 +232,26 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
       fxmin = fmin(fxmin, fAx); fxmax = fmax(fxmax, fAx);
       fymin = fmin(fymin, fAy); fymax = fmax(fymax, fAy);
       fdmin = fmin(fdmin, fAd); fdmax = fmax(fdmax, fAd);
+      const double fAs = fAx + fAy;
+      if (VD) { fsmin = fmin(fsmin, fAs); fsmax = fmax(fsmax, fAs); }
       const int si = seg_clampi((int)floor(fAx), -1, sx_hi), sj = seg_clampi((int)floor(fAy), -1, sy_hi);
-      const bool upper = (fAd - (double)(si - sj)) < 0.0;  // low side of the square's diagonal = face 1
       const double *rv = seg_rv(p, si, sj);
-      const double r00 = rv[0], r11 = rv[gs + 1], rmid = upper ? rv[1] : rv[gs];
-      const double a = (upper ? (r11 - rmid) : (rmid - r00)) * inv_dx;
-      const double b = (upper ? (rmid - r00) : (r11 - rmid)) * inv_dy;
-      const double r = r00 - a * (((double)si - ox) * p.gdx) - b * (((double)sj - oy) * p.gdy);
+      double a, b, r;
+      if (VD && seg_diag(p, si, sj)) {
+        // "-" square: low side of fx + fy = si + sj + 1 is the triangle at vertex (si, sj), high side the one at (si+1, sj+1)
+        const bool low = (fAs - (double)(si + sj + 1)) < 0.0;
+        const double r00 = rv[0], r10 = rv[gs], r01 = rv[1], r11 = rv[gs + 1];
+        a = (low ? (r10 - r00) : (r11 - r01)) * inv_dx;
+        b = (low ? (r01 - r00) : (r11 - r10)) * inv_dy;
+        r = low ? r00 - a * (((double)si - ox) * p.gdx) - b * (((double)sj - oy) * p.gdy)
+                : r11 - a * (((double)(si + 1) - ox) * p.gdx) - b * (((double)(sj + 1) - oy) * p.gdy);
+      } else {
+        const bool upper = (fAd - (double)(si - sj)) < 0.0;  // low side of the square's diagonal = face 1
+        const double r00 = rv[0], r11 = rv[gs + 1], rmid = upper ? rv[1] : rv[gs];
+        a = (upper ? (r11 - rmid) : (rmid - r00)) * inv_dx;
+        b = (upper ? (rmid - r00) : (r11 - rmid)) * inv_dy;
+        r = r00 - a * (((double)si - ox) * p.gdx) - b * (((double)sj - oy) * p.gdy);
+      }
       seg_item_cell<MODE>(Ax, Ay, Bx, By, a, b, r, hL, acc);
       if (MODE == MODE_KANTOROVICH) E[k * ES] = a * (0.5 * (Ax + Bx)) + b * (0.5 * (Ay + By)) + r;
       Ax = Bx; Ay = By;
@@ -229,13 +266,14 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
   // run-time family evens out the trip counts across a warp but costs more in selects than it saves — measured.)
   const unsigned nmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
 #pragma unroll
-  for (int fam = 0; fam < 3; ++fam) {
-    const double lo_f = fam == 0 ? fxmin : (fam == 1 ? fymin : fdmin);
-    const double hi_f = fam == 0 ? fxmax : (fam == 1 ? fymax : fdmax);
+  for (int fam = 0; fam < (VD ? 4 : 3); ++fam) {
+    const double lo_f = fam == 0 ? fxmin : (fam == 1 ? fymin : (fam == 2 ? fdmin : fsmin));
+    const double hi_f = fam == 0 ? fxmax : (fam == 1 ? fymax : (fam == 2 ? fdmax : fsmax));
     int k0 = (int)floor(lo_f) + 1, k1 = (int)floor(hi_f);
     if (fam == 0) { k0 = max(k0, 0); k1 = min(k1, sx_hi); }
     else if (fam == 1) { k0 = max(k0, 0); k1 = min(k1, sy_hi); }
-    else { k0 = max(k0, -sy_hi - 1); k1 = min(k1, sx_hi + 1); }
+    else if (fam == 2) { k0 = max(k0, -sy_hi - 1); k1 = min(k1, sx_hi + 1); }
+    else { k0 = max(k0, -1); k1 = min(k1, sx_hi + sy_hi + 1); }
     const double fscale = fam == 0 ? p.gdx : (fam == 1 ? p.gdy : ninv);  // level function -> distance
     for (int k = k0; k <= k1; ++k)
     {
@@ -243,7 +281,7 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
       // level function at vertex v (always this very expression: its sign is THE side of v)
       auto gat = [&](int v) {
         const double Qx = P.X(v) * inv_dx + ox, Qy = P.Y(v) * inv_dy + oy;
-        return (fam == 0 ? Qx : (fam == 1 ? Qy : Qx - Qy)) - lev;
+        return (fam == 0 ? Qx : (fam == 1 ? Qy : (fam == 2 ? Qx - Qy : Qx + Qy))) - lev;
       };
       // the edges with a sign change: one bit per vertex, then bit tricks (cells of more than 32 vertices, which only
       // the largest capacity class can hold, scan edge by edge)
@@ -279,12 +317,14 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
       int mlo, mhi;
       if (fam == 0) { mlo = -1; mhi = sy_hi; }
       else if (fam == 1) { mlo = -1; mhi = sx_hi; }
-      else { mlo = max(-1, k - 1); mhi = min(sx_hi, sy_hi + k); }
+      else if (fam == 2) { mlo = max(-1, k - 1); mhi = min(sx_hi, sy_hi + k); }
+      else { mlo = max(-1, k - 1 - sy_hi); mhi = min(sx_hi, k); }
       if (mhi < mlo) continue;
       double hcoef;  // h of this line (n = the direction in which the level function grows)
       if (fam == 0) hcoef = (lev - ox) * p.gdx;
       else if (fam == 1) hcoef = (lev - oy) * p.gdy;
-      else hcoef = (lev - (ox - oy)) * ninv;
+      else if (fam == 2) hcoef = (lev - (ox - oy)) * ninv;
+      else hcoef = (lev - (ox + oy)) * ninv;
       double send[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -313,8 +353,12 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
           const double ga2 = Ay * inv_dy + oy, gb2 = By * inv_dy + oy;
           if (fabs(gb2 - ga2) < fabs(fb - fa)) mm = (int)floor(tc <= 0.5 ? ga2 + tc * (gb2 - ga2) : gb2 - tau * (gb2 - ga2)) + k;
         }
+        if (fam == 3) {  // the same for a "-" diagonal: its unit edge is square (mm, k - mm - 1)
+          const double ga2 = Ay * inv_dy + oy, gb2 = By * inv_dy + oy;
+          if (fabs(gb2 - ga2) < fabs(fb - fa)) mm = k - 1 - (int)floor(tc <= 0.5 ? ga2 + tc * (gb2 - ga2) : gb2 - tau * (gb2 - ga2));
+        }
         mm = seg_clampi(mm, mlo, mhi);
-        const double kap = seg_kappa(p, fam, k, mm, inv_dx, inv_dy, dcoef);
+        const double kap = seg_kappa<VD>(p, fam, k, mm, inv_dx, inv_dy, dcoef);
         const double sgn = (ga < 0.0) ? 1.0 : -1.0;  // direction of travel across the line
         const double dB = fabs(gb) * fscale;         // n_c.B - h_c
         const double hL = dy * Ax - dx * Ay;
@@ -329,7 +373,8 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
       for (int mm = m0; mm <= m1; ++mm) {
         const double s0 = fmax(lo, (double)mm), s1 = fmin(hi, (double)(mm + 1));
         if (!(s1 > s0)) continue;
-        const double kappa = seg_kappa(p, fam, k, mm, inv_dx, inv_dy, dcoef);
+        const double kappa = seg_kappa<VD>(p, fam, k, mm, inv_dx, inv_dy, dcoef);
+        if (VD && kappa == 0.0) continue;
         double ax, ay, bx, by, len;
         if (fam == 0) {
           ax = bx = hcoef;
@@ -339,9 +384,13 @@ MA_DEV unsigned long long cell_integrate_lines(const Params &p, int i, const Pol
           ay = by = hcoef;
           ax = (s0 - ox) * p.gdx; bx = (s1 - ox) * p.gdx;
           len = (s1 - s0) * p.gdx;
-        } else {
+        } else if (fam == 2) {
           ax = (s0 - ox) * p.gdx; bx = (s1 - ox) * p.gdx;
           ay = ((s0 - lev) - oy) * p.gdy; by = ((s1 - lev) - oy) * p.gdy;
+          len = (s1 - s0) * ddiag;
+        } else {
+          ax = (s0 - ox) * p.gdx; bx = (s1 - ox) * p.gdx;
+          ay = ((lev - s0) - oy) * p.gdy; by = ((lev - s1) - oy) * p.gdy;
           len = (s1 - s0) * ddiag;
         }
         seg_item_mesh<MODE>(ax, ay, bx, by, kappa * h2 * len, acc);

@@ -48,6 +48,22 @@ def grid_triangles(n: int, m: int):
     return tri
 
 
+def grid_triangles_diag(n: int, m: int, diag):
+    """The same grid with a per-square choice of diagonal: diag[i, j] = 0 splits square (i, j) along (i,j)-(i+1,j+1) as
+    grid_triangles does, 1 along (i+1,j)-(i,j+1) — what a Delaunay triangulation of the (co-circular) pixel grid may pick,
+    SURVEY App. B T1.  Faces 2q, 2q+1 of square q = i (m-1) + j, CCW."""
+    diag = np.asarray(diag).reshape(n - 1, m - 1).astype(bool).reshape(-1)
+    tri = grid_triangles(n, m)
+    i, j = np.meshgrid(np.arange(n - 1), np.arange(m - 1), indexing="ij")
+    i = i.reshape(-1); j = j.reshape(-1)
+    v00, v10, v11, v01 = i * m + j, (i + 1) * m + j, (i + 1) * m + j + 1, i * m + j + 1
+    alt0 = np.stack([v00, v10, v01], 1).astype(np.int32)
+    alt1 = np.stack([v10, v11, v01], 1).astype(np.int32)
+    tri[0::2][diag] = alt0[diag]
+    tri[1::2][diag] = alt1[diag]
+    return tri
+
+
 def image_vertex_density(image: np.ndarray):
     """image[i, j] = CImg image(i, j) (i = column / x index, j = row index) -> rho at vertex index
     i*m + j, = image(i, m-j-1)/255 + 1e-3 (functions.hpp:102)."""

@@ -52,6 +52,20 @@ def warm_counts():
     return tuple(out)
 
 
+def pack_diag(diag):
+    """diag[i, j] in {0, 1} for the real squares (i < n-1, j < m-1): 1 = split along (i+1,j)-(i,j+1).  -> bit array over the
+    padded squares i in [-1, n-1], j in [-1, m-1] as ma_seg.cuh reads it (the fictitious layer is 0)."""
+    diag = np.asarray(diag)
+    nx, ny = diag.shape
+    pad = np.zeros((nx + 2, ny + 2), np.uint8)
+    pad[1:-1, 1:-1] = diag
+    flat = pad.reshape(-1)
+    nwords = (len(flat) + 31) // 32
+    bits = np.zeros(nwords * 32, np.uint8)
+    bits[:len(flat)] = flat
+    return np.ascontiguousarray((bits.reshape(nwords, 32).astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(1).astype(np.uint32))
+
+
 def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_target=2, nlanes=32, seg=False, seeds=None):
     """mesh: dict(kind='grid', n, m, x0, y0, x1, y1, abc) or dict(kind='mesh', vx, vy, tri, abc).
     seeds: the `seeds` entry of an earlier result for the same X (K2 then takes the warm path, ma_warm.cuh).
@@ -80,6 +94,12 @@ def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_t
     rho = np.ascontiguousarray(mesh["rho"], np.float64).reshape(-1) if mesh.get("rho") is not None else None
     if seg and mesh["kind"] == "grid":
         assert rho is not None, "the segment path reads the vertex densities"
+    dbits = None
+    if seg and mesh["kind"] == "grid" and mesh.get("diag") is not None:
+        dbits = pack_diag(mesh["diag"])
+        lib().emu_set_diag(p(dbits))
+    else:
+        lib().emu_set_diag(None)
     if seeds is not None:
         assert kmax == 16
         snbr = np.ascontiguousarray(seeds[0], np.int32); scnt = np.ascontiguousarray(seeds[1], np.int32)
@@ -91,6 +111,7 @@ def evaluate(mesh, X, w, kmax=16, maxv_piece=12, mode=0, filter_tol=1e-11, bin_t
                         p(mom), p(counters), C.byref(flags))
     assert rc == 0
     lib().emu_set_seeds(None, None)
+    lib().emu_set_diag(None)
     raw = dict(mass=mass.copy(), nbr=nbr.copy(), nbr_cnt=nbr_cnt.copy(), hslot=hslot.copy(), fcell=fcell.copy())
     g = np.zeros(N); g[perm] = mass
     momc = np.zeros((N, 6)); momc[perm] = mom.reshape(N, 6)

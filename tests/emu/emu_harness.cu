@@ -28,6 +28,8 @@ static int emu_lean[4] = {0, 0, 0, 0};
 extern "C" void emu_set_lean(int on) { emu_lean[0] = on; }
 // K2 warm path (ma_warm.cuh): seeds = adjacency of an earlier evaluation of the same points, internal order, 16 per cell;
 // emu_warm: [0] used (certified), [1] cells rebuilt in round 0, [2] in round 1, [3..5] failing cells per match
+static const unsigned *emu_diag = nullptr;  // grid meshes with per-square diagonals: one bit per padded square (ma_seg.cuh)
+extern "C" void emu_set_diag(const unsigned *bits) { emu_diag = bits; }
 static const int *emu_seed_nbr = nullptr, *emu_seed_cnt = nullptr;
 static int emu_warm[6] = {0, 0, 0, 0, 0, 0};
 extern "C" void emu_set_seeds(const int *nbr, const int *cnt) { emu_seed_nbr = nbr; emu_seed_cnt = cnt; }
@@ -102,6 +104,7 @@ extern "C" int emu_eval(int mesh_kind,
       for (int b = -1; b <= gm; ++b)
         rho_pad[(size_t)(a + 1) * (gm + 2) + (b + 1)] = rho_v[(size_t)std::min(std::max(a, 0), gn - 1) * gm + std::min(std::max(b, 0), gm - 1)];
     p.rho_p = rho_pad.data();
+    p.diag = emu_diag;
   }
   // ---- K1 on the host ----
   double bx0 = 1e300, bx1 = -1e300, by0 = 1e300, by1 = -1e300;
@@ -322,9 +325,16 @@ extern "C" int emu_eval(int mesh_kind,
         unsigned long long tch = 0;
         {  // line-major formulation (what k_seg runs)
           double E[80];
-          if (mode == MODE_KANTOROVICH) tch = cell_integrate_lines<MODE_KANTOROVICH, 1>(p, i, P, n, acc, hslot + (size_t)i * kmax, E, [&](int k) { return P.T(k); });
-          else if (mode == MODE_MOMENTS1) cell_integrate_lines<MODE_MOMENTS1, 1>(p, i, P, n, acc, nullptr, E, [&](int k) { return P.T(k); });
-          else cell_integrate_lines<MODE_MOMENTS2, 1>(p, i, P, n, acc, nullptr, E, [&](int k) { return P.T(k); });
+          auto tg = [&](int k) { return P.T(k); };
+          if (emu_diag) {
+            if (mode == MODE_KANTOROVICH) tch = cell_integrate_lines<MODE_KANTOROVICH, 1, true>(p, i, P, n, acc, hslot + (size_t)i * kmax, E, tg);
+            else if (mode == MODE_MOMENTS1) cell_integrate_lines<MODE_MOMENTS1, 1, true>(p, i, P, n, acc, nullptr, E, tg);
+            else cell_integrate_lines<MODE_MOMENTS2, 1, true>(p, i, P, n, acc, nullptr, E, tg);
+          } else {
+            if (mode == MODE_KANTOROVICH) tch = cell_integrate_lines<MODE_KANTOROVICH, 1>(p, i, P, n, acc, hslot + (size_t)i * kmax, E, tg);
+            else if (mode == MODE_MOMENTS1) cell_integrate_lines<MODE_MOMENTS1, 1>(p, i, P, n, acc, nullptr, E, tg);
+            else cell_integrate_lines<MODE_MOMENTS2, 1>(p, i, P, n, acc, nullptr, E, tg);
+          }
         }
         mass[i] = acc.mass;
         fcell[i] = acc.mass * ws[i] - acc.cost;

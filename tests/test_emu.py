@@ -378,3 +378,57 @@ def test_warm_path_gives_up_on_degenerate_lattices(emu_mod):
     used = emu_mod.warm_counts()[0]
     _same_raw(first, warm)
     assert used in (0, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 on grids whose squares are split along EITHER diagonal (what CGAL's Delaunay of the pixel grid produces)
+# ------------------------------------------------------------------------------------------------
+def _random_diagonal_case(name, scale, weights, seed, X=None):
+    case = common.make_case(name, scale, weights)
+    cfg = case["cfg"]
+    n, m = cfg["n"], cfg["m"]
+    diag = np.random.default_rng(seed).integers(0, 2, (n - 1, m - 1))
+    tri = inputs.grid_triangles_diag(n, m, diag)
+    cfg = dict(cfg, tri=tri)
+    abc = inputs.pl_coefficients(cfg["vx"], cfg["vy"], cfg["rho"], tri)
+    case = dict(case, cfg=cfg, abc=abc, emu_mesh=dict(case["emu_mesh"], abc=abc, diag=diag))
+    if X is not None:
+        case["X"] = X
+        case["N"] = len(X)
+        case["w"] = np.zeros(len(X))
+    return case
+
+
+@pytest.mark.parametrize("name,scale,weights", [("c2", 0.004, "zero"), ("c2", 0.004, "0.5"), ("c3", 0.0005, "0.3"), ("c4", 0.002, "0.2")])
+def test_segment_path_with_random_diagonals(oracle_mod, emu_mod, name, scale, weights):
+    """The oracle sees an explicit triangulation (general-mesh enumeration), the line-major K3 the grid + one bit per square."""
+    case = _random_diagonal_case(name, scale, weights, seed=5)
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(case["w"], mode=oracle_mod.MODE_PER_CELL)
+    r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], seg=True)
+    assert r["flags"] == 0
+    assert abs(r["f"] - f0) <= 1e-10 * abs(f0)
+    assert np.abs(r["g"] - g0).max() <= 1e-10 * np.abs(g0).max()
+    assert common.same_pattern(H0, r["H"])
+    assert abs(H0 - r["H"]).max() <= 1e-10 * np.abs(H0.diagonal()).max()
+    # moments through the same kernel
+    m0 = orc.moments(case["w"], 2) if hasattr(orc, "moments") else None
+    if m0 is not None:
+        rm = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], seg=True, mode=2)
+        ref = np.column_stack([m0[0], m0[1], m0[2]]) if isinstance(m0, tuple) else np.asarray(m0)
+        assert np.abs(rm["mom"] - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+def test_random_diagonals_on_pixel_aligned_lattice(oracle_mod, emu_mod):
+    """Cell edges ON grid lines and cell vertices ON grid vertices, every second square split the other way."""
+    case0 = common.make_case("c2", 0.004, "zero")
+    n = case0["cfg"]["n"]
+    k = (n - 1) // 2
+    g = -1.0 + (2.0 * np.arange(k) + 1.0) * (2.0 / (n - 1))  # Diracs at the odd grid vertices: cells = 2 x 2 blocks of squares
+    X = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    case = _random_diagonal_case("c2", 0.004, "zero", seed=9, X=X)
+    orc = common.oracle_for(oracle_mod, case)
+    f0, g0, H0 = orc.kantorovich(case["w"], mode=oracle_mod.MODE_PER_CELL)
+    r = emu_mod.evaluate(case["emu_mesh"], case["X"], case["w"], seg=True)
+    assert np.abs(r["g"] - g0).max() <= 1e-10 * np.abs(g0).max()
+    assert abs(r["f"] - f0) <= 1e-10 * abs(f0)
