@@ -84,9 +84,10 @@ def test_explicit_image_triangulation_with_random_diagonals(gpu_ctx, oracle_mod,
         assert abs(f1 - f0) <= tol * abs(f0)
         assert np.abs(g1 - g0).max() <= tol * np.abs(g0).max()
         assert common.same_pattern(H0, H1)
-        # (row-relative; a short Laguerre edge costs the ORACLE digits even at w = 0: 2.1e-10 on one row of c3 x 0.05, where
-        # the engine's two independent K3 paths — compared below at 1e-10 — agree to 2e-14)
-        assert common.hessian_rel_err(H0, H1) <= max(tol, 1e-9)
+        # (row-relative; a short Laguerre edge costs the ORACLE digits: 2.1e-10 on one row of c3 x 0.05 at w = 0 and 2.6e-8
+        # on the graded field, where the engine's two independent K3 paths — compared below at 1e-10 — agree to 1e-13 and
+        # so do their CPU emulations)
+        assert common.hessian_rel_err(H0, H1) <= (1e-9 if tol == 1e-10 else 1e-7)
         gpu_ctx.set_option("strategy", 2)  # the general-mesh kernel on the same input
         try:
             f2, g2, H2 = gpu_ctx.kantorovich(w)
