@@ -44,7 +44,10 @@ int ma_abi_version(void);   /* 2: ma_comm_*, options "lean" / "block_target" / "
  * Replaces the (T densityT, Functions densityF) pair of kantorovich.hpp:37-39 / lloyd.hpp:31-33:
  * T is given as vertices + CCW index triples (the input format of
  * include/CGAL/Triangulation_incremental_builder_2.h:25-81, tests/test_triangulation.cpp:12-34),
- * densityF as abc[3 f + (0,1,2)] with rho_f(x,y) = a x + b y + c (functions.hpp:55-80). */
+ * densityF as abc[3 f + (0,1,2)] with rho_f(x,y) = a x + b y + c (functions.hpp:55-80).
+ * A triangulation that is a regular grid with each square split along one of its diagonals (the Delaunay triangulation of
+ * an image's pixel grid) and whose face functions agree at the shared vertices is recognised: the integrating calls then
+ * run on the grid kernel (ma_get_info "grid_overlay" = 1; option "detect_grid" = 0 turns the recognition off). */
 int ma_set_mesh(ma_ctx *ctx, int nV, const double *vx, const double *vy, int nF, const int *tri,
                 const double *abc);
 /* Same, building the per-face functions from per-vertex values as MA::Linear_function's
