@@ -38,7 +38,7 @@ int ma_create(ma_ctx **out, int device);
 void ma_destroy(ma_ctx *ctx);
 const char *ma_last_error(const ma_ctx *ctx);
 /* ABI version, bumped on any signature change. */
-int ma_abi_version(void);   /* 2: ma_comm_*, options "lean" / "block_target" / "amg*" */
+int ma_abi_version(void);   /* 3: + ma_evaluate_async / ma_sync;  2: ma_comm_*, options "lean" / "block_target" / "amg*" */
 
 /* ---- source density: a triangulation with one linear function per face --------------------
  * Replaces the (T densityT, Functions densityF) pair of kantorovich.hpp:37-39 / lloyd.hpp:31-33:
@@ -148,6 +148,14 @@ int ma_cells_get(ma_ctx *ctx, int *ptr /* N+1 */, double *xy /* 2*nvertices */, 
  * device-resident state and leaves masses / Hessian on the device (internal Morton order). */
 int ma_set_weights(ma_ctx *ctx, const double *weights);
 int ma_evaluate(ma_ctx *ctx, int with_hessian);
+/* The same without waiting for the device: the evaluation is queued on the context's stream and the call returns; the next
+ * call on the context (any call; ma_sync does nothing else) waits for it, reads its scalars and, in the rare case that it
+ * needs a larger capacity class, repeats it.  For back-to-back evaluations (a parameter sweep, a benchmark loop): the
+ * host round trip between two evaluations — 30 us alone, several times that with 8 processes on one box — leaves the
+ * pipeline.  Evaluations that need the host in the middle (line-search trials, warm path, communicator, profiling) are
+ * carried out synchronously by this call as well. */
+int ma_evaluate_async(ma_ctx *ctx, int with_hessian);
+int ma_sync(ma_ctx *ctx);
 
 /* Multi-GPU: this context evaluates only the Morton tile `rank` of `nranks` of the Diracs (every cell is
  * independent once points and weights are replicated, kantorovich.hpp:87-136 writes only g[idv] and

@@ -26,7 +26,7 @@ SYMBOLS = (
     "ma_create", "ma_destroy", "ma_last_error", "ma_abi_version", "ma_set_mesh", "ma_set_mesh_pl", "ma_set_grid",
     "ma_set_image", "ma_set_points", "ma_kantorovich", "ma_get_hessian_csr", "ma_moments", "ma_lloyd",
     "ma_solve_laplacian", "ma_ot_solve", "ma_pieces_build", "ma_pieces_get", "ma_cells_build", "ma_cells_get",
-    "ma_set_weights", "ma_evaluate",
+    "ma_set_weights", "ma_evaluate", "ma_evaluate_async", "ma_sync",
     "ma_get_adjacency", "ma_set_profiling", "ma_get_timings", "ma_set_stats", "ma_get_counters", "ma_flush_l2",
     "ma_measure_fp64_peak", "ma_set_option", "ma_get_info", "ma_set_partition", "ma_timer_start", "ma_timer_stop",
     "ma_comm_unique_id", "ma_comm_init", "ma_comm_destroy", "ma_get_tile_rows", "ma_draw_laguerre_diagram",
@@ -80,6 +80,8 @@ def load_library(path: str | None = None):
     L.ma_cells_get.argtypes = [vp, vp, vp, vp]
     L.ma_set_weights.argtypes = [vp, vp]
     L.ma_evaluate.argtypes = [vp, C.c_int]
+    L.ma_evaluate_async.argtypes = [vp, C.c_int]
+    L.ma_sync.argtypes = [vp]
     L.ma_get_adjacency.argtypes = [vp, vp, vp, C.c_int]
     L.ma_set_profiling.argtypes = [vp, C.c_int]
     L.ma_get_timings.argtypes = [vp, vp]
@@ -313,6 +315,13 @@ class Context:
 
     def evaluate(self, hessian=True):
         self._ck(self.L.ma_evaluate(self.h, int(hessian)))
+
+    def evaluate_async(self, hessian=True):
+        """Queues the evaluation and returns; the next call on the context (or sync()) completes it."""
+        self._ck(self.L.ma_evaluate_async(self.h, int(hessian)))
+
+    def sync(self):
+        self._ck(self.L.ma_sync(self.h))
 
     def set_partition(self, rank, nranks):
         self._ck(self.L.ma_set_partition(self.h, rank, nranks))

@@ -43,6 +43,8 @@ struct ma_ctx {
   int k3_overlap = 0;               // 1: K3 of the cells the first block kernel certifies runs on the side stream under K2's tail.
                                     // Measured (profiles/r02y): K2 + K3 2.18 ms against 2.23 ms in sequence, and slower when replayed
                                     // as a graph (stream priorities are not captured) — the tail is not idle time, so off by default.
+  bool pending = false, pending_hess = false;  // ma_evaluate_async: an evaluation is in flight, its scalars not yet read
+  bool want_async = false;
   int use_graph = 1;                // evaluations are replayed as CUDA graphs (captured per distinct launch sequence)
   struct EvalGraph { std::string key; cudaGraphExec_t exec = nullptr; int launches = 0; unsigned long long stamp = 0; };
   std::vector<EvalGraph> graphs;
@@ -299,7 +301,7 @@ void invalidate_eval(ma_ctx *c) {
 // =============================================================================================
 // context
 // =============================================================================================
-extern "C" int ma_abi_version(void) { return 2; }
+extern "C" int ma_abi_version(void) { return 3; }
 
 extern "C" int ma_create(ma_ctx **out, int device) {
   if (!out) return MA_INVALID;
@@ -382,11 +384,16 @@ extern "C" void ma_destroy(ma_ctx *c) {
 
 extern "C" const char *ma_last_error(const ma_ctx *c) { return c ? c->err.c_str() : "null context"; }
 
+namespace { int finish_pending(ma_ctx *c); }
 #define NEED_CTX()                                                                  \
   do {                                                                              \
     if (!c) return MA_INVALID;                                                      \
     if (!c->stream) return fail(c, MA_CUDA_ERROR, "context has no CUDA device");    \
     cudaSetDevice(c->device);                                                       \
+    if (c->pending) {                                                               \
+      const int r_pending_ = finish_pending(c);                                     \
+      if (r_pending_ != MA_OK) return r_pending_;                                   \
+    }                                                                               \
   } while (0)
 
 extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
@@ -433,6 +440,7 @@ extern "C" int ma_set_option(ma_ctx *c, const char *name, double value) {
 }
 
 extern "C" double ma_get_info(ma_ctx *c, const char *name) {
+  if (c && c->stream && c->pending) { cudaSetDevice(c->device); finish_pending(c); }  // (an evaluation in flight: its scalars first)
   if (!c || !name) return -1;
   std::string n(name);
   if (n == "kmax") return c->kmax;
@@ -1460,6 +1468,12 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       if (hess) CK(cudaMemcpyAsync(&c->hs->nnz, c->rowptr.as<int>() + p.cell_hi, 4, cudaMemcpyDeviceToHost, c->stream));
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[MA_T_COUNT + 1], c->stream));
+    if (c->want_async && attempt == 0 && MODE == MODE_KANTOROVICH && !was_warm && !c->abort_on_empty && !is_dist(c) && !c->profiling && !c->stats) {
+      // ma_evaluate_async: the launches and the read-back of the scalars are queued, the host does not wait (finish_pending does)
+      c->pending = true;
+      c->pending_hess = hess;
+      return MA_OK;
+    }
     CK(cudaStreamSynchronize(c->stream));
     const int h_flags = c->hs->flags, h_nnz = c->hs->nnz;
     c->cell_fallbacks = c->hs->cell_fallbacks;
@@ -1575,6 +1589,41 @@ extern "C" int ma_set_weights(ma_ctx *c, const double *w) {
 extern "C" int ma_evaluate(ma_ctx *c, int with_hessian) {
   NEED_CTX();
   return evaluate_mode<MODE_KANTOROVICH>(c, with_hessian != 0);
+}
+
+namespace {
+// completes the evaluation ma_evaluate_async left in flight; if its flags ask for anything (a larger capacity class, a
+// Hessian that outgrew its arrays) the evaluation is simply done again synchronously
+int finish_pending(ma_ctx *c) {
+  if (!c->pending) return MA_OK;
+  c->pending = false;
+  CK(cudaStreamSynchronize(c->stream));
+  const int h_flags = c->hs->flags, h_nnz = c->hs->nnz;
+  const bool fits = !c->pending_hess || (size_t)h_nnz <= std::min<size_t>(c->col.cap / 4, c->val.cap / 8);
+  if ((h_flags & (FLAG_CELL_OVERFLOW | FLAG_PIECE_OVERFLOW | FLAG_KMAX_OVERFLOW | FLAG_STACK_OVERFLOW)) || !fits)
+    return evaluate_mode<MODE_KANTOROVICH>(c, c->pending_hess);
+  c->cell_fallbacks = c->hs->cell_fallbacks;
+  c->fval = c->hs->red[0];
+  c->mass_sum = c->hs->red[4];
+  c->mass_min = c->hs->red[6];
+  if (c->pending_hess) c->nnz = h_nnz;
+  c->aborted = false;
+  c->have_eval = true;
+  c->have_hessian = c->pending_hess;
+  return MA_OK;
+}
+}  // namespace
+
+extern "C" int ma_evaluate_async(ma_ctx *c, int with_hessian) {
+  NEED_CTX();  // (completes the previous one: its buffers are about to be reused)
+  c->want_async = true;
+  const int rc = evaluate_mode<MODE_KANTOROVICH>(c, with_hessian != 0);
+  c->want_async = false;
+  return rc;
+}
+extern "C" int ma_sync(ma_ctx *c) {
+  NEED_CTX();
+  return MA_OK;
 }
 
 extern "C" int ma_kantorovich(ma_ctx *c, const double *w, double *fval, double *g, int *nnz) {

@@ -41,7 +41,7 @@ def test_library_is_sm100a_only(libpath):
 
 def test_loads_with_ctypes_and_reports_version(libpath):
     L = capi.load_library()
-    assert L.ma_abi_version() == 2
+    assert L.ma_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device(libpath):

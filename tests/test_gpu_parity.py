@@ -395,3 +395,31 @@ def test_closed_forms_one_and_two_diracs(gpu_ctx):
     gpu_ctx.set_points(np.array([[0.5, 0.5], [0.5, 0.5], [0.2, 0.2]]))
     f, g, H = gpu_ctx.kantorovich(np.array([0.0, 0.05, 0.0]))
     assert g[0] == 0.0 and abs(g.sum() - 1.0) <= 1e-14 and H[0].nnz == 0
+
+
+def test_async_evaluation_equals_the_blocking_one(gpu_ctx):
+    """ma_evaluate_async queues the evaluation; the next call completes it.  Same numbers, and a cell that outgrows the
+    capacity class in flight is handled when the evaluation is completed (it is then repeated synchronously)."""
+    case = common.make_case("c2", 0.05, "0.3")
+    common.load_engine(gpu_ctx, case)
+    gpu_ctx.set_weights(case["w"])
+    gpu_ctx.evaluate(True)
+    ref = (gpu_ctx.info("fval"), gpu_ctx.info("mass_sum"), gpu_ctx.info("mass_min"), gpu_ctx.info("nnz"))
+    for _ in range(3):
+        gpu_ctx.evaluate_async(True)
+    gpu_ctx.sync()
+    assert (gpu_ctx.info("fval"), gpu_ctx.info("mass_sum"), gpu_ctx.info("mass_min"), gpu_ctx.info("nnz")) == ref
+    gpu_ctx.evaluate_async(True)
+    f, g, H = gpu_ctx.kantorovich(case["w"])  # any call completes the one in flight first
+    assert f == ref[0] and H.nnz == ref[3]
+    # a 40-sided cell: class 16 overflows, the completion escalates
+    t = np.linspace(0, 2 * np.pi, 40, endpoint=False)
+    X = np.vstack([[0.0, 0.0], 0.5 * np.c_[np.cos(t), np.sin(t)]])
+    gpu_ctx.set_points(X)
+    gpu_ctx.set_weights(np.zeros(len(X)))
+    gpu_ctx.evaluate_async(True)
+    gpu_ctx.sync()
+    assert gpu_ctx.info("kmax") > 16
+    gpu_ctx.evaluate(True)
+    ptr, idx = gpu_ctx.adjacency()
+    assert ptr[1] - ptr[0] == 40
