@@ -10,7 +10,11 @@
 // arithmetic line by line and is pinned only by (i) closed-form known answers
 // (tests/golden/), (ii) the invariants the reference's drivers print (area / mass
 // conservation, finite-difference gradient & Hessian), (iii) an independent SciPy/Qhull
-// lifted-hull adjacency cross-check and (iv) __float128 arbitration of near-ties.
+// lifted-hull adjacency cross-check, (iv) __float128 arbitration of near-ties and (v) independent golden vectors
+// computed in exact rational arithmetic without this file and without the engine (tests/golden/make_independent.py,
+// tests/test_independent_golden.py).  Known limit: the reference's global-coordinate radical axis
+// (predicates.hpp:46-52), restated here as it stands, loses digits on short Laguerre edges and on cells far from
+// their Dirac (up to 3e-8 row-relative in H on graded weights); tests arbitrate those cases with exact arithmetic.
 //
 // What follows the reference (paths relative to /root/reference):
 //   include/MA/kantorovich.hpp:59-141                        -> Oracle::kantorovich / piece_callback
