@@ -1754,41 +1754,56 @@ extern "C" int ma_get_adjacency(ma_ctx *c, int *ptr, int *idx, int capacity) {
 // =============================================================================================
 // moments / lloyd
 // =============================================================================================
+namespace {
+// moments of all cells in internal order (6 per cell) -> the caller's ordering, column-major like Eigen's N x 2 / N x 3
+// (lloyd.hpp:30-123); centroids = true divides the first moments by the mass (lloyd.hpp:139-143)
+__global__ void k_moments_to_caller(int N, const int *__restrict__ perm, const double *__restrict__ mom, int order, bool centroids,
+                                    double *__restrict__ out_m, double *__restrict__ out_1, double *__restrict__ out_2) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const int i = perm[k];
+  const double *o = mom + 6 * (size_t)k;
+  const double m = o[0];
+  out_m[i] = m;
+  out_1[i] = centroids ? o[1] / m : o[1];
+  out_1[(size_t)N + i] = centroids ? o[2] / m : o[2];
+  if (order == 2) { out_2[i] = o[3]; out_2[(size_t)N + i] = o[4]; out_2[2 * (size_t)N + i] = o[5]; }
+}
+
+int moments_impl(ma_ctx *c, const double *w, int order, double *masses, double *m1, double *m2, bool centroids) {
+  CKR(ma_set_weights(c, w));
+  if (order == 1) CKR(evaluate_mode<MODE_MOMENTS1>(c, false));
+  else CKR(evaluate_mode<MODE_MOMENTS2>(c, false));
+  if (is_dist(c)) CKR(dist_gather_slices(c, c->mom.p, 48));  // every rank returns the moments of ALL cells
+  const size_t N = c->N;
+  CKR(ensure(c, c->scratch_d, 6 * N * 8));
+  double *om = c->scratch_d.as<double>(), *o1 = om + N, *o2 = om + 3 * N;
+  k_moments_to_caller<<<cdiv((int)N, 256), 256, 0, c->stream>>>((int)N, c->perm.as<int>(), c->mom.as<double>(), order, centroids, om, o1, o2);
+  c->launches++;
+  CK(cudaGetLastError());
+  if (masses) CK(cudaMemcpyAsync(masses, om, N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (m1) CK(cudaMemcpyAsync(m1, o1, 2 * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (order == 2 && m2) CK(cudaMemcpyAsync(m2, o2, 3 * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MA_OK;
+}
+}  // namespace
+
 extern "C" int ma_moments(ma_ctx *c, const double *w, int order, double *masses, double *m1, double *m2) {
   NEED_CTX();
   if (order != 1 && order != 2) return fail(c, MA_INVALID, "ma_moments: order must be 1 or 2");
   if (order == 2 && !m2) return fail(c, MA_INVALID, "ma_moments: m2 is required for order 2");
   if (c->part_n > 1 && !c->comm)
     return fail(c, MA_INVALID, "ma_moments on a partitioned context needs a communicator (ma_comm_init): it returns all cells");
-  CKR(ma_set_weights(c, w));
-  if (order == 1) CKR(evaluate_mode<MODE_MOMENTS1>(c, false));
-  else CKR(evaluate_mode<MODE_MOMENTS2>(c, false));
-  if (is_dist(c)) CKR(dist_gather_slices(c, c->mom.p, 48));  // every rank returns the moments of ALL cells
-  const int N = c->N;
-  std::vector<double> h((size_t)N * 6);
-  std::vector<int> perm(N);
-  CK(cudaMemcpy(h.data(), c->mom.p, h.size() * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(perm.data(), c->perm.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
-  for (int k = 0; k < N; ++k) {
-    int i = perm[k];
-    const double *o = &h[6 * (size_t)k];
-    if (masses) masses[i] = o[0];
-    if (m1) { m1[i] = o[1]; m1[(size_t)N + i] = o[2]; }
-    if (order == 2) { m2[i] = o[3]; m2[(size_t)N + i] = o[4]; m2[2 * (size_t)N + i] = o[5]; }
-  }
-  return MA_OK;
+  return moments_impl(c, w, order, masses, m1, m2, false);
 }
 
 extern "C" int ma_lloyd(ma_ctx *c, const double *w, double *masses, double *centroids) {
   NEED_CTX();
   if (!masses || !centroids) return fail(c, MA_INVALID, "ma_lloyd: null output");
-  CKR(ma_moments(c, w, 1, masses, centroids, nullptr));
-  const int N = c->N;
-  for (int i = 0; i < N; ++i) {  // lloyd.hpp:139-143
-    centroids[i] /= masses[i];
-    centroids[(size_t)N + i] /= masses[i];
-  }
-  return MA_OK;
+  if (c->part_n > 1 && !c->comm)
+    return fail(c, MA_INVALID, "ma_lloyd on a partitioned context needs a communicator (ma_comm_init): it returns all cells");
+  return moments_impl(c, w, 1, masses, centroids, nullptr, true);  // lloyd.hpp:139-143: centroid = first moment / mass
 }
 
 // =============================================================================================
