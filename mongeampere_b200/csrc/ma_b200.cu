@@ -2311,7 +2311,13 @@ extern "C" int ma_ot_solve(ma_ctx *c, const double *nu, double *w, int have_init
       // ~1 s on 8, profiles/r02v).  The solve is replicated in both variants; all ranks return the same bits.
       if (c->comm && c->part_n > 1 && !c->newton_sharded) { c->part_rank = 0; c->part_n = 1; }
     }
-    ~NewtonScope() { c->in_newton = false; c->part_rank = rank; c->part_n = n; invalidate_eval(c); }
+    ~NewtonScope() {
+      c->in_newton = false;
+      if (c->part_n != n || c->part_rank != rank) {  // the loop ran replicated: back to this rank's tile, whose results are not the last evaluation's
+        c->part_rank = rank; c->part_n = n;
+        invalidate_eval(c);
+      }
+    }
   } newton_scope(c);
   CKR(ensure(c, c->nu_s, (size_t)N * 8)); CKR(ensure(c, c->x0_s, (size_t)N * 8));
   CKR(ensure(c, c->d_s, (size_t)N * 8)); CKR(ensure(c, c->g_s, (size_t)N * 8));
