@@ -169,5 +169,44 @@ int main(int argc, const char **argv) {
       carea += MA::voronoi_polygon_intersection(C, dt, v).area();
     printf("cross_area %.17g\ncross_cells_area_sum %.17g\n", C.area(), carea);
   }
+  // ---- the same image as an EXPLICIT triangulation (vertices + index triples, as from CGAL's Delaunay of the pixel
+  //      grid, which may pick either diagonal of a square: SURVEY App. B T1).  (a) the diagonals of make_grid: the bridge
+  //      sends it through ma_set_mesh, which recognises the grid, and kantorovich must give the same numbers;
+  //      (b) every second square split the other way: another PL function, its cells still carry its total mass. ----
+  for (int variant = 0; variant < 2; ++variant) {
+    std::vector<Point> pts((size_t)n * n);
+    std::vector<int> tr;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) pts[(size_t)i * n + j] = Point(-1 + 2.0 * i / (n - 1), -1 + 2.0 * j / (n - 1));
+    for (int i = 0; i + 1 < n; ++i)
+      for (int j = 0; j + 1 < n; ++j) {
+        const int a = i * n + j, b = (i + 1) * n + j, c = (i + 1) * n + j + 1, d = i * n + j + 1;
+        if (variant == 1 && ((i + j) & 1)) { tr.insert(tr.end(), {a, b, d}); tr.insert(tr.end(), {b, c, d}); }
+        else { tr.insert(tr.end(), {a, b, c}); tr.insert(tr.end(), {a, c, d}); }
+      }
+    T t2;
+    t2.assign(pts, tr);
+    std::map<T::Face_handle, MA::Linear_function<K>> f2;
+    double tm2 = 0;
+    for (T::Finite_faces_iterator f = t2.finite_faces_begin(); f != t2.finite_faces_end(); ++f) {
+      Point p[3];
+      double v[3];
+      for (int k = 0; k < 3; ++k) {
+        p[k] = f->vertex(k)->point();
+        const int id = t2.index(f->vertex(k)), i = id / n, j = id % n;
+        v[k] = image(i, n - j - 1) / 255.0 + 1e-3;
+      }
+      f2[f] = MA::Linear_function<K>(p[0], v[0], p[1], v[1], p[2], v[2]);
+      const double area = 0.5 * ((p[1].x() - p[0].x()) * (p[2].y() - p[0].y()) - (p[2].x() - p[0].x()) * (p[1].y() - p[0].y()));
+      tm2 += area * (v[0] + v[1] + v[2]) / 3.0;
+    }
+    VectorXd g2;
+    SparseMatrix h2;
+    const double fe = MA::kantorovich(t2, f2, X, weights, g2, h2);
+    printf(variant == 0 ? "f0_explicit %.17g\n" : "f0_alternating %.17g\n", fe);
+    printf(variant == 0 ? "sum_g0_explicit %.17g\n" : "sum_g0_alternating %.17g\n", g2.sum());
+    printf(variant == 0 ? "tm_explicit %.17g\n" : "tm_alternating %.17g\n", tm2);
+    printf(variant == 0 ? "nnz0_explicit %zu\n" : "nnz0_alternating %zu\n", h2.nonZeros());
+  }
   return 0;
 }

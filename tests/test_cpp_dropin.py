@@ -102,6 +102,14 @@ def test_cpp_dropin_matches_c_abi(gpu_ctx):
     # tests/test_voronoi_ad.cpp:60: the same with a non-convex polygon (a cross)
     assert abs(out["cross_area"][0] - (4 * 0.3 * 0.9 + 4 * 0.3 * 0.6)) <= 1e-14  # 2a*2b + 2*(b-a)*2a
     assert abs(out["cross_cells_area_sum"][0] - out["cross_area"][0]) <= 1e-12
+    # the image handed over as an explicit triangulation: the same diagonals give the same numbers (ma_set_mesh recognises
+    # the grid), alternating diagonals another PL density whose cells carry its own total mass
+    assert abs(out["f0_explicit"][0] - out["f0"][0]) <= 1e-12 * abs(out["f0"][0])
+    assert out["nnz0_explicit"][0] == out["nnz0"][0]
+    assert abs(out["sum_g0_explicit"][0] - out["tm_explicit"][0]) <= 1e-11 * tm
+    assert abs(out["tm_explicit"][0] - tm) <= 1e-12 * tm
+    assert abs(out["sum_g0_alternating"][0] - out["tm_alternating"][0]) <= 1e-11 * tm
+    assert out["nnz0_alternating"][0] == out["nnz0"][0]  # the Laguerre adjacency does not depend on the density
 
 
 def test_header_layer_host_parts():
