@@ -149,8 +149,9 @@ int ma_cells_get(ma_ctx *ctx, int *ptr /* N+1 */, double *xy /* 2*nvertices */, 
 int ma_set_weights(ma_ctx *ctx, const double *weights);
 int ma_evaluate(ma_ctx *ctx, int with_hessian);
 /* The same without waiting for the device: the evaluation is queued on the context's stream and the call returns; the next
- * call on the context (any call; ma_sync does nothing else) waits for it, reads its scalars and, in the rare case that it
- * needs a larger capacity class, repeats it.  For back-to-back evaluations (a parameter sweep, a benchmark loop): the
+ * call on the context other than ma_set_weights / ma_evaluate_async (any call; ma_sync does nothing else) waits for it,
+ * reads its scalars and, in the rare case that it needs a larger capacity class, repeats it.  A further ma_evaluate_async
+ * is queued behind the one in flight and supersedes it (the results live in the same device buffers).  For back-to-back evaluations (a parameter sweep, a benchmark loop): the
  * host round trip between two evaluations — 30 us alone, several times that with 8 processes on one box — leaves the
  * pipeline.  Evaluations that need the host in the middle (line-search trials, warm path, communicator, profiling) are
  * carried out synchronously by this call as well. */

@@ -385,6 +385,13 @@ extern "C" void ma_destroy(ma_ctx *c) {
 extern "C" const char *ma_last_error(const ma_ctx *c) { return c ? c->err.c_str() : "null context"; }
 
 namespace { int finish_pending(ma_ctx *c); }
+// (the same without completing an evaluation that is still in flight: calls that only append to the stream)
+#define NEED_CTX_NOWAIT()                                                           \
+  do {                                                                              \
+    if (!c) return MA_INVALID;                                                      \
+    if (!c->stream) return fail(c, MA_CUDA_ERROR, "context has no CUDA device");    \
+    cudaSetDevice(c->device);                                                       \
+  } while (0)
 #define NEED_CTX()                                                                  \
   do {                                                                              \
     if (!c) return MA_INVALID;                                                      \
@@ -1580,7 +1587,7 @@ extern "C" int ma_timer_stop(ma_ctx *c, float *ms) {
 }
 
 extern "C" int ma_set_weights(ma_ctx *c, const double *w) {
-  NEED_CTX();
+  NEED_CTX_NOWAIT();  // stream-ordered: an evaluation in flight has read its weights by the time this copy runs
   if (!w || c->N < 1) return fail(c, MA_INVALID, "ma_set_weights: bad arguments");
   CK(cudaMemcpyAsync(c->w.p, w, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
   return MA_OK;
@@ -1615,7 +1622,10 @@ int finish_pending(ma_ctx *c) {
 }  // namespace
 
 extern "C" int ma_evaluate_async(ma_ctx *c, int with_hessian) {
-  NEED_CTX();  // (completes the previous one: its buffers are about to be reused)
+  // An evaluation still in flight is NOT waited for: this one is queued behind it on the stream and supersedes it (same
+  // buffers, and the scalars the host finally reads are those of the last one queued) — that is what keeps the device
+  // busy from one evaluation to the next.
+  NEED_CTX_NOWAIT();
   c->want_async = true;
   const int rc = evaluate_mode<MODE_KANTOROVICH>(c, with_hessian != 0);
   c->want_async = false;
