@@ -171,24 +171,6 @@ __global__ void __launch_bounds__(RED_NT) k_reduce2_stage2(const double *__restr
 // ================================================================================================
 // K1: Morton-ordered uniform bins of the Diracs (once per point set) + per-eval max-weight pyramid
 // ================================================================================================
-__global__ void __launch_bounds__(1024) k_bbox(const double *__restrict__ x, const double *__restrict__ y, int n,
-                                                double *__restrict__ out) {
-  double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
-  for (int i = threadIdx.x; i < n; i += 1024) {
-    x0 = fmin(x0, x[i]); x1 = fmax(x1, x[i]);
-    y0 = fmin(y0, y[i]); y1 = fmax(y1, y[i]);
-  }
-  __shared__ double sh[4][32];
-  x0 = warp_min(x0); x1 = warp_max(x1); y0 = warp_min(y0); y1 = warp_max(y1);
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { sh[0][warp] = x0; sh[1][warp] = x1; sh[2][warp] = y0; sh[3][warp] = y1; }
-  __syncthreads();
-  if (warp == 0) {
-    x0 = warp_min(sh[0][lane]); x1 = warp_max(sh[1][lane]); y0 = warp_min(sh[2][lane]); y1 = warp_max(sh[3][lane]);
-    if (lane == 0) { out[0] = x0; out[1] = y0; out[2] = x1; out[3] = y1; }
-  }
-}
-
 __global__ void k_bin_count(const double *__restrict__ x, const double *__restrict__ y, int n, double px0, double py0,
                             double pinv, int G, unsigned *__restrict__ code, int *__restrict__ count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
