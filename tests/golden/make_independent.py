@@ -146,7 +146,7 @@ def qhull_edges(X, w):
     return E
 
 
-def grid_mesh(n, m):
+def grid_mesh(n, m, diag=None):
     xs = np.linspace(-1, 1, n)
     ys = np.linspace(-1, 1, m)
     vx = np.repeat(xs, m)
@@ -155,7 +155,10 @@ def grid_mesh(n, m):
     for i in range(n - 1):
         for j in range(m - 1):
             v00, v10, v11, v01 = i * m + j, (i + 1) * m + j, (i + 1) * m + j + 1, i * m + j + 1
-            tri += [[v00, v10, v11], [v00, v11, v01]]
+            if diag is not None and diag[i, j]:
+                tri += [[v00, v10, v01], [v10, v11, v01]]
+            else:
+                tri += [[v00, v10, v11], [v00, v11, v01]]
     return vx, vy, np.array(tri, np.int32)
 
 
@@ -164,6 +167,9 @@ CASES = {
     "indep_square_n40": ("square", 40, 11, 0.3),
     "indep_grid5x4_n60": ("grid5x4", 60, 12, 0.4),
     "indep_grid9_n30_w0": ("grid9", 30, 13, 0.0),
+    # the squares split along either diagonal at random (what a Delaunay triangulation of the pixel grid gives):
+    # pins the per-square-diagonal form of the boundary-integration kernel (k_seg<VD>) and ma_set_mesh's grid recognition
+    "indep_grid6x5_altdiag_n50": ("grid6x5alt", 50, 14, 0.3),
 }
 
 
@@ -178,8 +184,9 @@ def build(name):
         n = m = 0
         area = 1.0
     else:
-        n, m = (5, 4) if kind == "grid5x4" else (9, 9)
-        vx, vy, tri = grid_mesh(n, m)
+        n, m = {"grid5x4": (5, 4), "grid9": (9, 9), "grid6x5alt": (6, 5)}[kind]
+        diag = rng.integers(0, 2, (n - 1, m - 1)) if kind.endswith("alt") else None
+        vx, vy, tri = grid_mesh(n, m, diag)
         rho = 0.2 + rng.random(n * m) + np.exp(-((vx - 0.3) ** 2 + (vy + 0.2) ** 2) / 0.1)
         X = rng.uniform(-0.97, 0.97, (N, 2))
         area = 4.0
@@ -195,8 +202,9 @@ def build(name):
         ar = ((vx[b] - vx[a]) * (vy[c] - vy[a]) - (vx[c] - vx[a]) * (vy[b] - vy[a])) / 2
         tot += ar * (rho[a] + rho[b] + rho[c]) / 3
     assert abs(g.sum() - tot) < 1e-13 * tot
+    extra = dict(diag=diag) if kind != "square" and diag is not None else {}
     np.savez_compressed(os.path.join(HERE, name + ".npz"), kind=kind, n=n, m=m, vx=vx, vy=vy, tri=tri, rho=rho, X=X, w=w,
-                        f=f, g=g, H=H, npieces=npieces)
+                        f=f, g=g, H=H, npieces=npieces, **extra)
     print(name, "N", N, "pieces", npieces, "nnz", int((H != 0).sum()), "f", f)
 
 

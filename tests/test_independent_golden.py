@@ -12,7 +12,7 @@ import scipy.sparse as sp
 from mongeampere_b200 import inputs
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-NAMES = ["indep_square_n40", "indep_grid5x4_n60", "indep_grid9_n30_w0"]
+NAMES = ["indep_square_n40", "indep_grid5x4_n60", "indep_grid9_n30_w0", "indep_grid6x5_altdiag_n50"]
 
 
 def load(name):
@@ -46,12 +46,14 @@ def test_oracle_matches_independent_vectors(oracle_mod, name):
 def test_emulated_kernels_match_independent_vectors(emu_mod, name):
     z, abc = load(name)
     grid = str(z["kind"]) != "square"
-    mesh = (dict(kind="grid", n=int(z["n"]), m=int(z["m"]), abc=abc, rho=z["rho"]) if grid
-            else dict(kind="mesh", vx=z["vx"], vy=z["vy"], tri=z["tri"], abc=abc))
+    alt = "diag" in z.files  # squares split along either diagonal: explicit mesh for the piece kernel, grid + bits for k_seg
+    gmesh = dict(kind="grid", n=int(z["n"]), m=int(z["m"]), abc=abc, rho=z["rho"], diag=z["diag"] if alt else None)
+    emesh = dict(kind="mesh", vx=z["vx"], vy=z["vy"], tri=z["tri"], abc=abc)
     for lean in (False, True):
         emu_mod.set_lean(lean)
         try:
             for seg in ((False, True) if grid else (False,)):
+                mesh = gmesh if grid and (seg or not alt) else emesh
                 r = emu_mod.evaluate(mesh, z["X"], z["w"], seg=seg, maxv_piece=24)
                 assert r["flags"] == 0
                 check(z, r["f"], r["g"], r["H"])
@@ -66,6 +68,10 @@ def test_engine_matches_independent_vectors(gpu_ctx, name):
     if str(z["kind"]) == "square":
         gpu_ctx.set_mesh(z["vx"], z["vy"], z["tri"], abc)
         variants = [0]
+    elif "diag" in z.files:  # an explicit triangulation that ma_set_mesh recognises as a grid (either diagonal per square)
+        gpu_ctx.set_mesh(z["vx"], z["vy"], z["tri"], abc)
+        assert gpu_ctx.info("grid_overlay") == 1
+        variants = [0, 2]  # k_seg with the diagonal bits, and the general-mesh piece kernel
     else:
         gpu_ctx.set_grid(int(z["n"]), int(z["m"]), z["rho"])
         variants = [0, 2]  # boundary-integration K3 and piece-clipping K3
