@@ -1099,6 +1099,8 @@ template <int KMAX, int MAXV, int MODE> __global__ void __launch_bounds__(PIECES
 // loads into shared memory (row stride KMAX + 1: conflict-free column access), each lane then sorts
 // its row and the sorted rows are staged in shared memory again so that the warp writes the whole
 // contiguous range [rowptr[first row], rowptr[last row + 1]) with coalesced stores.
+// (Fetching only the slots a row uses — lanes of the unused ones sit the load out, a third less DRAM traffic — was
+// measured: 0.122 ms against 0.108 ms, the shuffle + predicate per element costs more than the sectors save.)
 template <int KMAX> constexpr int csr_wpb() { return KMAX <= 16 ? 4 : (KMAX <= 32 ? 2 : 1); }  // warps per block (48 KB of static shared memory)
 template <int KMAX>
 __global__ void __launch_bounds__(csr_wpb<KMAX>() * 32) k_csr_fill(int row_lo, int N, const int *__restrict__ nbr, const double *__restrict__ hslot,
