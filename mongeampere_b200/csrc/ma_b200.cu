@@ -736,6 +736,9 @@ extern "C" int ma_set_points(ma_ctx *c, int N, const double *x, const double *y)
   if (N < 1 || !x || !y) return fail(c, MA_INVALID, "ma_set_points: bad arguments");
   c->N = N;
   invalidate_eval(c);
+  c->prev_stride = 0;  // the saved adjacency (seeds of the warm path / quick test) belongs to the previous point set
+  c->seeds_global = false;
+  c->warm_skip = 0;
   CKR(upload(c, c->x, x, (size_t)N * 8));
   CKR(upload(c, c->y, y, (size_t)N * 8));
   CKR(ensure(c, c->red_out, 16 * sizeof(double)));
