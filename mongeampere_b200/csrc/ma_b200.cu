@@ -48,6 +48,7 @@ struct ma_ctx {
   int use_graph = 1;                // evaluations are replayed as CUDA graphs (captured per distinct launch sequence)
   struct EvalGraph { std::string key; cudaGraphExec_t exec = nullptr; int launches = 0; unsigned long long stamp = 0; };
   std::vector<EvalGraph> graphs;
+  std::string graph_candidate;      // key of the last configuration that ran without a graph
   unsigned long long graph_clock = 0;
   cudaEvent_t ev_chunk[8] = {};
   std::string err;
@@ -1435,7 +1436,13 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
       ma_ctx::EvalGraph *g = nullptr;
       for (auto &e : c->graphs)
         if (e.key == key) g = &e;
-      if (!g) {
+      if (!g && key != c->graph_candidate) {
+        // a configuration seen for the first time runs directly; it is captured when it comes back (Lloyd iterations move
+        // the points — and with them the bins' origin, part of the key — every time: capturing + instantiating a graph
+        // that is launched once costs more than the launches it saves)
+        c->graph_candidate = key;
+        CKR(enqueue());
+      } else if (!g) {
         const long long l0 = c->launches;
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
         const int rc_q = enqueue();
@@ -1459,9 +1466,11 @@ template <int MODE> int evaluate_mode(ma_ctx *c, bool with_hessian) {
         c->launches = l0;
         g = &c->graphs.back();
       }
-      g->stamp = ++c->graph_clock;
-      CK(cudaGraphLaunch(g->exec, c->stream));
-      c->launches += g->launches;
+      if (g) {
+        g->stamp = ++c->graph_clock;
+        CK(cudaGraphLaunch(g->exec, c->stream));
+        c->launches += g->launches;
+      }
     } else {
       CKR(enqueue());
     }
